@@ -1,0 +1,167 @@
+"""CPU oracle for the KalmanODE hot path -- TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of ``oracle/kalman_oracle.c`` (a plain-C restatement of the reference's
+``rodeo/eigen/KalmanTV.h`` + ``rodeo/eigen/KalmanTVODE.h`` arithmetic driven in the call
+order of ``rodeo/cython/KalmanODE.pyx``).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+the CPU-baseline legs of ``bench.py`` may import this package; the product package
+``rodeo_legacy_b200`` never does.
+
+Parity pin: checked against golden vectors generated from the reference's own pure-Python
+path (``tests/golden/make_golden.py``), see ``tests/test_oracle_golden.py``.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+ODE_IDS = {"chkrebtii": 0, "fitz": 1, "lorenz63": 2, "mseir": 3}
+MODE_MV, MODE_SIM, MODE_BOTH = 1, 2, 3
+INTERROGATE = {"probde": 0, "schobert": 1, "chkrebtii": 2}
+
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+def build(force=False):
+    """Compile liboracle.so with gcc (idempotent)."""
+    src = os.path.join(_HERE, "kalman_oracle.c")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+        return _LIB_PATH
+    subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.oracle_solve.restype = ctypes.c_int
+        _lib.oracle_solve_batch.restype = ctypes.c_int
+        _lib.oracle_max_threads.restype = ctypes.c_int
+        _lib.oracle_loglik.restype = ctypes.c_double
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _f(a):
+    """column-major float64 copy (what the C side expects for matrices)."""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+class Problem:
+    """The shared part of a batch of solves: prior (Q, c, R), W, grid and RHS name."""
+
+    def __init__(self, ode, W, tmin, tmax, n_eval, wgt_state, mu_state, var_state,
+                 interrogate="probde"):
+        self.ode = ODE_IDS[ode]
+        self.interrogate = INTERROGATE[interrogate]
+        self.W = _f(W)
+        self.m, self.n = self.W.shape
+        self.tmin, self.tmax, self.N = float(tmin), float(tmax), int(n_eval)
+        self.Q, self.R = _f(wgt_state), _f(var_state)
+        self.c = np.ascontiguousarray(mu_state, dtype=np.float64)
+        assert self.Q.shape == (self.n, self.n) and self.R.shape == (self.n, self.n)
+
+
+def solve(prob, x0, theta=None, z=None, mode=MODE_MV, return_hist=False):
+    """One solve.  z is (n, N) as the reference's z_state.  Returns dict."""
+    n, N = prob.n, prob.N
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    theta = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    zf = None if z is None else _f(z)
+    if (mode & MODE_SIM or prob.interrogate == 2) and zf is None:
+        raise ValueError("z required")
+    x = np.zeros((N + 1, n)) if mode & MODE_SIM else None
+    mu = np.zeros((N + 1, n)) if mode & MODE_MV else None
+    var = np.zeros((N + 1, n, n)) if mode & MODE_MV else None
+    hist = np.zeros((N + 1) * (2 * n + 2 * n * n)) if return_hist else None
+    st = lib().oracle_solve(
+        ctypes.c_int(prob.ode), ctypes.c_int(prob.interrogate), ctypes.c_int(n),
+        ctypes.c_int(prob.m), ctypes.c_int(N), ctypes.c_double(prob.tmin),
+        ctypes.c_double(prob.tmax), _p(prob.W), _p(prob.Q), _p(prob.c), _p(prob.R),
+        _p(x0), _p(theta), _p(zf), ctypes.c_int(mode), _p(x), _p(mu), _p(var), _p(hist))
+    out = {"status": st, "x": x, "mu": mu, "var": var}
+    if return_hist:
+        T = N + 1
+        o = 0
+        out["mu_pred"] = hist[o:o + T * n].reshape(T, n); o += T * n
+        # stored column-major per step: [t][j][i] = Sigma(i, j)
+        out["var_pred"] = hist[o:o + T * n * n].reshape(T, n, n); o += T * n * n
+        out["mu_filt"] = hist[o:o + T * n].reshape(T, n); o += T * n
+        out["var_filt"] = hist[o:o + T * n * n].reshape(T, n, n)
+    return out
+
+
+def solve_batch(prob, x0, theta=None, z=None, mode=MODE_MV, nthreads=0):
+    """Batch of solves, OpenMP over systems.  x0 (B,n); theta (B,k); z (n,N) or (B,n,N)."""
+    n, N = prob.n, prob.N
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    B = x0.shape[0]
+    n_theta = 0
+    if theta is not None:
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        n_theta = theta.shape[1]
+    z_stride = 0
+    if z is not None:
+        z = np.asarray(z, dtype=np.float64)
+        if z.ndim == 3:
+            z = np.ascontiguousarray(np.transpose(z, (0, 2, 1)))  # (B, N, n): column-major per system
+            z_stride = n * N
+        else:
+            z = _f(z)
+    x = np.zeros((B, N + 1, n)) if mode & MODE_SIM else None
+    mu = np.zeros((B, N + 1, n)) if mode & MODE_MV else None
+    var = np.zeros((B, N + 1, n, n)) if mode & MODE_MV else None
+    status = np.zeros(B, dtype=np.int32)
+    lib().oracle_solve_batch(
+        ctypes.c_int(prob.ode), ctypes.c_int(prob.interrogate), ctypes.c_int(n),
+        ctypes.c_int(prob.m), ctypes.c_int(N), ctypes.c_double(prob.tmin),
+        ctypes.c_double(prob.tmax), _p(prob.W), _p(prob.Q), _p(prob.c), _p(prob.R),
+        ctypes.c_long(B), _p(x0), _p(theta), ctypes.c_int(n_theta), _p(z),
+        ctypes.c_long(z_stride), ctypes.c_int(mode), _p(x), _p(mu), _p(var),
+        status.ctypes.data_as(_ip), ctypes.c_int(nthreads))
+    return {"status": status, "x": x, "mu": mu, "var": var}
+
+
+def max_threads():
+    return lib().oracle_max_threads()
+
+
+def ode_eval(ode, X, t, theta):
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    m = lib().oracle_ode_n_meas(ctypes.c_int(ODE_IDS[ode]))
+    out = np.zeros(m)
+    lib().oracle_ode_eval(ctypes.c_int(ODE_IDS[ode]), _p(X), ctypes.c_int(len(X)),
+                          ctypes.c_double(t), _p(th), _p(out))
+    return out
+
+
+def thinning_index(data_t, ode_t):
+    data_t = np.ascontiguousarray(data_t, dtype=np.float64)
+    ode_t = np.ascontiguousarray(ode_t, dtype=np.float64)
+    ind = np.zeros(len(data_t), dtype=np.int32)
+    lib().oracle_thinning_index(_p(data_t), ctypes.c_int(len(data_t)), _p(ode_t),
+                                ctypes.c_int(len(ode_t)), ind.ctypes.data_as(_ip))
+    return ind
+
+
+def loglik(X, ind, state_ind, Y, gamma):
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    ind = np.ascontiguousarray(ind, dtype=np.int32)
+    state_ind = np.ascontiguousarray(state_ind, dtype=np.int32)
+    return lib().oracle_loglik(_p(X), ctypes.c_int(X.shape[1]), ind.ctypes.data_as(_ip),
+                               ctypes.c_int(len(ind)), state_ind.ctypes.data_as(_ip),
+                               ctypes.c_int(len(state_ind)), _p(Y), ctypes.c_double(gamma))

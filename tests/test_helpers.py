@@ -1,0 +1,80 @@
+"""Host-side prior helpers against values produced by the reference's own helpers
+(tests/golden/helpers.npz, made by tests/golden/make_golden.py)."""
+import numpy as np
+
+from rodeo_legacy_b200 import ibm_init, car_init, indep_init, zero_pad, rand_mat
+from rodeo_legacy_b200.utils import norm_sim, solveV, mvncond
+from tests.common import load_golden
+
+TOL = dict(rtol=1e-13, atol=0)
+
+
+def test_ibm_init_matches_reference():
+    g = load_golden("helpers")
+    ib = ibm_init(0.1, [3, 4], [0.1, 0.7])
+    np.testing.assert_allclose(ib["wgt_state"][0], g["ibm_wgt0"], **TOL)
+    np.testing.assert_allclose(ib["var_state"][0], g["ibm_var0"], **TOL)
+    np.testing.assert_allclose(ib["wgt_state"][1], g["ibm_wgt1"], **TOL)
+    np.testing.assert_allclose(ib["var_state"][1], g["ibm_var1"], **TOL)
+    assert ib["mu_state"].shape == (7,) and not ib["mu_state"].any()
+    one = ibm_init(0.05, [4], [0.5])
+    np.testing.assert_allclose(one["wgt_state"], g["ibm_single_wgt"], **TOL)
+    np.testing.assert_allclose(one["var_state"], g["ibm_single_var"], **TOL)
+    # SURVEY appendix A check value: p=3, dt=0.1, sigma=0.1 -> Q[0,0]
+    np.testing.assert_allclose(ib["var_state"][0][0, 0], 3.96825397e-12, rtol=1e-8)
+
+
+def test_indep_init_and_zero_pad():
+    g = load_golden("helpers")
+    k = indep_init(ibm_init(0.1, [3, 4], [0.1, 0.7]), [3, 4])
+    np.testing.assert_allclose(k["wgt_state"], g["indep_wgt"], **TOL)
+    np.testing.assert_allclose(k["var_state"], g["indep_var"], **TOL)
+    assert k["wgt_state"].flags.f_contiguous
+    v = zero_pad(np.array([1.0, 2, 3, 4, 5]), [1, 2], [3, 5])
+    np.testing.assert_array_equal(v, g["zero_pad_vec"])
+    m = zero_pad(np.array([[0.0, 1, 0, 0, 0], [0, 0, 0, 0, 1]]), [1, 2], [3, 5])
+    np.testing.assert_array_equal(m, g["zero_pad_mat"])
+    # single-variable dict passes through indep_init too
+    one = indep_init(ibm_init(0.05, [4], [0.5]), [4])
+    np.testing.assert_allclose(one["wgt_state"], g["ibm_single_wgt"], **TOL)
+
+
+def test_car_init_matches_reference():
+    g = load_golden("helpers")
+    c = car_init(0.01, [4], [1.3], [0.5])
+    np.testing.assert_allclose(c["wgt_state"], g["car_wgt"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(c["var_state"], g["car_var"], rtol=1e-9, atol=1e-20)
+    lg = load_golden("lorenz_car_n600")
+    np.random.seed(7)
+    X0 = np.column_stack([[-12, -5, 38], [70, 125, -124 / 3]])
+    init, x0 = car_init(2.4 / 600, [3, 3, 3], np.array([1.3] * 3), np.array([0.5] * 3), X0)
+    np.testing.assert_allclose(init["wgt_state"][0], lg["car_wgt"], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(init["var_state"][0], lg["car_var"], rtol=1e-9, atol=1e-20)
+    # same seed, same draw order -> same conditional initial draw
+    np.testing.assert_allclose(x0, lg["x0"], rtol=1e-9, atol=1e-12)
+
+
+def test_rand_mat_shape_and_quirk():
+    np.random.seed(0)
+    z = rand_mat(10, 4)
+    assert z.shape == (4, 10) and z.flags.f_contiguous
+    np.random.seed(0)
+    np.testing.assert_array_equal(z, np.random.randn(4, 10))
+    sq = rand_mat(4, 4)                    # p == n: V V^T (reference quirk 8)
+    assert np.all(np.linalg.eigvalsh(sq) > 0)
+
+
+def test_small_linear_helpers():
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((5, 5))
+    V = A @ A.T + 5 * np.eye(5)
+    B = rng.standard_normal((5, 3))
+    np.testing.assert_allclose(V @ solveV(V, B), B, rtol=1e-12, atol=1e-12)
+    z = rng.standard_normal(5)
+    mu = rng.standard_normal(5)
+    np.testing.assert_allclose(norm_sim(z, mu, V), np.linalg.cholesky(V) @ z + mu, rtol=1e-13)
+    icond = np.array([True, True, False, False, False])
+    Ac, b, Vc = mvncond(mu, V, icond)
+    np.testing.assert_allclose(Ac, V[2:, :2] @ np.linalg.inv(V[:2, :2]), rtol=1e-10)
+    np.testing.assert_allclose(Vc, V[2:, 2:] - Ac @ V[:2, 2:], rtol=1e-12)
+    np.testing.assert_allclose(b, mu[2:] - Ac @ mu[:2], rtol=1e-12)
