@@ -1,0 +1,172 @@
+/*
+ * rodeo_cuda.h -- C ABI of the B200-native batched KalmanODE backend.
+ *
+ * This is the drop-in boundary for the ONE hot path of mlysy/rodeo-legacy: a batch of
+ * independent KalmanODE solves (forward time-varying Kalman filter + backward
+ * smoother).  Plain pointers and sizes only; no torch / C++ types.  A binding in the
+ * reference (Cython `cdef extern`, ctypes, cffi) needs nothing but this header and
+ * librodeo_cuda.so -- see INTEGRATION.md.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference):
+ *
+ *   rodeo_cuda_problem_create   KalmanODE.__cinit__            rodeo/cython/KalmanODE.pyx:170-218
+ *                               KalmanTVODE::KalmanTVODE       rodeo/eigen/KalmanTVODE.h:104-139
+ *                               (cdef extern at rodeo/eigen/KalmanTVODE.pxd:1-14)
+ *   rodeo_cuda_problem_set      the wgt_meas/mu_state/wgt_state/var_state property setters
+ *                                                              rodeo/cython/KalmanODE.pyx:220-270
+ *                               and the per-call `W` override  rodeo/cython/KalmanODE.pyx:441-442
+ *   rodeo_cuda_solve            _solve_filter + solve_mv / solve_sim / solve, batched
+ *                                                              rodeo/cython/KalmanODE.pyx:280-463
+ *                               predict/forecast_probde/update/smooth_update
+ *                                                              rodeo/eigen/KalmanTVODE.h:149-183, 273-296, 333-341
+ *                               with the arithmetic of         rodeo/eigen/KalmanTV.h:280-294, 324-357,
+ *                                                              447-467, 503-533, 619-628
+ *   rodeo_cuda_solve_host       the same, with HOST buffers (what a NumPy caller of the
+ *                               reference passes): H2D / D2H copies are done inside.
+ *   rodeo_cuda_loglik           kalman_nlpost's solve -> thinning -> loglike chain
+ *                                                              examples/inference.py:54-56, 66-94
+ *
+ * Conventions
+ *   - float64 only (as the reference, README.md:15-16).
+ *   - Prior / measurement matrices are COLUMN-MAJOR (Fortran order), exactly what the
+ *     reference's constructor receives: wgt_meas (n_meas x n_state), wgt_state and
+ *     var_state (n_state x n_state), mu_state (n_state).
+ *   - Batched I/O is batch-major C order:  x0 (B, n_state), theta (B, n_theta),
+ *     x_out / mu_out (B, n_eval+1, n_state), var_out (B, n_eval+1, n_state, n_state):
+ *     per system these are the reference's return values (the `.T` views at
+ *     KalmanODE.pyx:394, 427, 463).  var_out[:, 0] is written as zeros (the reference
+ *     leaves it uninitialised; the initial state is known exactly).
+ *   - z (standard-normal draws): column-major (n_state x n_eval) per system as the
+ *     reference's z_state; column k is consumed at time index k+1
+ *     (KalmanODE.pyx:410-425).  z_batch_stride = 0 shares one z across the batch,
+ *     n_state*n_eval gives every system its own.
+ *   - ode_fun is a registered device functor selected by id (there is no Python
+ *     callback on the path): RHS formulas follow tests/eigen/ode_functions.pyx:8-60
+ *     and examples/{chkrebtii,fitz,lorenz,mseir}.py.
+ *   - All functions return 0 on success, a negative RODEO_E_* code otherwise;
+ *     rodeo_cuda_last_error() gives the message (thread-local).  Per-system Cholesky
+ *     failures (non-positive pivot; silently ignored by the reference) are reported
+ *     in `status` (0 = ok, k+1 = first failed pivot index) and do not fail the call.
+ *   - A handle is not thread-safe; one solve in flight per handle.
+ */
+#ifndef RODEO_CUDA_H
+#define RODEO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RODEO_CUDA_ABI_VERSION 1
+
+/* registered right-hand sides */
+enum {
+  RODEO_ODE_CHKREBTII = 0, /* x'' = sin(2t) - x          n_meas 1, n_theta 0 */
+  RODEO_ODE_FITZ = 1,      /* FitzHugh-Nagumo            n_meas 2, n_theta 3 */
+  RODEO_ODE_LORENZ63 = 2,  /* Lorenz 63                  n_meas 3, n_theta 3 */
+  RODEO_ODE_MSEIR = 3      /* MSEIR epidemic             n_meas 5, n_theta 6 */
+};
+
+/* what the backward pass returns (KalmanODE.solve_mv / solve_sim / solve) */
+enum { RODEO_MODE_MV = 1, RODEO_MODE_SIM = 2, RODEO_MODE_BOTH = 3 };
+
+/* interrogation variants (rodeo/cython/KalmanODE.pyx:13-102); probde is what ships */
+enum { RODEO_INTERROGATE_PROBDE = 0, RODEO_INTERROGATE_SCHOBERT = 1, RODEO_INTERROGATE_CHKREBTII = 2 };
+
+/* fields selectable in rodeo_cuda_problem_set */
+enum { RODEO_FIELD_WGT_MEAS = 0, RODEO_FIELD_MU_STATE = 1, RODEO_FIELD_WGT_STATE = 2, RODEO_FIELD_VAR_STATE = 3 };
+
+/* error codes */
+enum {
+  RODEO_OK = 0,
+  RODEO_E_INVALID = -1,     /* bad argument (NULL, non-positive size, unknown id) */
+  RODEO_E_UNSUPPORTED = -2, /* (ode, n_state, n_meas, interrogate) has no compiled kernel */
+  RODEO_E_CUDA = -3,        /* CUDA runtime error (message has the CUDA string) */
+  RODEO_E_NOMEM = -4        /* workspace allocation failed */
+};
+
+typedef struct rodeo_problem rodeo_problem; /* opaque */
+
+typedef struct {
+  int32_t n_state;        /* n */
+  int32_t n_meas;         /* m */
+  int32_t n_eval;         /* N: number of steps; outputs have N+1 time points */
+  int32_t ode;            /* RODEO_ODE_* */
+  int32_t interrogate;    /* RODEO_INTERROGATE_* */
+  int32_t reserved;       /* must be 0 */
+  double tmin, tmax;
+  const double *wgt_meas;  /* host, column-major (m x n) */
+  const double *wgt_state; /* host, column-major (n x n) */
+  const double *mu_state;  /* host, (n) */
+  const double *var_state; /* host, column-major (n x n), symmetric */
+} rodeo_problem_desc;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int rodeo_cuda_abi_version(void);
+const char *rodeo_cuda_last_error(void);
+
+/* n_meas / n_theta of a registered RHS, or RODEO_E_INVALID */
+int rodeo_cuda_ode_n_meas(int ode);
+int rodeo_cuda_ode_n_theta(int ode);
+/* 1 if a kernel is compiled for this combination, else 0 */
+int rodeo_cuda_supported(int ode, int n_state, int n_meas, int interrogate);
+
+/* Creates a problem on the CURRENT CUDA device.  The descriptor's host arrays are copied. */
+int rodeo_cuda_problem_create(const rodeo_problem_desc *desc, rodeo_problem **out);
+int rodeo_cuda_problem_destroy(rodeo_problem *p);
+/* Overwrite one of the prior / measurement arrays (host pointer, column-major). */
+int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *host_values);
+
+/* ---- workspace (filter history streamed through HBM between the two passes) ------ */
+/* Bytes of history one system needs for this problem. */
+size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p);
+/* Upper bound for the handle-owned history workspace (default: 48 GiB).  A batch whose
+ * history exceeds it is processed in chunks, transparently. */
+int rodeo_cuda_set_workspace_limit(rodeo_problem *p, size_t bytes);
+/* Pre-allocate the workspace for batches up to max_batch (otherwise grown on demand). */
+int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch);
+
+/* ---- the hot path ----------------------------------------------------------------- */
+/* Device-pointer entry point.  All pointers are device memory on the problem's device.
+ * theta may be NULL when the RHS has no parameters; z may be NULL for RODEO_MODE_MV with
+ * probde/schobert interrogation; outputs not produced by `mode` may be NULL; status may
+ * be NULL.  Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and
+ * the call returns without synchronising. */
+int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0,
+                     const double *theta, const double *z, int64_t z_batch_stride,
+                     double *x_out, double *mu_out, double *var_out, int32_t *status,
+                     void *cuda_stream);
+
+/* Host-pointer entry point (the call a NumPy user of the reference makes): copies the
+ * inputs to the device, solves in chunks with copy/compute overlap, copies the results
+ * back and synchronises.  Host buffers may be pageable or pinned (pinned is faster). */
+int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const double *x0,
+                          const double *theta, const double *z, int64_t z_batch_stride,
+                          double *x_out, double *mu_out, double *var_out, int32_t *status);
+
+/* Thinned Gaussian log-likelihood of the posterior mean (use_draw = 0) or of a posterior
+ * draw (use_draw = 1, needs z) against observations Y (n_obs_times x n_obs_comp, row
+ * major):  sum_d sum_k  log N(Y[d,k]; X[thin_index[d], state_index[k]], sd = gamma).
+ * One double per system in loglik_out (device).  No per-step output is materialised. */
+int rodeo_cuda_loglik(rodeo_problem *p, int use_draw, int64_t batch, const double *x0,
+                      const double *theta, const double *z, int64_t z_batch_stride,
+                      const int32_t *thin_index, int32_t n_obs_times,
+                      const int32_t *state_index, int32_t n_obs_comp, const double *Y,
+                      double gamma, double *loglik_out, int32_t *status, void *cuda_stream);
+
+/* ---- introspection for benchmarks -------------------------------------------------- */
+/* kernels launched by this handle since creation (or since the last reset) */
+int64_t rodeo_cuda_launch_count(const rodeo_problem *p);
+int rodeo_cuda_reset_launch_count(rodeo_problem *p);
+/* Device time (ms) of the forward and backward kernels of the most recent
+ * rodeo_cuda_solve call, measured with CUDA events on its stream; synchronises. */
+int rodeo_cuda_last_kernel_ms(rodeo_problem *p, float *forward_ms, float *backward_ms);
+/* enable (1) / disable (0) the event recording used by rodeo_cuda_last_kernel_ms */
+int rodeo_cuda_set_timing(rodeo_problem *p, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RODEO_CUDA_H */

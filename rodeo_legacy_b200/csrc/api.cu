@@ -1,0 +1,417 @@
+// api.cu -- the C ABI declared in include/rodeo_cuda.h.
+//
+// Host-side runtime around the kernels: problem handles, the HBM history workspace,
+// batch chunking, the pinned/pageable host path with copy/compute overlap, launch
+// accounting and event timing.  No torch, no Python: plain CUDA runtime.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rodeo_cuda.h"
+#include "registry.cuh"
+
+using namespace rodeo;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+  return fail(RODEO_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                      \
+  do {                                                \
+    cudaError_t e_ = (call);                          \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+struct rodeo_problem {
+  int n, m, N, ode, ig, device;
+  double tmin, tmax;
+  std::vector<double> W, Q, c, R;  // column-major host copies
+  const KernelSet *ks;
+  void *ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t ws_limit = (size_t)48 << 30;
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;     // 3 per chunk of the last solve
+  int ev_chunks = 0;
+  // host-path device buffers (grow-only)
+  void *hbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t hbuf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;
+  cudaEvent_t e_done[2] = {nullptr, nullptr}, e_copied[2] = {nullptr, nullptr};
+};
+
+static const int kOdeMeas[4] = {1, 2, 3, 5};
+static const int kOdeTheta[4] = {0, 3, 3, 6};
+
+extern "C" {
+
+int rodeo_cuda_abi_version(void) { return RODEO_CUDA_ABI_VERSION; }
+const char *rodeo_cuda_last_error(void) { return g_err.c_str(); }
+
+int rodeo_cuda_ode_n_meas(int ode) { return (ode >= 0 && ode < 4) ? kOdeMeas[ode] : RODEO_E_INVALID; }
+int rodeo_cuda_ode_n_theta(int ode) { return (ode >= 0 && ode < 4) ? kOdeTheta[ode] : RODEO_E_INVALID; }
+
+int rodeo_cuda_supported(int ode, int n_state, int n_meas, int interrogate) {
+  const KernelSet *k = find_kernel_set(ode, n_state);
+  return (k && k->m == n_meas && interrogate >= 0 && interrogate <= 2) ? 1 : 0;
+}
+
+int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) {
+  if (!d || !out) return fail(RODEO_E_INVALID, "null descriptor or output");
+  *out = nullptr;
+  if (d->n_state <= 0 || d->n_meas <= 0 || d->n_eval < 1)
+    return fail(RODEO_E_INVALID, "n_state, n_meas must be positive and n_eval >= 1");
+  if (!d->wgt_meas || !d->wgt_state || !d->mu_state || !d->var_state)
+    return fail(RODEO_E_INVALID, "wgt_meas, wgt_state, mu_state, var_state must be set");
+  if (d->ode < 0 || d->ode > 3) return fail(RODEO_E_INVALID, "unknown ode id");
+  if (d->interrogate < 0 || d->interrogate > 2) return fail(RODEO_E_INVALID, "unknown interrogate id");
+  const KernelSet *ks = find_kernel_set(d->ode, d->n_state);
+  if (!ks || ks->m != d->n_meas) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "no compiled kernel for ode=%d n_state=%d n_meas=%d (see rodeo_cuda_supported)", d->ode,
+             d->n_state, d->n_meas);
+    return fail(RODEO_E_UNSUPPORTED, buf);
+  }
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  rodeo_problem *p = new rodeo_problem();
+  p->n = d->n_state;
+  p->m = d->n_meas;
+  p->N = d->n_eval;
+  p->ode = d->ode;
+  p->ig = d->interrogate;
+  p->device = dev;
+  p->tmin = d->tmin;
+  p->tmax = d->tmax;
+  p->ks = ks;
+  p->W.assign(d->wgt_meas, d->wgt_meas + (size_t)p->m * p->n);
+  p->Q.assign(d->wgt_state, d->wgt_state + (size_t)p->n * p->n);
+  p->c.assign(d->mu_state, d->mu_state + p->n);
+  p->R.assign(d->var_state, d->var_state + (size_t)p->n * p->n);
+  *out = p;
+  return RODEO_OK;
+}
+
+int rodeo_cuda_problem_destroy(rodeo_problem *p) {
+  if (!p) return RODEO_OK;
+  cudaSetDevice(p->device);
+  if (p->ws) cudaFree(p->ws);
+  for (int i = 0; i < 8; i++)
+    if (p->hbuf[i]) cudaFree(p->hbuf[i]);
+  for (auto e : p->ev) cudaEventDestroy(e);
+  for (int i = 0; i < 2; i++) {
+    if (p->e_done[i]) cudaEventDestroy(p->e_done[i]);
+    if (p->e_copied[i]) cudaEventDestroy(p->e_copied[i]);
+  }
+  if (p->s_compute) cudaStreamDestroy(p->s_compute);
+  if (p->s_copy) cudaStreamDestroy(p->s_copy);
+  delete p;
+  return RODEO_OK;
+}
+
+int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *v) {
+  if (!p || !v) return fail(RODEO_E_INVALID, "null problem or values");
+  switch (field) {
+    case RODEO_FIELD_WGT_MEAS: p->W.assign(v, v + (size_t)p->m * p->n); break;
+    case RODEO_FIELD_MU_STATE: p->c.assign(v, v + p->n); break;
+    case RODEO_FIELD_WGT_STATE: p->Q.assign(v, v + (size_t)p->n * p->n); break;
+    case RODEO_FIELD_VAR_STATE: p->R.assign(v, v + (size_t)p->n * p->n); break;
+    default: return fail(RODEO_E_INVALID, "unknown field");
+  }
+  return RODEO_OK;
+}
+
+size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
+  return p ? (size_t)p->N * p->ks->hist_elems * sizeof(double) : 0;
+}
+
+int rodeo_cuda_set_workspace_limit(rodeo_problem *p, size_t bytes) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  p->ws_limit = bytes;
+  return RODEO_OK;
+}
+
+}  // extern "C"
+
+static long round_up(long x, long q) { return (x + q - 1) / q * q; }
+
+// systems per chunk such that the history fits the workspace limit
+static long chunk_capacity(const rodeo_problem *p, long batch) {
+  size_t per = rodeo_cuda_history_bytes_per_system(p);
+  long cap = (long)(p->ws_limit / per);
+  cap = cap / 1024 * 1024;                 // whole CTAs, 256 B aligned history rows
+  if (cap < 1024) cap = 1024;
+  return std::min(cap, round_up(batch, 32));
+}
+
+static int ensure_workspace(rodeo_problem *p, long stride) {
+  size_t need = rodeo_cuda_history_bytes_per_system(p) * (size_t)stride;
+  if (need <= p->ws_bytes) return RODEO_OK;
+  if (p->ws) {
+    cudaFree(p->ws);
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+  }
+  cudaError_t e = cudaMalloc(&p->ws, need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char buf[160];
+    snprintf(buf, sizeof buf, "history workspace of %.2f GiB could not be allocated: %s",
+             need / 1073741824.0, cudaGetErrorString(e));
+    return fail(RODEO_E_NOMEM, buf);
+  }
+  p->ws_bytes = need;
+  return RODEO_OK;
+}
+
+static int ensure_buf(rodeo_problem *p, int slot, size_t need) {
+  if (need <= p->hbuf_bytes[slot]) return RODEO_OK;
+  if (p->hbuf[slot]) cudaFree(p->hbuf[slot]);
+  p->hbuf[slot] = nullptr;
+  p->hbuf_bytes[slot] = 0;
+  cudaError_t e = cudaMalloc(&p->hbuf[slot], need);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(RODEO_E_NOMEM, std::string("device staging buffer: ") + cudaGetErrorString(e));
+  }
+  p->hbuf_bytes[slot] = need;
+  return RODEO_OK;
+}
+
+struct LoglikSpec {
+  const int *thin_index = nullptr, *state_index = nullptr;
+  const double *Y = nullptr;
+  double gamma = 1.0;
+  int n_obs_times = 0, n_obs_comp = 0;
+  double *out = nullptr;
+};
+
+// One pass over `batch` systems in chunks: forward kernel then backward kernel per chunk.
+static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const double *x0,
+                      const double *theta, const double *z, long z_stride, double *x_out,
+                      double *mu_out, double *var_out, int *status, const LoglikSpec *ll,
+                      cudaStream_t stream) {
+  const int n = p->n, nth = kOdeTheta[p->ode];
+  const long T1 = (long)p->N + 1;
+  const long cap = chunk_capacity(p, batch);
+  int rc = ensure_workspace(p, cap);
+  if (rc) return rc;
+  HostPrior hp{p->n, p->m, p->N, p->tmin, p->tmax, p->W.data(), p->Q.data(), p->c.data(), p->R.data()};
+  const long n_chunks = (batch + cap - 1) / cap;
+  if (p->timing) {
+    while ((long)p->ev.size() < 3 * n_chunks) {
+      cudaEvent_t e;
+      CK(cudaEventCreate(&e));
+      p->ev.push_back(e);
+    }
+    p->ev_chunks = (int)n_chunks;
+  }
+  for (long ci = 0; ci < n_chunks; ci++) {
+    const long off = ci * cap, B = std::min(cap, batch - off);
+    SolveArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B;
+    a.hist_stride = cap;
+    a.x0 = x0 + off * n;
+    a.theta = theta ? theta + off * nth : nullptr;
+    a.z = z ? z + off * z_stride : nullptr;
+    a.z_stride = z_stride;
+    a.hist = (double *)p->ws;
+    a.x_out = x_out ? x_out + off * T1 * n : nullptr;
+    a.mu_out = mu_out ? mu_out + off * T1 * n : nullptr;
+    a.var_out = var_out ? var_out + off * T1 * n * n : nullptr;
+    a.status = status ? status + off : nullptr;
+    if (ll) {
+      a.thin_index = ll->thin_index;
+      a.state_index = ll->state_index;
+      a.Y = ll->Y;
+      a.gamma = ll->gamma;
+      a.n_obs_times = ll->n_obs_times;
+      a.n_obs_comp = ll->n_obs_comp;
+      a.loglik = ll->out + off;
+    }
+    if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 0], stream));
+    CK(p->ks->forward[p->ig](hp, a, stream));
+    if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
+    CK(p->ks->backward[bk](hp, a, stream));
+    if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
+    p->launches += 2;
+  }
+  return RODEO_OK;
+}
+
+static int check_solve_args(rodeo_problem *p, int mode, int64_t batch, const double *x0,
+                            const double *theta, const double *z, double *x_out, double *mu_out,
+                            double *var_out) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (mode != RODEO_MODE_MV && mode != RODEO_MODE_SIM && mode != RODEO_MODE_BOTH)
+    return fail(RODEO_E_INVALID, "mode must be RODEO_MODE_MV, _SIM or _BOTH");
+  if (batch < 0) return fail(RODEO_E_INVALID, "negative batch");
+  if (batch > 0 && !x0) return fail(RODEO_E_INVALID, "x0 is null");
+  if (batch > 0 && kOdeTheta[p->ode] > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
+  if (batch > 0 && ((mode & RODEO_MODE_SIM) || p->ig == RODEO_INTERROGATE_CHKREBTII) && !z)
+    return fail(RODEO_E_INVALID, "z is null but the requested mode consumes normal draws");
+  if (batch > 0 && (mode & RODEO_MODE_MV) && (!mu_out || !var_out)) return fail(RODEO_E_INVALID, "mu_out / var_out is null");
+  if (batch > 0 && (mode & RODEO_MODE_SIM) && !x_out) return fail(RODEO_E_INVALID, "x_out is null");
+  return RODEO_OK;
+}
+
+extern "C" {
+
+int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch) {
+  if (!p || max_batch < 0) return fail(RODEO_E_INVALID, "bad arguments");
+  if (max_batch == 0) return RODEO_OK;
+  CK(cudaSetDevice(p->device));
+  return ensure_workspace(p, chunk_capacity(p, (long)max_batch));
+}
+
+int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0, const double *theta,
+                     const double *z, int64_t z_batch_stride, double *x_out, double *mu_out,
+                     double *var_out, int32_t *status, void *cuda_stream) {
+  int rc = check_solve_args(p, mode, batch, x0, theta, z, x_out, mu_out, var_out);
+  if (rc) return rc;
+  if (batch == 0) return RODEO_OK;
+  CK(cudaSetDevice(p->device));
+  BackwardKind bk = mode == RODEO_MODE_MV ? BK_MV : mode == RODEO_MODE_SIM ? BK_SIM : BK_BOTH;
+  return run_chunks(p, bk, (long)batch, x0, theta, z, (long)z_batch_stride, x_out, mu_out, var_out,
+                    status, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int rodeo_cuda_loglik(rodeo_problem *p, int use_draw, int64_t batch, const double *x0, const double *theta,
+                      const double *z, int64_t z_batch_stride, const int32_t *thin_index,
+                      int32_t n_obs_times, const int32_t *state_index, int32_t n_obs_comp,
+                      const double *Y, double gamma, double *loglik_out, int32_t *status,
+                      void *cuda_stream) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (batch < 0 || n_obs_times < 0 || n_obs_comp < 0) return fail(RODEO_E_INVALID, "negative size");
+  if (batch == 0) return RODEO_OK;
+  if (!x0 || !loglik_out) return fail(RODEO_E_INVALID, "x0 / loglik_out is null");
+  if (kOdeTheta[p->ode] > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
+  if ((use_draw || p->ig == RODEO_INTERROGATE_CHKREBTII) && !z) return fail(RODEO_E_INVALID, "z is null but draws are requested");
+  if (n_obs_times * n_obs_comp > 0 && (!thin_index || !state_index || !Y)) return fail(RODEO_E_INVALID, "thin_index / state_index / Y is null");
+  if (!(gamma > 0.0)) return fail(RODEO_E_INVALID, "gamma must be positive");
+  CK(cudaSetDevice(p->device));
+  LoglikSpec ll;
+  ll.thin_index = thin_index;
+  ll.state_index = state_index;
+  ll.Y = Y;
+  ll.gamma = gamma;
+  ll.n_obs_times = n_obs_times;
+  ll.n_obs_comp = n_obs_comp;
+  ll.out = loglik_out;
+  return run_chunks(p, use_draw ? BK_LL_DRAW : BK_LL_MEAN, (long)batch, x0, theta, z, (long)z_batch_stride,
+                    nullptr, nullptr, nullptr, status, &ll, (cudaStream_t)cuda_stream);
+}
+
+// Host-buffer path: H2D inputs, solve chunk k on the compute stream into one of two device
+// output buffers while the copy stream drains chunk k-1 to the host.
+int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const double *x0, const double *theta,
+                          const double *z, int64_t z_batch_stride, double *x_out, double *mu_out,
+                          double *var_out, int32_t *status) {
+  int rc = check_solve_args(p, mode, batch, x0, theta, z, x_out, mu_out, var_out);
+  if (rc) return rc;
+  if (batch == 0) return RODEO_OK;
+  CK(cudaSetDevice(p->device));
+  const int n = p->n, nth = kOdeTheta[p->ode];
+  const long T1 = (long)p->N + 1;
+  if (!p->s_compute) {
+    CK(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&p->e_done[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->e_copied[i], cudaEventDisableTiming));
+    }
+  }
+  const bool mv = mode & RODEO_MODE_MV, sim = mode & RODEO_MODE_SIM;
+  const size_t out_per = (size_t)T1 * n * sizeof(double) * ((mv ? 1 + n : 0) + (sim ? 1 : 0));
+  // output staging: two buffers of at most 2 GiB each, and never more systems than a history chunk
+  long hc = (long)std::max<size_t>(1, ((size_t)2 << 30) / out_per);
+  hc = std::min(hc, chunk_capacity(p, (long)batch));
+  hc = std::min(hc, (long)batch);
+  if (hc > 1024) hc = hc / 1024 * 1024;
+  const bool need_z = z != nullptr;
+  const size_t z_elems = need_z ? (size_t)n * p->N : 0;
+  // slots: 0 x0, 1 theta, 2 z, 3 status, 4/5 output buffers
+  if ((rc = ensure_buf(p, 0, (size_t)hc * n * sizeof(double)))) return rc;
+  if (nth && (rc = ensure_buf(p, 1, (size_t)hc * nth * sizeof(double)))) return rc;
+  if (need_z && (rc = ensure_buf(p, 2, (z_batch_stride ? (size_t)hc : 1) * z_elems * sizeof(double)))) return rc;
+  if ((rc = ensure_buf(p, 3, (size_t)hc * sizeof(int)))) return rc;
+  if ((rc = ensure_buf(p, 4, (size_t)hc * out_per))) return rc;
+  if ((rc = ensure_buf(p, 5, (size_t)hc * out_per))) return rc;
+  if (need_z && !z_batch_stride)
+    CK(cudaMemcpyAsync(p->hbuf[2], z, z_elems * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
+  BackwardKind bk = mode == RODEO_MODE_MV ? BK_MV : mode == RODEO_MODE_SIM ? BK_SIM : BK_BOTH;
+  const long n_chunks = ((long)batch + hc - 1) / hc;
+  for (long ci = 0; ci < n_chunks; ci++) {
+    const long off = ci * hc, B = std::min(hc, (long)batch - off);
+    const int slot = (int)(ci & 1);
+    double *ob = (double *)p->hbuf[4 + slot];
+    double *d_mu = mv ? ob : nullptr;
+    double *d_var = mv ? ob + (size_t)B * T1 * n : nullptr;
+    double *d_x = sim ? ob + (mv ? (size_t)B * T1 * n * (1 + n) : 0) : nullptr;
+    // inputs of this chunk (the previous chunk's kernels are ordered before us on s_compute)
+    CK(cudaMemcpyAsync(p->hbuf[0], x0 + off * n, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
+    if (nth) CK(cudaMemcpyAsync(p->hbuf[1], theta + off * nth, (size_t)B * nth * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
+    if (need_z && z_batch_stride)
+      CK(cudaMemcpyAsync(p->hbuf[2], z + off * z_batch_stride, (size_t)B * z_elems * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
+    if (ci >= 2) CK(cudaStreamWaitEvent(p->s_compute, p->e_copied[slot], 0));
+    rc = run_chunks(p, bk, B, (const double *)p->hbuf[0], nth ? (const double *)p->hbuf[1] : nullptr,
+                    need_z ? (const double *)p->hbuf[2] : nullptr, z_batch_stride ? (long)z_elems : 0, d_x,
+                    d_mu, d_var, (int *)p->hbuf[3], nullptr, p->s_compute);
+    if (rc) return rc;
+    if (status) CK(cudaMemcpyAsync(status + off, p->hbuf[3], (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, p->s_compute));
+    CK(cudaEventRecord(p->e_done[slot], p->s_compute));
+    CK(cudaStreamWaitEvent(p->s_copy, p->e_done[slot], 0));
+    if (mv) {
+      CK(cudaMemcpyAsync(mu_out + off * T1 * n, d_mu, (size_t)B * T1 * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
+      CK(cudaMemcpyAsync(var_out + off * T1 * n * n, d_var, (size_t)B * T1 * n * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
+    }
+    if (sim) CK(cudaMemcpyAsync(x_out + off * T1 * n, d_x, (size_t)B * T1 * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
+    CK(cudaEventRecord(p->e_copied[slot], p->s_copy));
+  }
+  CK(cudaStreamSynchronize(p->s_compute));
+  CK(cudaStreamSynchronize(p->s_copy));
+  return RODEO_OK;
+}
+
+int64_t rodeo_cuda_launch_count(const rodeo_problem *p) { return p ? p->launches : 0; }
+int rodeo_cuda_reset_launch_count(rodeo_problem *p) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  p->launches = 0;
+  return RODEO_OK;
+}
+int rodeo_cuda_set_timing(rodeo_problem *p, int enabled) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  p->timing = enabled != 0;
+  return RODEO_OK;
+}
+int rodeo_cuda_last_kernel_ms(rodeo_problem *p, float *forward_ms, float *backward_ms) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (!p->timing || p->ev_chunks == 0) return fail(RODEO_E_INVALID, "timing was not enabled for the last solve");
+  CK(cudaSetDevice(p->device));
+  float f = 0.f, b = 0.f;
+  for (int ci = 0; ci < p->ev_chunks; ci++) {
+    CK(cudaEventSynchronize(p->ev[3 * ci + 2]));
+    float t;
+    CK(cudaEventElapsedTime(&t, p->ev[3 * ci + 0], p->ev[3 * ci + 1]));
+    f += t;
+    CK(cudaEventElapsedTime(&t, p->ev[3 * ci + 1], p->ev[3 * ci + 2]));
+    b += t;
+  }
+  if (forward_ms) *forward_ms = f;
+  if (backward_ms) *backward_ms = b;
+  return RODEO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// registry.cuh -- table of compiled (ode, n_state) kernel sets and their launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kalman_tps.cuh"
+
+namespace rodeo {
+
+// Everything the host side needs to fill a Prior<n, m> without knowing n, m statically.
+struct HostPrior {
+  int n, m, n_eval;
+  double tmin, tmax;
+  const double *W, *Q, *c, *R;  // column-major host arrays
+};
+
+enum BackwardKind { BK_MV = 0, BK_SIM = 1, BK_BOTH = 2, BK_LL_MEAN = 3, BK_LL_DRAW = 4, BK_COUNT = 5 };
+
+typedef cudaError_t (*launch_fn)(const HostPrior &, const SolveArgs &, cudaStream_t);
+
+struct KernelSet {
+  int ode, n, m;
+  const char *name;
+  launch_fn forward[3];           // by interrogation variant
+  launch_fn backward[BK_COUNT];   // by BackwardKind
+  int hist_elems;                 // doubles of history per system per step
+};
+
+const KernelSet *find_kernel_set(int ode, int n);
+int kernel_set_count();
+const KernelSet *kernel_set_at(int i);
+
+}  // namespace rodeo

@@ -1,0 +1,77 @@
+"""The CUDA kernel bodies (thread-per-system), executed on the CPU by tests/hostsim,
+against the C oracle: catches algebra / indexing / layout errors without a GPU."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import hostsim
+from tests.common import load_golden, traj_err, var_err, ode_name
+
+# (golden case, mean tol, var tol, draw tol): floors measured in tests/test_oracle_golden.py --
+# the CAR-prior Lorenz case is ill-conditioned (cond R = 2.5e12) and chaotic.
+CASES = [("chkrebtii_n200", 1e-10, 1e-8, 1e-5), ("fitz_n400", 1e-10, 1e-9, 1e-9),
+         ("lorenz_car_n600", 1e-7, 1e-6, 1e-7), ("mseir_n1000", 1e-10, 1e-8, 1e-7)]
+
+
+def _setup(name, B=3):
+    g = load_golden(name)
+    ode = ode_name(name)
+    p = oracle.Problem(ode, g["W"], float(g["tmin"]), float(g["tmax"]), int(g["N"]), g["Q"], g["c"], g["R"])
+    rng = np.random.default_rng(11)
+    x0 = np.tile(g["x0"], (B, 1))
+    theta = None
+    if "theta" in g:
+        th = np.atleast_2d(g["theta"])
+        theta = th[np.arange(B) % len(th)] * np.exp(0.02 * rng.standard_normal((B, th.shape[1])))
+    return g, ode, p, x0, theta
+
+
+@pytest.mark.parametrize("name,mtol,vtol,xtol", CASES)
+def test_bodies_match_oracle(name, mtol, vtol, xtol):
+    g, ode, p, x0, theta = _setup(name)
+    ref = oracle.solve_batch(p, x0, theta, g["z"], oracle.MODE_BOTH)
+    args = (ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, g["z"])
+    both = hostsim.solve(*args, kind="both")
+    assert not both["status"].any() and not ref["status"].any()
+    assert traj_err(both["mu"], ref["mu"]).max() < mtol
+    assert var_err(both["var"][:, 1:], ref["var"][:, 1:]).max() < vtol
+    assert not both["var"][:, 0].any()
+    assert traj_err(both["x"], ref["x"]).max() < xtol
+    mv = hostsim.solve(*args, kind="mv")
+    sim = hostsim.solve(*args, kind="sim")
+    np.testing.assert_array_equal(mv["mu"], both["mu"])
+    np.testing.assert_array_equal(mv["var"], both["var"])
+    np.testing.assert_array_equal(sim["x"], both["x"])
+
+
+def test_per_system_z_and_loglik():
+    g, ode, p, x0, theta = _setup("fitz_n400", B=4)
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((4, p.n, p.N))
+    ref = oracle.solve_batch(p, x0, theta, z, oracle.MODE_BOTH)
+    args = (ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, z)
+    sim = hostsim.solve(*args, kind="sim")
+    assert traj_err(sim["x"], ref["x"]).max() < 1e-9
+    ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
+    for kind, key in (("ll_mean", "mu"), ("ll_draw", "x")):
+        r = hostsim.solve(*args, kind=kind, thin_index=ind, state_index=[0, 3], Y=Y, gamma=gam)
+        want = [oracle.loglik(ref[key][b], ind, [0, 3], Y, gam) for b in range(4)]
+        np.testing.assert_allclose(r["loglik"], want, rtol=1e-9)
+
+
+@pytest.mark.parametrize("ig,name", [(1, "schobert"), (2, "chkrebtii")])
+def test_interrogation_variants(ig, name):
+    g, ode, p, x0, theta = _setup("fitz_n400", B=2)
+    po = oracle.Problem(ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], interrogate=name)
+    # schobert (H = 0) leaves Sigma_f singular, so its sampling pass is degenerate (the
+    # reference ships it disabled): compare mean/variance only for it.
+    mode, kind = (oracle.MODE_MV, "mv") if ig == 1 else (oracle.MODE_BOTH, "both")
+    theta = np.tile(g["theta"][0], (2, 1))       # schobert diverges for other draws
+    ref = oracle.solve_batch(po, x0, theta, g["z"], mode)
+    assert np.isfinite(ref["mu"]).all()
+    r = hostsim.solve(ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, g["z"],
+                      kind=kind, ig=ig)
+    assert traj_err(r["mu"], ref["mu"]).max() < 1e-9
+    assert var_err(r["var"][:, 1:], ref["var"][:, 1:]).max() < 1e-8
+    if ig == 2:
+        assert traj_err(r["x"], ref["x"]).max() < 1e-8
