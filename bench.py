@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- batched KalmanODE solves/s on the headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path over one batch: FitzHugh-Nagumo (n_state 6, n_meas 2),
+n_eval 400, 65,536 theta draws per GPU, solve_mv (posterior mean + variance for every
+system and time point).  For N > 1 launch under torchrun (one rank per GPU); the batch is
+replicated per rank (weak scaling), no collective on the data path.
+
+Prints ONE JSON line (rank 0).  `value` times the device-pointer entry point with inputs
+resident in HBM; `e2e` times the host-buffer entry point (pinned host buffers, H2D of the
+inputs and D2H of every output inside the timed region); `roofline` is the dominant
+(backward) kernel against the measured HBM bandwidth with SURVEY section 8(d)'s algorithmic bytes;
+`cpu_baseline` is the C oracle (a port of the reference's arithmetic) on the host cores.
+`--impl reference` times that CPU port alone with all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "batched KalmanODE solves/sec (FitzHugh-Nagumo, 64k theta)"
+UNIT = "solves/s"
+BATCH = 65536
+N_EVAL, N_STATE, N_MEAS = 400, 6, 2
+# SURVEY section 8(d), general mode, per system per step: the reference's four dense history
+# arrays written once by the filter and read once by the smoother, plus the solve_mv output.
+HIST_BYTES_STEP = 8 * (2 * N_STATE + 2 * N_STATE * N_STATE)          # 672
+OUT_BYTES_STEP = 8 * (N_STATE + N_STATE * N_STATE)                   # 336
+ALG_BYTES_SOLVE = N_EVAL * (2 * HIST_BYTES_STEP + OUT_BYTES_STEP)    # 672,000
+ALG_BYTES_BACKWARD = N_EVAL * (HIST_BYTES_STEP + OUT_BYTES_STEP)     # the smoother kernel's share
+ALG_BYTES_FORWARD = N_EVAL * HIST_BYTES_STEP
+
+
+def workload_config(extra=None):
+    c = {"workload": "fitzhugh-nagumo solve_mv, n_state 6, n_meas 2, n_eval 400, "
+                     "65536 theta draws per GPU (BASELINE configs[1])",
+         "batch_per_gpu": BATCH, "n_eval": N_EVAL, "mode": "solve_mv", "prior": "ibm q=3, sigma 0.1",
+         "l2": "no flush: each step streams 5.7 GB of history and 8.8 GB of output per GPU, "
+               ">100x the 126 MB L2"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:            # NVML missing: report that, do not fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(2.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_baseline(seconds=10.0, chunk=1024, nthreads=0):
+    """The C oracle (port of rodeo/eigen/KalmanTV.h + KalmanTVODE.h), OpenMP over the batch,
+    on a bounded sample of the SAME workload: chunks of `chunk` solves until `seconds` elapse."""
+    import numpy as np
+    import oracle
+    from tests import workloads as wl
+    oracle.build()
+    w, x0, theta = wl.fitz_batch(chunk * 64, seed=0)
+    p = wl.make_oracle_problem(w)
+    cores = oracle.max_threads() if nthreads <= 0 else nthreads
+    oracle.solve_batch(p, x0[:max(cores, 8)], theta[:max(cores, 8)], None, oracle.MODE_MV, nthreads)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        lo = done % (chunk * 64)
+        oracle.solve_batch(p, x0[lo:lo + chunk], theta[lo:lo + chunk], None, oracle.MODE_MV, nthreads)
+        done += chunk
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return {"value": done / el, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": f"{done} of the workload's solves (chunks of {chunk}), {el:.1f} s, "
+                      "C port of the reference arithmetic, gcc -O3, OpenMP over systems"}, done, el
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Its compiled backends
+    cannot be built in this image (Eigen and `kalmantv` are absent), so this is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    chunk = 2048
+    import numpy as np
+    import oracle
+    from tests import workloads as wl
+    oracle.build()
+    w, x0, theta = wl.fitz_batch(chunk, seed=0)
+    p = wl.make_oracle_problem(w)
+    cores = oracle.max_threads()
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV)
+    el = time.perf_counter() - t0
+    v = steps * chunk / el
+    sample = (f"each step = {chunk} of the workload's 65536 solves; {steps} steps timed "
+              f"(capped at 20 so the run ends within minutes)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config({"reference_sample": sample}),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": int(cores), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def host_memory_ok(nbytes):
+    try:
+        avail = None
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+        lim = None
+        for pth in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+            if os.path.exists(pth):
+                s = open(pth).read().strip()
+                if s.isdigit():
+                    lim = int(s)
+        cap = min(x for x in (avail, lim) if x is not None)
+        return nbytes * 2.5 < cap
+    except Exception:
+        return False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tests import workloads as wl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    w, x0, theta = wl.fitz_batch(B, seed=rank)
+    k = wl.make_kode(w)
+    k.reserve(B)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+
+    # ---- device-resident throughput ("value") ---------------------------------------------
+    for _ in range(args.warmup):
+        mu, var = k.solve_mv(x0d, theta=thd)
+    barrier()
+    k.set_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = k.launch_count
+    fwd_ms = bwd_ms = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        mu, var = k.solve_mv(x0d, theta=thd)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = k.launch_count - launches0
+    # per-kernel device times of the last timed step (events on the launching stream)
+    f, b = k.last_kernel_ms()
+    fwd_ms, bwd_ms = f, b
+    k.set_timing(False)
+    status_bad = int(k.status.abs().sum())
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        del mu, var
+        torch.cuda.empty_cache()
+        Be = B
+        out_bytes = Be * (N_EVAL + 1) * (N_STATE + N_STATE * N_STATE) * 8
+        while Be > 4096 and not host_memory_ok(out_bytes * max(1, min(world, 8))):
+            Be //= 2
+            out_bytes = Be * (N_EVAL + 1) * (N_STATE + N_STATE * N_STATE) * 8
+        pin = lambda *s: torch.empty(s, dtype=torch.float64, pin_memory=True)
+        x0p, thp = pin(Be, N_STATE), pin(Be, 3)
+        x0p.copy_(torch.from_numpy(x0[:Be]))
+        thp.copy_(torch.from_numpy(theta[:Be]))
+        mup, varp = pin(Be, N_EVAL + 1, N_STATE), pin(Be, N_EVAL + 1, N_STATE, N_STATE)
+        x0n, thn, mun, varn = x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy()
+        k.solve_mv_into(x0n, thn, mun, varn)           # warm-up (allocates staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            k.solve_mv_into(x0n, thn, mun, varn)       # synchronous: returns with results on the host
+        barrier()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        e2e = {"value": world * Be * args.e2e_steps / el, "unit": UNIT,
+               "h2d_bytes_per_step": Be * (N_STATE + 3) * 8,
+               "d2h_bytes_per_step": out_bytes + Be * 4,
+               "batch_per_gpu": Be, "steps": args.e2e_steps, "ms_per_step": 1e3 * el / args.e2e_steps,
+               "host_buffers": "pinned", "checksum": float(mun[:, -1, 0].sum())}
+        del mup, varp
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _, _ = cpu_baseline(args.cpu_seconds)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bwd_gbs = ALG_BYTES_BACKWARD * B / (bwd_ms * 1e-3) / 1e9
+        fwd_gbs = ALG_BYTES_FORWARD * B / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None
+        step_gbs = ALG_BYTES_SOLVE * B * args.steps / (ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config({"parallelism": f"batch replicated x{world} (weak), no collective"}),
+            "roofline": {"bound": "hbm", "kernel": "kalman_backward (smoother, solve_mv)",
+                         "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALG_BYTES_BACKWARD * B,
+                         "kernel_ms": bwd_ms, "forward_kernel_ms": fwd_ms,
+                         "forward_achieved": fwd_gbs,
+                         "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "status_nonzero": status_bad,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,360 @@
+"""Batched KalmanODE front end over the CUDA library.
+
+Mirrors the reference's backend class (``rodeo/cython/KalmanODE.pyx``): constructor
+``KalmanODE(W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state, z_state=None)``
+(:170-172), properties ``wgt_meas / mu_state / var_state / wgt_state / z_state`` with
+shape- and contiguity-checked setters and the ``z_state`` deleter that re-zeros (:220-278),
+methods ``solve / solve_sim / solve_mv (x0, W=None, theta=None)`` (:335, :396, :429).
+
+Differences, all forced by batching on a GPU:
+  * ``ode_fun`` is the NAME of a registered device functor ("chkrebtii", "fitz", "lorenz63",
+    "mseir") -- there is no Python callback per step.  A callable carrying a
+    ``rodeo_cuda_name`` attribute is accepted too.
+  * ``x0`` may be (n,) or (B, n); ``theta`` (k,) or (B, k); ``z_state`` (n, N) shared by the
+    batch or (B, n, N).  A 1-D ``x0`` returns the reference's shapes (N+1, n) / (N+1, n, n);
+    a 2-D one returns batch-major arrays (B, N+1, n) / (B, N+1, n, n).
+  * NumPy in -> NumPy out through the host-buffer entry point; torch CUDA tensors in ->
+    torch CUDA tensors out through the device-pointer entry point (nothing leaves HBM).
+  * ``var[..., 0, :, :]`` is zeros (the compiled reference backends leave it uninitialised).
+  * ``solve_mv`` never touches the RNG; ``solve_sim`` / ``solve`` fill an all-zero
+    ``z_state`` from ``rand_mat`` (global NumPy RNG) exactly like the reference (:285-286).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ..utils import rand_mat
+
+ODE_FUNS = {"chkrebtii": 0, "fitz": 1, "lorenz63": 2, "mseir": 3}
+_ALIASES = {"lorenz": "lorenz63", "fitzhugh_nagumo": "fitz", "fitzhugh-nagumo": "fitz", "fn": "fitz"}
+_INTERROGATE = {"probde": 0, "schobert": 1, "chkrebtii": 2}
+MODE_MV, MODE_SIM, MODE_BOTH = 1, 2, 3
+_FIELDS = {"wgt_meas": 0, "mu_state": 1, "wgt_state": 2, "var_state": 3}
+
+
+def register_names():
+    """Names of the compiled right-hand sides."""
+    return sorted(ODE_FUNS)
+
+
+def _ode_id(ode_fun):
+    name = getattr(ode_fun, "rodeo_cuda_name", ode_fun)
+    if isinstance(name, str):
+        name = _ALIASES.get(name.lower(), name.lower())
+        if name in ODE_FUNS:
+            return ODE_FUNS[name]
+        raise ValueError(f"unknown ode_fun {name!r}; registered: {register_names()}")
+    if isinstance(name, (int, np.integer)) and 0 <= int(name) <= 3:
+        return int(name)
+    raise TypeError("rodeo.cuda runs ode_fun on the GPU: pass the name of a registered device "
+                    f"functor ({register_names()}), not a Python callable")
+
+
+def _copynm(dest, source, name):
+    """The reference's checked copy (KalmanODE.pyx:104-110)."""
+    source = np.asarray(source)
+    if not source.flags.f_contiguous:
+        raise TypeError('{} is not f contiguous.'.format(name))
+    if not source.shape == dest.shape:
+        raise TypeError('{} has incorrect shape.'.format(name))
+    dest[...] = source
+    return source
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
+class KalmanODE:
+    def __init__(self, W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state,
+                 z_state=None, interrogate="probde", device=None):
+        self._lib = _lib.load()                      # raises if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
+        W = np.asarray(W, dtype=np.float64)
+        self.n_meas, self.n_state = W.shape
+        self.tmin, self.tmax = float(tmin), float(tmax)
+        self.n_eval = int(n_eval)
+        self.n_steps = self.n_eval + 1
+        self.ode_fun = ode_fun
+        self._ode = _ode_id(ode_fun)
+        self._ig = _INTERROGATE[interrogate]
+        self.n_theta = self._lib.rodeo_cuda_ode_n_theta(self._ode)
+        if self._lib.rodeo_cuda_ode_n_meas(self._ode) != self.n_meas:
+            raise TypeError('{} has incorrect shape.'.format('W'))
+        n, m = self.n_state, self.n_meas
+        self._wgt_meas = np.empty((m, n), order='F')
+        self._mu_state = np.empty(n, order='F')
+        self._wgt_state = np.empty((n, n), order='F')
+        self._var_state = np.empty((n, n), order='F')
+        self._z_state = np.zeros((n, self.n_eval), order='F')
+        self._wgt_meas[:] = W
+        self._mu_state[:] = mu_state
+        self._wgt_state[:] = wgt_state
+        self._var_state[:] = var_state
+        if z_state is not None:
+            self.z_state = z_state
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        desc = _lib.ProblemDesc(n, m, self.n_eval, self._ode, self._ig, 0, self.tmin, self.tmax,
+                                self._wgt_meas.ctypes.data, self._wgt_state.ctypes.data,
+                                self._mu_state.ctypes.data, self._var_state.ctypes.data)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rodeo_cuda_problem_create(ctypes.byref(desc), ctypes.byref(h)))
+        self._h = h
+        self._z_dev = None          # cached device copy of the shared z
+        self._ll_cache = {}
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.rodeo_cuda_problem_destroy(h)
+            except Exception:
+                pass
+
+    # ---- properties (KalmanODE.pyx:220-278) ---------------------------------------------
+    def _push(self, name):
+        arr = getattr(self, "_" + name)
+        _lib.check(self._lib.rodeo_cuda_problem_set(self._h, _FIELDS[name], arr.ctypes.data))
+
+    @property
+    def wgt_meas(self):
+        return self._wgt_meas
+
+    @wgt_meas.setter
+    def wgt_meas(self, v):
+        _copynm(self._wgt_meas, v, 'wgt_meas')
+        self._push("wgt_meas")
+
+    @property
+    def mu_state(self):
+        return self._mu_state
+
+    @mu_state.setter
+    def mu_state(self, v):
+        _copynm(self._mu_state, v, 'mu_state')
+        self._push("mu_state")
+
+    @property
+    def var_state(self):
+        return self._var_state
+
+    @var_state.setter
+    def var_state(self, v):
+        _copynm(self._var_state, v, 'var_state')
+        self._push("var_state")
+
+    @property
+    def wgt_state(self):
+        return self._wgt_state
+
+    @wgt_state.setter
+    def wgt_state(self, v):
+        _copynm(self._wgt_state, v, 'wgt_state')
+        self._push("wgt_state")
+
+    @property
+    def z_state(self):
+        return self._z_state
+
+    @z_state.setter
+    def z_state(self, v):
+        v = np.asarray(v, dtype=np.float64)
+        if v.ndim == 3:                      # per-system draws (B, n, N): batched extension
+            if v.shape[1:] != (self.n_state, self.n_eval):
+                raise TypeError('{} has incorrect shape.'.format('z_state'))
+            self._z_state = v
+        else:
+            if self._z_state.ndim != 2:
+                self._z_state = np.zeros((self.n_state, self.n_eval), order='F')
+            _copynm(self._z_state, v, 'z_state')
+        self._z_dev = None
+
+    @z_state.deleter
+    def z_state(self):
+        self._z_state = np.zeros((self.n_state, self.n_eval), order='F')
+        self._z_dev = None
+
+    # ---- workspace / introspection ----------------------------------------------------------
+    def reserve(self, max_batch):
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rodeo_cuda_reserve(self._h, int(max_batch)))
+
+    def set_workspace_limit(self, nbytes):
+        _lib.check(self._lib.rodeo_cuda_set_workspace_limit(self._h, int(nbytes)))
+
+    @property
+    def history_bytes_per_system(self):
+        return int(self._lib.rodeo_cuda_history_bytes_per_system(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.rodeo_cuda_launch_count(self._h))
+
+    def set_timing(self, enabled=True):
+        _lib.check(self._lib.rodeo_cuda_set_timing(self._h, int(bool(enabled))))
+
+    def last_kernel_ms(self):
+        f, b = ctypes.c_float(), ctypes.c_float()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rodeo_cuda_last_kernel_ms(self._h, ctypes.byref(f), ctypes.byref(b)))
+        return f.value, b.value
+
+    # ---- argument handling --------------------------------------------------------------------
+    def _prep(self, x0, W, theta, need_z):
+        if W is not None:
+            self._wgt_meas[:] = np.asarray(W, dtype=np.float64)     # KalmanODE.pyx:441-442
+            self._push("wgt_meas")
+        on_dev = isinstance(x0, torch.Tensor)
+        if on_dev:
+            if x0.dtype != torch.float64 or not x0.is_cuda:
+                raise TypeError("x0 must be a float64 CUDA tensor (or a NumPy array)")
+            single = x0.dim() == 1
+            x0b = x0.reshape(-1, self.n_state).contiguous() if x0.numel() % self.n_state == 0 else None
+        else:
+            x0a = np.asarray(x0, dtype=np.float64)
+            if x0a.ndim == 1 and not x0a.flags.f_contiguous:
+                raise TypeError('{} is not f contiguous.'.format('x0'))
+            single = x0a.ndim == 1
+            x0b = np.ascontiguousarray(x0a.reshape(-1, self.n_state)) if x0a.size % self.n_state == 0 else None
+        if x0b is None or x0b.shape[-1] != self.n_state or (single and x0b.shape[0] != 1):
+            raise TypeError('{} has incorrect shape.'.format('x0'))
+        B = x0b.shape[0]
+        th = None
+        if self.n_theta:
+            if theta is None:
+                raise TypeError("theta is required by this ode_fun")
+            if on_dev:
+                th = torch.as_tensor(theta, dtype=torch.float64, device=x0b.device)
+                th = th.reshape(-1, self.n_theta)
+                th = (th.expand(B, self.n_theta) if th.shape[0] == 1 else th).contiguous()
+            else:
+                th = np.asarray(theta, dtype=np.float64).reshape(-1, self.n_theta)
+                th = np.ascontiguousarray(np.broadcast_to(th, (B, self.n_theta)) if th.shape[0] == 1 else th)
+            if th.shape[0] != B:
+                raise TypeError('{} has incorrect shape.'.format('theta'))
+        z, z_stride = None, 0
+        if need_z:
+            if not np.any(self._z_state):                               # KalmanODE.pyx:285-286
+                self._z_state = rand_mat(self.n_eval, self.n_state)
+                self._z_dev = None
+            zs = self._z_state
+            if zs.ndim == 3:
+                if zs.shape[0] != B:
+                    raise TypeError('{} has incorrect shape.'.format('z_state'))
+                # per system column-major (n x N)  ==  C-order (B, N, n)
+                zc = np.ascontiguousarray(np.transpose(zs, (0, 2, 1)))
+                z_stride = self.n_state * self.n_eval
+            else:
+                zc = np.asfortranarray(zs)
+            if on_dev:
+                if self._z_dev is None or self._z_dev.device != x0b.device:
+                    # column-major bytes, whatever the torch shape says
+                    flat = zc.ravel(order="K") if zs.ndim == 3 else zc.ravel(order="F")
+                    self._z_dev = torch.from_numpy(np.ascontiguousarray(flat)).to(x0b.device)
+                z = self._z_dev
+            else:
+                z = zc
+        return on_dev, single, B, x0b, th, z, z_stride
+
+    def _run(self, mode, x0, W, theta, out=None):
+        need_z = bool(mode & MODE_SIM) or self._ig == 2
+        on_dev, single, B, x0b, th, z, z_stride = self._prep(x0, W, theta, need_z)
+        n, T = self.n_state, self.n_steps
+        mv, sim = bool(mode & MODE_MV), bool(mode & MODE_SIM)
+        if on_dev:
+            dev = x0b.device
+            mk = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+            x = mk(B, T, n) if sim else None
+            mu = mk(B, T, n) if mv else None
+            var = mk(B, T, n, n) if mv else None
+            status = torch.zeros(B, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                _lib.check(self._lib.rodeo_cuda_solve(
+                    self._h, mode, B, _ptr(x0b), _ptr(th), _ptr(z), z_stride, _ptr(x), _ptr(mu),
+                    _ptr(var), _ptr(status), stream))
+        else:
+            if out is not None:
+                x, mu, var = out
+            else:
+                x = np.empty((B, T, n)) if sim else None
+                mu = np.empty((B, T, n)) if mv else None
+                var = np.empty((B, T, n, n)) if mv else None
+            status = np.zeros(B, dtype=np.int32)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.rodeo_cuda_solve_host(
+                    self._h, mode, B, _ptr(x0b), _ptr(th), _ptr(z), z_stride, _ptr(x), _ptr(mu),
+                    _ptr(var), _ptr(status)))
+        self.status = status
+        if single:
+            x, mu, var = (None if a is None else a[0] for a in (x, mu, var))
+        return x, mu, var
+
+    # ---- the reference's three methods -----------------------------------------------------
+    def solve(self, x0, W=None, theta=None):
+        """(kalman_sim, kalman_mu, kalman_var) -- KalmanODE.pyx:335-394."""
+        return self._run(MODE_BOTH, x0, W, theta)
+
+    def solve_sim(self, x0, W=None, theta=None):
+        """A draw from the solution posterior -- KalmanODE.pyx:396-427."""
+        return self._run(MODE_SIM, x0, W, theta)[0]
+
+    def solve_mv(self, x0, W=None, theta=None):
+        """(posterior mean, posterior variance) -- KalmanODE.pyx:429-463."""
+        return self._run(MODE_MV, x0, W, theta)[1:]
+
+    def solve_mv_into(self, x0, theta, mu_out, var_out):
+        """Host path writing into caller-provided (e.g. pinned) NumPy buffers."""
+        self._run(MODE_MV, x0, None, theta, out=(None, mu_out, var_out))
+
+    # ---- fused thinning + Gaussian log-likelihood (examples/inference.py:54-56, 66-94) ------
+    def loglik(self, x0, theta, Y, thin_index, state_ind, gamma, use_draw=False):
+        """One log-likelihood per system, no per-step output materialised.
+
+        sum_d sum_k log N(Y[d, k]; X[thin_index[d], state_ind[k]], sd=gamma) with X the
+        posterior mean (use_draw=False) or a posterior draw (use_draw=True, as
+        ``kalman_nlpost`` does with solve_sim).  Inputs NumPy or torch CUDA; returns the same kind.
+        """
+        need_z = bool(use_draw) or self._ig == 2
+        on_dev, single, B, x0b, th, z, z_stride = self._prep(x0, None, theta, need_z)
+        dev = x0b.device if on_dev else self.device
+        thin = np.ascontiguousarray(thin_index, dtype=np.int32)
+        si = np.ascontiguousarray(state_ind, dtype=np.int32)
+        Yc = np.ascontiguousarray(Y.detach().cpu().numpy() if isinstance(Y, torch.Tensor) else Y,
+                                  dtype=np.float64)
+        if Yc.shape != (len(thin), len(si)):
+            raise TypeError('{} has incorrect shape.'.format('Y'))
+        if thin.size and (thin.min() < 0 or thin.max() > self.n_eval or np.any(np.diff(thin) < 0)):
+            raise ValueError("thin_index must be ascending grid indices in [0, n_eval]")
+        if si.size and (si.min() < 0 or si.max() >= self.n_state):
+            raise ValueError("state_ind out of range")
+        key = (thin.tobytes(), si.tobytes(), Yc.tobytes(), str(dev))
+        if key not in self._ll_cache:
+            self._ll_cache.clear()
+            self._ll_cache[key] = tuple(torch.from_numpy(a).to(dev) for a in (thin, si, Yc))
+        d_thin, d_si, d_Y = self._ll_cache[key]
+        if not on_dev:
+            x0b = torch.from_numpy(x0b).to(dev)
+            th = None if th is None else torch.from_numpy(th).to(dev)
+            z = None if z is None else torch.from_numpy(
+                np.ascontiguousarray(z.ravel(order="K" if z_stride else "F"))).to(dev)
+        out = torch.empty(B, dtype=torch.float64, device=dev)
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(self._lib.rodeo_cuda_loglik(
+                self._h, int(bool(use_draw)), B, _ptr(x0b), _ptr(th), _ptr(z), z_stride,
+                _ptr(d_thin), len(thin), _ptr(d_si), len(si), _ptr(d_Y), float(gamma),
+                _ptr(out), _ptr(status), stream))
+        self.status = status if on_dev else status.cpu().numpy()
+        res = out if on_dev else out.cpu().numpy()
+        return res[0] if single else res

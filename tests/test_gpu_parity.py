@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) by the Python front
+end, against (a) the golden vectors of the reference's own Python path, (b) the C oracle on
+the same seeded inputs, (c) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are the trajectory-scaled FP64 noise floors established in
+tests/test_oracle_golden.py (north-star: mean/variance rtol 1e-10, draws 1e-9 where the
+problem's conditioning allows two FP64 implementations to agree that closely)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from tests import workloads as wl
+from tests.common import load_golden, traj_err, var_err, ode_name
+
+pytestmark = pytest.mark.gpu
+
+
+def _kode_from_golden(g, name, **kw):
+    from rodeo_legacy_b200.cuda import KalmanODE
+    return KalmanODE(np.asfortranarray(g["W"]), float(g["tmin"]), float(g["tmax"]), int(g["N"]),
+                     ode_name(name), g["c"], np.asfortranarray(g["Q"]), np.asfortranarray(g["R"]), **kw)
+
+
+# (case, mean tol, var tol, draw tol, horizon for the tight mean/draw check)
+GOLDEN = [("chkrebtii_n100", 1e-10, 1e-8, 1e-5, None), ("chkrebtii_n200", 1e-10, 1e-8, 1e-5, None),
+          ("fitz_n400", 1e-10, 1e-9, 1e-9, None), ("lorenz_n5000", 1e-9, 1e-7, 1e-9, 2500),
+          ("lorenz_car_n600", 1e-7, 1e-6, 1e-7, None), ("mseir_n1000", 1e-10, 1e-8, 1e-7, None)]
+
+
+@pytest.mark.parametrize("name,mtol,vtol,xtol,hor", GOLDEN)
+def test_golden_vectors_host_and_device_paths(name, mtol, vtol, xtol, hor):
+    g = load_golden(name)
+    k = _kode_from_golden(g, name, z_state=np.asfortranarray(g["z"]))
+    batched = g["mu"].ndim == 3
+    B = g["mu"].shape[0] if batched else 1
+    x0 = np.tile(g["x0"], (B, 1)) if batched else np.asfortranarray(g["x0"])
+    theta = g["theta"] if "theta" in g else None
+    every = int(g["var_every"]) if "var_every" in g else 1
+    sl = slice(None) if hor is None else slice(0, hor + 1)
+    # host path (NumPy in / NumPy out), all three methods
+    x, mu, var = k.solve(x0, theta=theta)
+    mu2, var2 = k.solve_mv(x0, theta=theta)
+    x2 = k.solve_sim(x0, theta=theta)
+    assert x.shape == g["x"].shape and mu.shape == g["mu"].shape
+    assert not np.asarray(k.status).any()
+    np.testing.assert_array_equal(mu, mu2)
+    np.testing.assert_array_equal(var, var2)
+    np.testing.assert_array_equal(x, x2)
+    vthin = var[..., ::every, :, :]
+    assert traj_err(mu[..., sl, :], g["mu"][..., sl, :]).max() < mtol
+    assert traj_err(x[..., sl, :], g["x"][..., sl, :]).max() < xtol
+    assert var_err(vthin[..., 1:, :, :], g["var"][..., 1:, :, :]).max() < vtol
+    assert not var[..., 0, :, :].any()
+    if hor is not None:                     # chaotic tail: loose, as between any two FP64 codes
+        assert traj_err(mu, g["mu"]).max() < 1e-3 and traj_err(x, g["x"]).max() < 1e-3
+    # device path (torch CUDA in / out) gives the same bits
+    x0d = torch.from_numpy(np.ascontiguousarray(x0)).cuda()
+    thd = None if theta is None else torch.from_numpy(np.ascontiguousarray(theta)).cuda()
+    xd, mud, vard = k.solve(x0d, theta=thd)
+    assert xd.is_cuda and mud.shape == mu.shape
+    np.testing.assert_array_equal(mud.cpu().numpy(), mu)
+    np.testing.assert_array_equal(vard.cpu().numpy(), var)
+    np.testing.assert_array_equal(xd.cpu().numpy(), x)
+
+
+@pytest.mark.parametrize("maker,B,mtol,vtol,xtol", [
+    (wl.fitz_batch, 1500, 1e-10, 1e-9, 1e-9),
+    (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7),
+    (lambda B: wl.lorenz_batch(B, N=500, tmax=2.0), 130, 1e-9, 1e-7, 1e-8)])
+def test_seeded_batch_against_oracle(maker, B, mtol, vtol, xtol):
+    w, x0, theta = maker(B)
+    rng = np.random.default_rng(42)
+    z = np.asfortranarray(rng.standard_normal((len(w["x0"]), w["N"])))
+    k = wl.make_kode(w, z_state=z)
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+    x, mu, var = k.solve(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda())
+    x, mu, var = x.cpu().numpy(), mu.cpu().numpy(), var.cpu().numpy()
+    assert not k.status.any().item() and not ref["status"].any()
+    assert traj_err(mu, ref["mu"]).max() < mtol
+    assert var_err(var[:, 1:], ref["var"][:, 1:]).max() < vtol
+    assert traj_err(x, ref["x"]).max() < xtol
+    np.testing.assert_array_equal(var, np.swapaxes(var, -1, -2))     # exactly symmetric
+
+
+def test_per_system_draws_and_ragged_chunks():
+    """z per system; batch not a multiple of anything; workspace limit forcing 3 chunks."""
+    w, x0, theta = wl.fitz_batch(2500, seed=9)
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((2500, 6, 400))
+    k = wl.make_kode(w, z_state=z)
+    k.set_workspace_limit(1024 * k.history_bytes_per_system)          # 1024 systems per chunk
+    x = k.solve_sim(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda()).cpu().numpy()
+    assert k.launch_count == 6
+    pick = [0, 1, 1023, 1024, 2047, 2048, 2499]
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], z[pick], oracle.MODE_SIM)
+    assert traj_err(x[pick], ref["x"]).max() < 1e-9
+    # host path, chunked the same way, same bits
+    xh = k.solve_sim(x0, theta=theta)
+    np.testing.assert_array_equal(xh, x)
+
+
+def test_fitz_full_size_properties():
+    """BASELINE config 2 (65,536 theta draws, n_eval 400, solve_mv) through properties that
+    do not need the oracle at full size, plus an oracle spot-check of 48 systems."""
+    B = 65536
+    w, x0, theta = wl.fitz_batch(B)
+    k = wl.make_kode(w)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    mu, var = k.solve_mv(x0d, theta=thd)
+    torch.cuda.synchronize()
+    assert mu.shape == (B, 401, 6) and var.shape == (B, 401, 6, 6)
+    assert int(k.status.abs().sum()) == 0
+    assert bool(torch.isfinite(mu).all()) and bool(torch.isfinite(var).all())
+    # F5: the covariance path does not depend on theta -> identical bits across the batch
+    assert bool((var == var[0:1]).all())
+    assert bool((mu[:, 0] == x0d).all())
+    # idempotence / determinism: a second solve gives the same bits
+    mu2, var2 = k.solve_mv(x0d, theta=thd)
+    assert bool((mu2 == mu).all()) and bool((var2 == var).all())
+    del mu2, var2
+    # permutation equivariance: solving a shuffled batch shuffles the answers
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    mu3, _ = k.solve_mv(x0d[perm], theta=thd[perm])
+    assert bool((mu3 == mu[perm]).all())
+    del mu3
+    pick = np.random.default_rng(0).choice(B, 48, replace=False)
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], None, oracle.MODE_MV)
+    assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
+    assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-9
+    # smoothed variance never exceeds the filtered one at the end point, and is PSD-diagonal
+    assert bool((torch.diagonal(var[0], dim1=-2, dim2=-1) >= 0).all())
+
+
+@pytest.mark.parametrize("maker,B,mode", [
+    (lambda B: wl.lorenz_batch(B), 1024, "sim"),
+    (lambda B: wl.mseir_batch(B), 2048, "mv")])
+def test_wide_state_configs_at_full_length(maker, B, mode):
+    """BASELINE configs 3 and 4 at their full n_eval (5000 / 1000) on a reduced batch, with
+    an oracle spot-check; batch-size independence is covered by permutation equivariance."""
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    np.random.seed(2)
+    z = np.asfortranarray(np.random.randn(n, w["N"]))
+    k = wl.make_kode(w, z_state=z)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    pick = [0, 7, B // 2, B - 1]
+    po = wl.make_oracle_problem(w)
+    if mode == "sim":
+        x = k.solve_sim(x0d, theta=thd)
+        assert bool(torch.isfinite(x).all()) and int(k.status.abs().sum()) == 0
+        ref = oracle.solve_batch(po, x0[pick], theta[pick], z, oracle.MODE_SIM)
+        got = x[pick].cpu().numpy()
+        assert traj_err(got[:, :2501], ref["x"][:, :2501]).max() < 1e-8
+        assert traj_err(got, ref["x"]).max() < 1e-3
+        perm = torch.arange(B - 1, -1, -1, device="cuda")
+        assert bool((k.solve_sim(x0d[perm], theta=thd[perm]) == x[perm]).all())
+    else:
+        mu, var = k.solve_mv(x0d, theta=thd)
+        assert bool(torch.isfinite(mu).all()) and int(k.status.abs().sum()) == 0
+        assert bool((var == var[0:1]).all())
+        ref = oracle.solve_batch(po, x0[pick], theta[pick], None, oracle.MODE_MV)
+        assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
+        assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+
+
+def test_loglik_matches_oracle_and_sharded_sweep_layout():
+    g = load_golden("fitz_n400")
+    w, x0, theta = wl.fitz_batch(3000, seed=4)
+    z = np.asfortranarray(g["z"])
+    k = wl.make_kode(w, z_state=z)
+    ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    ll_mean = k.loglik(x0d, thd, Y, ind, [0, 3], gam)
+    ll_draw = k.loglik(x0d, thd, Y, ind, [0, 3], gam, use_draw=True)
+    pick = [0, 1, 999, 2999]
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], z, oracle.MODE_BOTH)
+    for got, key in ((ll_mean, "mu"), (ll_draw, "x")):
+        want = [oracle.loglik(ref[key][i], ind, [0, 3], Y, gam) for i in range(len(pick))]
+        np.testing.assert_allclose(got[pick].cpu().numpy(), want, rtol=1e-9)
+    # golden: the reference's own thinning + loglike on its own solver output
+    ll_g = k.loglik(np.tile(g["x0"], (4, 1)), g["theta"], Y, ind, [0, 3], gam)
+    np.testing.assert_allclose(ll_g, g["loglik_mu"], rtol=1e-8)
+    # equals the likelihood of the materialised mean
+    mu, _ = k.solve_mv(x0d[:64], theta=thd[:64])
+    manual = [oracle.loglik(m, ind, [0, 3], Y, gam) for m in mu.cpu().numpy()]
+    np.testing.assert_allclose(ll_mean[:64].cpu().numpy(), manual, rtol=1e-12)
+
+
+def test_reference_unit_test_pattern():
+    """tests/test_kalmanode.py:13-66 and tests/test_deterministic.py:11-46 of the reference,
+    with rodeo.cuda in place of the compiled backends."""
+    from scipy import integrate
+    rel_err = lambda a, b: np.sum(np.abs((a.ravel() - b.ravel()) / a.ravel()))
+    w = wl.chkrebtii(100)
+    np.random.seed(0)
+    from rodeo_legacy_b200 import rand_mat
+    z = rand_mat(100, 4)
+    k = wl.make_kode(w)
+    k.z_state = z
+    ksim = k.solve_sim(w["x0"])
+    ref = oracle.solve(wl.make_oracle_problem(w), w["x0"], None, z, oracle.MODE_SIM)["x"]
+    assert ksim.shape == (101, 4)
+    assert rel_err(ksim[:, 0], ref[:, 0]) <= 0.001
+    assert rel_err(ksim[1:, 1], ref[1:, 1]) <= 0.001
+    w3 = wl.chkrebtii(300)
+    k3 = wl.make_kode(w3)
+    sim = k3.solve_sim(w3["x0"])            # z auto-filled from the global RNG, like the reference
+    assert np.any(k3.z_state)
+    det = integrate.odeint(lambda x, t: [x[1], np.sin(2 * t) - x[0]], [-1, 0], np.linspace(0, 10, 301))
+    assert rel_err(sim[:, 0], det[:, 0]) <= 10.0
+    assert rel_err(sim[1:, 1], det[1:, 1]) <= 10.0
+    del k3.z_state
+    assert not np.any(k3.z_state)
+    mu, var = k3.solve_mv(w3["x0"])          # solve_mv must not touch the RNG / z
+    assert not np.any(k3.z_state) and mu.shape == (301, 4) and var.shape == (301, 4, 4)
+
+
+def test_error_behaviour():
+    w = wl.fitz()
+    k = wl.make_kode(w)
+    with pytest.raises(TypeError, match="incorrect shape"):
+        k.solve_mv(np.zeros(5), theta=w["theta0"])
+    with pytest.raises(TypeError, match="not f contiguous"):
+        k.wgt_state = np.ascontiguousarray(np.arange(36.0).reshape(6, 6))
+    with pytest.raises(TypeError, match="incorrect shape"):
+        k.var_state = np.zeros((5, 5), order="F")
+    with pytest.raises(TypeError, match="theta"):
+        k.solve_mv(w["x0"])
+    from rodeo_legacy_b200.cuda import KalmanODE
+    with pytest.raises(NotImplementedError, match="no compiled kernel"):
+        KalmanODE(np.zeros((2, 14), order="F"), 0, 1, 10, "fitz", np.zeros(14), np.eye(14), np.eye(14))
+    with pytest.raises(TypeError, match="registered device functor"):
+        KalmanODE(w["W"], 0, 40, 400, lambda *a: None, w["c"], w["Q"], w["R"])
+    # a non positive-definite prior is reported per system, not raised
+    kb = wl.make_kode(w)
+    kb.var_state = np.asfortranarray(-np.eye(6))
+    kb.solve_mv(w["x0"], theta=w["theta0"])
+    assert np.asarray(kb.status).any()
+    # property setter takes effect: W override per call (KalmanODE.pyx:441-442)
+    mu_a, _ = k.solve_mv(w["x0"], theta=w["theta0"])
+    mu_b, _ = k.solve_mv(w["x0"], W=w["W"], theta=w["theta0"])
+    np.testing.assert_array_equal(mu_a, mu_b)
+    # empty batch
+    mu_e, var_e = k.solve_mv(np.zeros((0, 6)), theta=np.zeros((0, 3)))
+    assert mu_e.shape == (0, 401, 6) and var_e.shape == (0, 401, 6, 6)
