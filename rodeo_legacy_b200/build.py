@@ -39,7 +39,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False, ptxas_info=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + [
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inl")) + [
         os.path.join(os.path.dirname(HERE), "include", "rodeo_cuda.h"), os.path.abspath(__file__)]
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     jobs = []

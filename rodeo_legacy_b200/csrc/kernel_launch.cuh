@@ -28,14 +28,14 @@ template <class Ode, int n, int IG, bool UNROLL>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_forward(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) forward_body<Ode, n, IG, UNROLL>(P, a, b);
+  if (b < a.B) Impl<UNROLL>::template forward<Ode, n, IG>(P, a, b);
 }
 
 template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK, bool UNROLL>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_backward(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) backward_body<Ode, n, DO_MEAN, DO_VAR, DO_SIM, LOGLIK, UNROLL>(P, a, b);
+  if (b < a.B) Impl<UNROLL>::template backward<Ode, n, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
 }
 
 inline dim3 grid_for(long B) { return dim3((unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock)); }

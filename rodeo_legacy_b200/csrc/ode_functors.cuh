@@ -6,7 +6,7 @@
 // written V*V*V/3 as examples/fitz.py:14), :18-28 (Lorenz63), :47-60 (MSEIR); the k-th
 // variable's value is X[k*p] with p = n_state / n_var, as in the reference.
 #pragma once
-#include "kalman_math.cuh"
+#include "kalman_common.cuh"
 
 namespace rodeo {
 

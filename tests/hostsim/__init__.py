@@ -21,7 +21,8 @@ def lib():
     if _lib is None:
         src = os.path.join(_HERE, "hostsim.cpp")
         deps = [src] + [os.path.join(_ROOT, "rodeo_legacy_b200", "csrc", f)
-                        for f in ("kalman_tps.cuh", "kalman_math.cuh", "ode_functors.cuh")]
+                        for f in ("kalman_tps.cuh", "kalman_tps.inl", "kalman_math.inl", "kalman_common.cuh",
+                                  "ode_functors.cuh")]
         if not os.path.exists(_LIB) or any(os.path.getmtime(d) > os.path.getmtime(_LIB) for d in deps):
             os.makedirs(os.path.dirname(_LIB), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w",

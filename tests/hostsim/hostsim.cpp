@@ -40,17 +40,17 @@ static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
   std::vector<double> hist((size_t)h.n_eval * (n + Sym<n>::size) * a.hist_stride);
   a.hist = hist.data();
   for (long b = 0; b < a.B; b++) {
-    if (ig == 0) forward_body<Ode, n, IG_PROBDE, UNROLL>(P, a, b);
-    else if (ig == 1) forward_body<Ode, n, IG_SCHOBERT, UNROLL>(P, a, b);
-    else forward_body<Ode, n, IG_CHKREBTII, UNROLL>(P, a, b);
+    if (ig == 0) Impl<UNROLL>::template forward<Ode, n, IG_PROBDE>(P, a, b);
+    else if (ig == 1) Impl<UNROLL>::template forward<Ode, n, IG_SCHOBERT>(P, a, b);
+    else Impl<UNROLL>::template forward<Ode, n, IG_CHKREBTII>(P, a, b);
   }
   for (long b = 0; b < a.B; b++) {
     switch (kind) {
-      case 0: backward_body<Ode, n, true, true, false, false, UNROLL>(P, a, b); break;
-      case 1: backward_body<Ode, n, false, false, true, false, UNROLL>(P, a, b); break;
-      case 2: backward_body<Ode, n, true, true, true, false, UNROLL>(P, a, b); break;
-      case 3: backward_body<Ode, n, true, false, false, true, UNROLL>(P, a, b); break;
-      case 4: backward_body<Ode, n, false, false, true, true, UNROLL>(P, a, b); break;
+      case 0: Impl<UNROLL>::template backward<Ode, n, true, true, false, false>(P, a, b); break;
+      case 1: Impl<UNROLL>::template backward<Ode, n, false, false, true, false>(P, a, b); break;
+      case 2: Impl<UNROLL>::template backward<Ode, n, true, true, true, false>(P, a, b); break;
+      case 3: Impl<UNROLL>::template backward<Ode, n, true, false, false, true>(P, a, b); break;
+      case 4: Impl<UNROLL>::template backward<Ode, n, false, false, true, true>(P, a, b); break;
       default: return -1;
     }
   }
