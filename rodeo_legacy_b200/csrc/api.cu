@@ -222,7 +222,6 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     SolveArgs a;
     memset(&a, 0, sizeof a);
     a.B = B;
-    a.hist_stride = cap;
     a.x0 = x0 + off * n;
     a.theta = theta ? theta + off * nth : nullptr;
     a.z = z ? z + off * z_stride : nullptr;

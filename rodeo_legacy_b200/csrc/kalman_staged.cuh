@@ -1,0 +1,205 @@
+// kalman_staged.cuh -- backward (smoother) kernel of the register family with the
+// filter history staged through shared memory by bulk async copies (TMA, cp.async.bulk +
+// mbarrier) and the outputs transposed through shared memory into coalesced 16-byte stores.
+//
+// One warp owns one tile of 32 systems (one thread per system) for the whole backward pass:
+//   * its history record for one time index is NE*32 contiguous doubles in HBM (layout in
+//     kalman_common.cuh).  Lane 0 issues ONE cp.async.bulk per record into a two-slot
+//     ring in shared memory, two time indices ahead of the one being processed, so the
+//     DRAM latency of the read stream is hidden without spending registers on prefetch;
+//     each lane then reads its own column of the record (bank-conflict free).
+//   * every lane writes the step's outputs (mean, covariance, draw) into its own row of a
+//     staging tile; the warp then stores the tile so that each system's contiguous run in
+//     the user-visible layout  out[b][t][...]  is written by neighbouring lanes as 16-byte
+//     pieces -- full 32-byte sectors instead of 32 scattered 8-byte stores per instruction.
+// Warps never synchronise with each other (no __syncthreads after the prologue).
+#pragma once
+#include <cstdint>
+
+#include "kalman_tps.cuh"
+#include "registry.cuh"
+
+namespace rodeo {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D), completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kStagedWarps = 2;  // warps per CTA
+constexpr int kStagedThreads = kStagedWarps * 32;
+
+template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+struct StagedLayout {
+  static constexpr int NE = n + Sym<n>::size;
+  static constexpr int REC = NE * kTile;                                         // doubles per record
+  static constexpr int OUTW = (DO_MEAN ? n : 0) + (DO_VAR ? n * n : 0) + (DO_SIM ? n : 0);
+  static constexpr int ROW = (OUTW + 1) / 2 * 2;                                 // row stride (even)
+  static constexpr int WARP_DOUBLES = 2 * REC + kTile * ROW + 2;                 // + 2 mbarriers
+  static constexpr size_t smem_bytes = (size_t)kStagedWarps * WARP_DOUBLES * sizeof(double);
+};
+
+// Store one output array from the staging tile: every system s of the tile owns a run of
+// W doubles at stage[s*ROW + OFF ..]; its destination is out + ((b0+s)*T1 + t)*W.
+template <int W, int OFF, int ROW>
+__device__ __forceinline__ void flush_runs(const double *stage, double *out, long b0, long B, long T1, int t,
+                                           int lane) {
+  constexpr bool V2 = (W % 2 == 0) && (OFF % 2 == 0);
+  if (V2) {
+    constexpr int C = W / 2;
+#pragma unroll
+    for (int q0 = 0; q0 < kTile * C; q0 += kTile) {
+      const int q = q0 + lane;
+      if (q < kTile * C) {
+        const int s = q / C, c = q - s * C;
+        if (b0 + s < B) {
+          const double2 v = *reinterpret_cast<const double2 *>(stage + s * ROW + OFF + 2 * c);
+          *reinterpret_cast<double2 *>(out + ((b0 + s) * T1 + t) * W + 2 * c) = v;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q0 = 0; q0 < kTile * W; q0 += kTile) {
+      const int q = q0 + lane;
+      if (q < kTile * W) {
+        const int s = q / W, c = q - s * W;
+        if (b0 + s < B) out[((b0 + s) * T1 + t) * W + c] = stage[s * ROW + OFF + c];
+      }
+    }
+  }
+}
+
+template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+__global__ void __launch_bounds__(kStagedThreads)
+kalman_backward_staged(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
+  using L = StagedLayout<n, DO_MEAN, DO_VAR, DO_SIM>;
+  constexpr int m = Ode::n_meas, REC = L::REC, ROW = L::ROW;
+  constexpr int OFF_VAR = DO_MEAN ? n : 0, OFF_X = OFF_VAR + (DO_VAR ? n * n : 0);
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long tile = (long)blockIdx.x * kStagedWarps + warp;
+  const long n_tiles = (a.B + kTile - 1) / kTile;
+  if (tile >= n_tiles) return;  // warp-uniform; warps are independent from here on
+  double *ring = smem + (size_t)warp * L::WARP_DOUBLES;
+  double *stage = ring + 2 * REC;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(stage + kTile * ROW);
+  const int N = P.n_eval;
+  const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
+  const bool valid = b < a.B;
+  const double *hist_tile = a.hist + (size_t)tile * N * REC;
+  constexpr uint32_t kRecBytes = REC * sizeof(double);
+
+  if (lane == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+      if (N - 1 - k >= 0) {
+        mbar_arrive_expect_tx(&bar[k], kRecBytes);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)(N - 1 - k) * REC, kRecBytes, &bar[k]);
+      }
+  }
+  reg::SmoothState<n> st;
+  st.fail = 0;
+  const double *zb = DO_SIM ? a.z + (valid ? b : b0) * a.z_stride : nullptr;
+  double *row = stage + lane * ROW;
+  uint32_t phase = 0;
+  for (int t = N; t >= 0; t--) {
+    if (t >= 1) {
+      const int k = (N - t) & 1;
+      mbar_wait(&bar[k], (phase >> k) & 1u);
+      phase ^= 1u << k;
+      const double *rec = ring + k * REC + lane;
+      const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
+      if (t == N)
+        reg::backward_terminal<n, DO_MEAN, DO_VAR, DO_SIM>(rec, zt, st);
+      else
+        reg::backward_step<n, m, DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, st);
+      __syncwarp();  // every lane is done with ring slot k
+      if (lane == 0 && t - 3 >= 0) {
+        mbar_arrive_expect_tx(&bar[k], kRecBytes);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)(t - 3) * REC, kRecBytes, &bar[k]);
+      }
+    } else {  // time index 0: the initial state is known, Sigma_0 = 0 (KalmanODE.pyx:445, 409)
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        const double v = valid ? a.x0[b * n + i] : 0.0;
+        if (DO_MEAN) st.mus[i] = v;
+        if (DO_SIM) st.x[i] = v;
+      }
+      if (DO_VAR) {
+#pragma unroll
+        for (int i = 0; i < Sym<n>::size; i++) st.Ss[i] = 0.0;
+      }
+    }
+    // ---- emit time index t through the staging tile ---------------------------------------
+    if (DO_MEAN) {
+#pragma unroll
+      for (int i = 0; i < n; i++) row[i] = st.mus[i];
+    }
+    if (DO_VAR) {
+#pragma unroll
+      for (int j = 0; j < n; j++)
+#pragma unroll
+        for (int i = 0; i < n; i++) row[OFF_VAR + j * n + i] = st.Ss[sidx<n>(i, j)];
+    }
+    if (DO_SIM) {
+#pragma unroll
+      for (int i = 0; i < n; i++) row[OFF_X + i] = st.x[i];
+    }
+    __syncwarp();
+    if (DO_MEAN) flush_runs<n, 0, ROW>(stage, a.mu_out, b0, a.B, T1, t, lane);
+    if (DO_VAR) flush_runs<n * n, OFF_VAR, ROW>(stage, a.var_out, b0, a.B, T1, t, lane);
+    if (DO_SIM) flush_runs<n, OFF_X, ROW>(stage, a.x_out, b0, a.B, T1, t, lane);
+    __syncwarp();
+  }
+  if (valid && a.status && st.fail && a.status[b] == 0) a.status[b] = st.fail;
+}
+
+template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  using L = StagedLayout<n, DO_MEAN, DO_VAR, DO_SIM>;
+  auto kern = kalman_backward_staged<Ode, n, DO_MEAN, DO_VAR, DO_SIM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
+  if (e != cudaSuccess) return e;
+  const long n_tiles = (a.B + kTile - 1) / kTile;
+  const unsigned grid = (unsigned)((n_tiles + kStagedWarps - 1) / kStagedWarps);
+  kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(make_prior<n, Ode::n_meas>(h), a);
+  return cudaGetLastError();
+}
+
+}  // namespace rodeo

@@ -5,11 +5,11 @@
 // time is spent; the product only ever launches them as CUDA kernels (kernels.cu).
 //
 // Data layout in HBM
-//   history  hist[s][e][b]   s = 0..N-1 (time index s+1), e = 0..NE-1, b = system:
-//            e < n        : mu_filt element e
-//            e >= n       : Sigma_filt packed upper element e-n
-//            batch-minor, so the 32 threads of a warp store/load 32 consecutive doubles
-//            per element (fully coalesced 256 B).  Only the FILTERED moments are kept:
+//   history  hist[tile][s][e][lane]  tile = b/32, lane = b%32, s = 0..N-1 (time index s+1),
+//            e = 0..NE-1:  e < n: mu_filt element e;  e >= n: Sigma_filt packed upper e-n.
+//            The 32 threads of a warp store 32 consecutive doubles per element (coalesced
+//            256 B) and a warp's whole record for one time index is contiguous (one bulk
+//            copy into shared memory in the backward pass).  Only the FILTERED moments are kept:
 //            the predicted moments the smoother needs (mu_{t+1|t}, Sigma_{t+1|t}) are
 //            recomputed from them in the backward pass with the same code the forward
 //            pass ran, which gives bit-identical values and saves
@@ -28,12 +28,11 @@ namespace rodeo {
 
 struct SolveArgs {
   long B;              // systems in this launch
-  long hist_stride;    // batch stride of the history (>= B)
   const double *x0;    // [B][n]
   const double *theta; // [B][n_theta] or nullptr
   const double *z;     // column-major (n x N) per system, or nullptr
   long z_stride;       // 0: shared, n*N: per system
-  double *hist;        // [N][NE][hist_stride]
+  double *hist;        // [ceil(B/32)][N][NE][32]
   double *x_out, *mu_out, *var_out;
   int *status;
   // thinned log-likelihood epilogue (examples/inference.py:54-56, 66-94)

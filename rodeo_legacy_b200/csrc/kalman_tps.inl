@@ -32,16 +32,16 @@ RD_UNROLL
     }
     int f = update<n, m>(P, mup, Sp, y, IG == IG_SCHOBERT);
     if (f && !fail) fail = f;
-    double *h = a.hist + (long)t * NE * a.hist_stride + b;
+    double *h = a.hist + hist_offset(b, t, N, NE);
 RD_UNROLL
     for (int i = 0; i < n; i++) {
       mu[i] = mup[i];
-      h[(long)i * a.hist_stride] = mup[i];
+      h[i * kTile] = mup[i];
     }
 RD_UNROLL
     for (int i = 0; i < NS; i++) {
       S[i] = Sp[i];
-      h[(long)(n + i) * a.hist_stride] = Sp[i];
+      h[(n + i) * kTile] = Sp[i];
     }
   }
   if (a.status) a.status[b] = fail;
@@ -62,169 +62,187 @@ RD_HD double loglik_terms(const SolveArgs &a, int d, const double *X) {
   return lp;
 }
 
-// Backward pass.  DO_MEAN / DO_VAR: smoothed mean / covariance recursion (smooth_mv);
-// DO_SIM: sampling recursion (smooth_sim); LOGLIK: no per-step output, accumulate the
-// thinned log-likelihood of the mean (DO_MEAN) or of the draw (DO_SIM) instead.
+// ---- backward pass ---------------------------------------------------------------------
+// State carried from time index t+1 to t.
+template <int n>
+struct SmoothState {
+  double mus[n];            // smoothed mean            (DO_MEAN)
+  double Ss[Sym<n>::size];  // smoothed covariance      (DO_VAR)
+  double x[n];              // posterior draw           (DO_SIM)
+  int fail;
+};
+
+// Terminal time index N (KalmanODE.pyx:445-449, 410-414).  `rec` points at this system's
+// history record for time index N (element e at rec[e * kTile]); zt = z[:, N-1].
+template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+RD_HD void backward_terminal(const double *rec, const double *zt_ptr, SmoothState<n> &st) {
+  constexpr int NS = Sym<n>::size;
+  double muf[n], Sf[NS];
+RD_UNROLL
+  for (int i = 0; i < n; i++) muf[i] = rec[i * kTile];
+RD_UNROLL
+  for (int i = 0; i < NS; i++) Sf[i] = rec[(n + i) * kTile];
+  if (DO_MEAN) {
+RD_UNROLL
+    for (int i = 0; i < n; i++) st.mus[i] = muf[i];
+  }
+  if (DO_VAR) {
+RD_UNROLL
+    for (int i = 0; i < NS; i++) st.Ss[i] = Sf[i];
+  }
+  if (DO_SIM) {
+    double zt[n];
+RD_UNROLL
+    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
+    int f = state_sim<n>(st.x, muf, Sf, zt);  // destroys Sf (not needed again)
+    if (f && !st.fail) st.fail = f;
+  }
+}
+
+// One smoother step t+1 -> t (KalmanODE.pyx:452-461 / 417-425 / 381-392).  `rec` is the
+// history record of time index t; zt_ptr = z[:, t-1].  The filtered covariance is re-read
+// from `rec` where it is needed a second time instead of being held in registers.
+template <int n, int m, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+RD_HD void backward_step(const Prior<n, m> &P, const double *rec, const double *zt_ptr,
+                         SmoothState<n> &st) {
+  constexpr int NS = Sym<n>::size;
+  const volatile double *rec2 = rec;  // second reads: do not keep Sigma_f live across the step
+  double muf[n], mup[n], Sp[NS], T[n * n], invd[n];
+  {
+    double Sf[NS];
+RD_UNROLL
+    for (int i = 0; i < n; i++) muf[i] = rec[i * kTile];
+RD_UNROLL
+    for (int i = 0; i < NS; i++) Sf[i] = rec[(n + i) * kTile];
+    // predicted moments at t+1, recomputed exactly as the forward pass computed them
+    predict_mean<n, m>(P, muf, mup);
+    predict_var<n, m, true>(P, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
+  }
+  if (DO_VAR) {                              // D = Sigma_s(t+1) - Sigma_p(t+1)  (:460)
+RD_UNROLL
+    for (int i = 0; i < NS; i++) st.Ss[i] -= Sp[i];
+  }
+  int f = chol_packed<n>(Sp, invd);          // LLT(Sigma_p)  (:457)
+  if (f && !st.fail) st.fail = f;
+RD_UNROLL
+  for (int j = 0; j < n; j++) chol_solve_vec<n>(Sp, invd, T + j, n);  // T~ (:458)
+  if (DO_MEAN) {                             // (:459, 463-464)
+    double dmu[n];
+RD_UNROLL
+    for (int k = 0; k < n; k++) dmu[k] = st.mus[k] - mup[k];
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double s = muf[i];
+RD_UNROLL
+      for (int k = 0; k < n; k++) s += T[k * n + i] * dmu[k];
+      st.mus[i] = s;
+    }
+  }
+  if (DO_SIM) {                              // KalmanTV.h:511-527
+    double dx[n], mt[n], V[NS], Sf[NS], zt[n];
+RD_UNROLL
+    for (int k = 0; k < n; k++) dx[k] = st.x[k] - mup[k];
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double s = muf[i];
+RD_UNROLL
+      for (int k = 0; k < n; k++) s += T[k * n + i] * dx[k];
+      mt[i] = s;
+    }
+RD_UNROLL
+    for (int i = 0; i < NS; i++) {
+      Sf[i] = rec2[(n + i) * kTile];
+      V[i] = Sf[i];
+    }
+    // V~ = Sigma_f - T~^T (Q Sigma_f): row k of Q Sigma_f is recomputed (T was overwritten)
+RD_UNROLL
+    for (int k = 0; k < n; k++) {
+      double Tk[n];
+RD_UNROLL
+      for (int j = 0; j < n; j++) {
+        double s = 0.0;
+RD_UNROLL
+        for (int l = 0; l < n; l++) s += P.Q[k * n + l] * Sf[sidx<n>(l, j)];
+        Tk[j] = s;
+      }
+RD_UNROLL
+      for (int i = 0; i < n; i++)
+RD_UNROLL
+        for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * Tk[j];
+    }
+RD_UNROLL
+    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
+    int f2 = state_sim<n>(st.x, mt, V, zt);
+    if (f2 && !st.fail) st.fail = f2;
+  }
+  if (DO_VAR) {                              // Sigma_s = Sigma_f + T~^T D T~  (:461-465)
+    double Sn[NS];
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double G[n];
+RD_UNROLL
+      for (int l = 0; l < n; l++) {
+        double s = 0.0;
+RD_UNROLL
+        for (int k = 0; k < n; k++) s += T[k * n + i] * st.Ss[sidx<n>(k, l)];
+        G[l] = s;
+      }
+RD_UNROLL
+      for (int j = i; j < n; j++) {
+        double s = rec2[(n + sidx<n>(i, j)) * kTile];
+RD_UNROLL
+        for (int l = 0; l < n; l++) s += G[l] * T[l * n + j];
+        Sn[sidx<n>(i, j)] = s;
+      }
+    }
+RD_UNROLL
+    for (int i = 0; i < NS; i++) st.Ss[i] = Sn[i];
+  }
+}
+
+// Generic backward pass: plain global loads and direct (per-thread) global stores.  Used by
+// the rolled family, by every log-likelihood kernel and by tests/hostsim; the register family's
+// solve_mv / solve_sim / solve kernels use the shared-memory staged version in
+// kalman_staged.cuh.  DO_MEAN / DO_VAR: smooth_mv; DO_SIM: smooth_sim; LOGLIK: no per-step
+// output, accumulate the thinned log-likelihood of the mean (DO_MEAN) or draw (DO_SIM).
 template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 RD_HD void backward_body(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
   constexpr int m = Ode::n_meas, NS = Sym<n>::size, NE = n + NS;
   const int N = P.n_eval;
   const long T1 = (long)N + 1;
-  double mus[n], Ss[NS], x[n];
-  int fail = 0;
+  SmoothState<n> st;
+  st.fail = 0;
   double lp = 0.0;
   int d = LOGLIK ? a.n_obs_times - 1 : -1;
   const double *zb = DO_SIM ? a.z + b * a.z_stride : nullptr;
   double *mu_o = (DO_MEAN && !LOGLIK) ? a.mu_out + b * T1 * n : nullptr;
   double *var_o = (DO_VAR && !LOGLIK) ? a.var_out + b * T1 * n * n : nullptr;
   double *x_o = (DO_SIM && !LOGLIK) ? a.x_out + b * T1 * n : nullptr;
-  {  // terminal step (KalmanODE.pyx:445-449, 410-414)
-    const double *h = a.hist + (long)(N - 1) * NE * a.hist_stride + b;
-    double muf[n], Sf[NS];
-RD_UNROLL
-    for (int i = 0; i < n; i++) muf[i] = h[(long)i * a.hist_stride];
-RD_UNROLL
-    for (int i = 0; i < NS; i++) Sf[i] = h[(long)(n + i) * a.hist_stride];
-    if (DO_MEAN) {
-RD_UNROLL
-      for (int i = 0; i < n; i++) mus[i] = muf[i];
-      if (!LOGLIK) {
-RD_UNROLL
-        for (int i = 0; i < n; i++) mu_o[(long)N * n + i] = muf[i];
-      }
-    }
-    if (DO_VAR) {
-RD_UNROLL
-      for (int i = 0; i < NS; i++) Ss[i] = Sf[i];
-      if (!LOGLIK) {
-RD_UNROLL
-        for (int j = 0; j < n; j++)
-RD_UNROLL
-          for (int i = 0; i < n; i++) var_o[((long)N * n + j) * n + i] = Sf[sidx<n>(i, j)];
-      }
-    }
-    if (DO_SIM) {
-      double zt[n];
-RD_UNROLL
-      for (int i = 0; i < n; i++) zt[i] = zb[(long)(N - 1) * n + i];
-      int f = state_sim<n>(x, muf, Sf, zt);  // destroys Sf (not needed again)
-      if (f && !fail) fail = f;
-      if (!LOGLIK) {
-RD_UNROLL
-        for (int i = 0; i < n; i++) x_o[(long)N * n + i] = x[i];
-      }
-    }
-    if (LOGLIK) {
-      while (d >= 0 && a.thin_index[d] == N) {
-        lp += loglik_terms<n>(a, d, DO_SIM ? x : mus);
-        d--;
-      }
-    }
-  }
-  for (int t = N - 1; t >= 1; t--) {  // KalmanODE.pyx:452-461 / 417-425 / 381-392
-    const double *h = a.hist + (long)(t - 1) * NE * a.hist_stride + b;
-    double muf[n], Sf[NS], mup[n], Sp[NS], T[n * n], invd[n];
-RD_UNROLL
-    for (int i = 0; i < n; i++) muf[i] = h[(long)i * a.hist_stride];
-RD_UNROLL
-    for (int i = 0; i < NS; i++) Sf[i] = h[(long)(n + i) * a.hist_stride];
-    // predicted moments at t+1, recomputed exactly as the forward pass computed them
-    predict_mean<n, m>(P, muf, mup);
-    predict_var<n, m, true>(P, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
-    if (DO_VAR) {                                   // D = Sigma_s(t+1) - Sigma_p(t+1)  (:460)
-RD_UNROLL
-      for (int i = 0; i < NS; i++) Ss[i] -= Sp[i];
-    }
-    int f = chol_packed<n>(Sp, invd);       // LLT(Sigma_p)  (:457)
-    if (f && !fail) fail = f;
-RD_UNROLL
-    for (int j = 0; j < n; j++) chol_solve_vec<n>(Sp, invd, T + j, n);  // T~ (:458)
-    if (DO_MEAN) {                                  // (:459, 463-464)
-      double dmu[n];
-RD_UNROLL
-      for (int k = 0; k < n; k++) dmu[k] = mus[k] - mup[k];
-RD_UNROLL
-      for (int i = 0; i < n; i++) {
-        double s = muf[i];
-RD_UNROLL
-        for (int k = 0; k < n; k++) s += T[k * n + i] * dmu[k];
-        mus[i] = s;
-      }
-    }
-    if (DO_SIM) {                                   // KalmanTV.h:511-527
-      double dx[n], mt[n], V[NS], zt[n];
-RD_UNROLL
-      for (int k = 0; k < n; k++) dx[k] = x[k] - mup[k];
-RD_UNROLL
-      for (int i = 0; i < n; i++) {
-        double s = muf[i];
-RD_UNROLL
-        for (int k = 0; k < n; k++) s += T[k * n + i] * dx[k];
-        mt[i] = s;
-      }
-RD_UNROLL
-      for (int i = 0; i < NS; i++) V[i] = Sf[i];
-      // V~ = Sigma_f - T~^T (Q Sigma_f): row k of Q Sigma_f is recomputed (T was overwritten)
-RD_UNROLL
-      for (int k = 0; k < n; k++) {
-        double Tk[n];
-RD_UNROLL
-        for (int j = 0; j < n; j++) {
-          double s = 0.0;
-RD_UNROLL
-          for (int l = 0; l < n; l++) s += P.Q[k * n + l] * Sf[sidx<n>(l, j)];
-          Tk[j] = s;
-        }
-RD_UNROLL
-        for (int i = 0; i < n; i++)
-RD_UNROLL
-          for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * Tk[j];
-      }
-RD_UNROLL
-      for (int i = 0; i < n; i++) zt[i] = zb[(long)(t - 1) * n + i];
-      int f2 = state_sim<n>(x, mt, V, zt);
-      if (f2 && !fail) fail = f2;
-      if (!LOGLIK) {
-RD_UNROLL
-        for (int i = 0; i < n; i++) x_o[(long)t * n + i] = x[i];
-      }
-    }
-    if (DO_VAR) {                                   // Sigma_s = Sigma_f + T~^T D T~  (:461-465)
-RD_UNROLL
-      for (int i = 0; i < n; i++) {
-        double G[n];
-RD_UNROLL
-        for (int l = 0; l < n; l++) {
-          double s = 0.0;
-RD_UNROLL
-          for (int k = 0; k < n; k++) s += T[k * n + i] * Ss[sidx<n>(k, l)];
-          G[l] = s;
-        }
-RD_UNROLL
-        for (int j = i; j < n; j++) {
-          double s = Sf[sidx<n>(i, j)];
-RD_UNROLL
-          for (int l = 0; l < n; l++) s += G[l] * T[l * n + j];
-          Sf[sidx<n>(i, j)] = s;
-        }
-      }
-RD_UNROLL
-      for (int i = 0; i < NS; i++) Ss[i] = Sf[i];
-    }
+  for (int t = N; t >= 1; t--) {
+    const double *rec = a.hist + hist_offset(b, t - 1, N, NE);
+    const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
+    if (t == N)
+      backward_terminal<n, DO_MEAN, DO_VAR, DO_SIM>(rec, zt, st);
+    else
+      backward_step<n, m, DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, st);
     if (!LOGLIK) {
       if (DO_MEAN) {
 RD_UNROLL
-        for (int i = 0; i < n; i++) mu_o[(long)t * n + i] = mus[i];
+        for (int i = 0; i < n; i++) mu_o[(long)t * n + i] = st.mus[i];
+      }
+      if (DO_SIM) {
+RD_UNROLL
+        for (int i = 0; i < n; i++) x_o[(long)t * n + i] = st.x[i];
       }
       if (DO_VAR) {
 RD_UNROLL
         for (int j = 0; j < n; j++)
 RD_UNROLL
-          for (int i = 0; i < n; i++) var_o[((long)t * n + j) * n + i] = Ss[sidx<n>(i, j)];
+          for (int i = 0; i < n; i++) var_o[((long)t * n + j) * n + i] = st.Ss[sidx<n>(i, j)];
       }
     } else {
       while (d >= 0 && a.thin_index[d] == t) {
-        lp += loglik_terms<n>(a, d, DO_SIM ? x : mus);
+        lp += loglik_terms<n>(a, d, DO_SIM ? st.x : st.mus);
         d--;
       }
     }
@@ -253,6 +271,5 @@ RD_UNROLL
     const double cst = -0.91893853320467274178 - log(a.gamma);
     a.loglik[b] = lp + cst * (double)(a.n_obs_times * a.n_obs_comp);
   }
-  if (a.status && fail && a.status[b] == 0) a.status[b] = fail;
+  if (a.status && st.fail && a.status[b] == 0) a.status[b] = st.fail;
 }
-

@@ -24,6 +24,10 @@ inline Prior<n, m> make_prior(const HostPrior &h) {
   return P;
 }
 
+}  // namespace rodeo
+#include "kalman_staged.cuh"
+namespace rodeo {
+
 template <class Ode, int n, int IG, bool UNROLL>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_forward(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
@@ -64,9 +68,15 @@ KernelSet make_kernel_set(const char *name) {
   k.forward[IG_PROBDE] = launch_forward<Ode, n, IG_PROBDE, UNROLL>;
   k.forward[IG_SCHOBERT] = launch_forward<Ode, n, IG_SCHOBERT, UNROLL>;
   k.forward[IG_CHKREBTII] = launch_forward<Ode, n, IG_CHKREBTII, UNROLL>;
-  k.backward[BK_MV] = launch_backward<Ode, n, true, true, false, false, UNROLL>;
-  k.backward[BK_SIM] = launch_backward<Ode, n, false, false, true, false, UNROLL>;
-  k.backward[BK_BOTH] = launch_backward<Ode, n, true, true, true, false, UNROLL>;
+  if constexpr (UNROLL) {  // register family: history and outputs staged through shared memory
+    k.backward[BK_MV] = launch_backward_staged<Ode, n, true, true, false>;
+    k.backward[BK_SIM] = launch_backward_staged<Ode, n, false, false, true>;
+    k.backward[BK_BOTH] = launch_backward_staged<Ode, n, true, true, true>;
+  } else {
+    k.backward[BK_MV] = launch_backward<Ode, n, true, true, false, false, UNROLL>;
+    k.backward[BK_SIM] = launch_backward<Ode, n, false, false, true, false, UNROLL>;
+    k.backward[BK_BOTH] = launch_backward<Ode, n, true, true, true, false, UNROLL>;
+  }
   k.backward[BK_LL_MEAN] = launch_backward<Ode, n, true, false, false, true, UNROLL>;
   k.backward[BK_LL_DRAW] = launch_backward<Ode, n, false, false, true, true, UNROLL>;
   k.hist_elems = n + Sym<n>::size;

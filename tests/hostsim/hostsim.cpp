@@ -37,7 +37,7 @@ static Prior<n, m> make_prior(const HostPrior &h) {
 template <class Ode, int n, bool UNROLL>
 static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
   auto P = make_prior<n, Ode::n_meas>(h);
-  std::vector<double> hist((size_t)h.n_eval * (n + Sym<n>::size) * a.hist_stride);
+  std::vector<double> hist((size_t)h.n_eval * (n + Sym<n>::size) * ((a.B + 31) / 32 * 32));
   a.hist = hist.data();
   for (long b = 0; b < a.B; b++) {
     if (ig == 0) Impl<UNROLL>::template forward<Ode, n, IG_PROBDE>(P, a, b);
@@ -67,7 +67,6 @@ extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, dou
   SolveArgs a;
   memset(&a, 0, sizeof a);
   a.B = B;
-  a.hist_stride = (B + 31) / 32 * 32;
   a.x0 = x0;
   a.theta = theta;
   a.z = z;
