@@ -78,6 +78,11 @@ enum { RODEO_INTERROGATE_PROBDE = 0, RODEO_INTERROGATE_SCHOBERT = 1, RODEO_INTER
 /* fields selectable in rodeo_cuda_problem_set */
 enum { RODEO_FIELD_WGT_MEAS = 0, RODEO_FIELD_MU_STATE = 1, RODEO_FIELD_WGT_STATE = 2, RODEO_FIELD_VAR_STATE = 3 };
 
+/* problem flags */
+enum {
+  RODEO_FLAG_FORCE_DENSE = 1 /* never use the block-diagonal kernel family, even when Q, R, W allow it */
+};
+
 /* error codes */
 enum {
   RODEO_OK = 0,
@@ -95,7 +100,7 @@ typedef struct {
   int32_t n_eval;         /* N: number of steps; outputs have N+1 time points */
   int32_t ode;            /* RODEO_ODE_* */
   int32_t interrogate;    /* RODEO_INTERROGATE_* */
-  int32_t reserved;       /* must be 0 */
+  int32_t flags;          /* RODEO_FLAG_* or 0 */
   double tmin, tmax;
   const double *wgt_meas;  /* host, column-major (m x n) */
   const double *wgt_state; /* host, column-major (n x n) */
@@ -110,7 +115,10 @@ const char *rodeo_cuda_last_error(void);
 /* n_meas / n_theta of a registered RHS, or RODEO_E_INVALID */
 int rodeo_cuda_ode_n_meas(int ode);
 int rodeo_cuda_ode_n_theta(int ode);
-/* 1 if a kernel is compiled for this combination, else 0 */
+/* Bit 0: a dense kernel set is compiled for this combination (any Q, R, W).  Bit 1: a
+ * block-diagonal set is compiled (used automatically when wgt_state / var_state are block
+ * diagonal with n_meas equal blocks and row a of wgt_meas lies inside block a -- what
+ * ibm_init / car_init + indep_init + zero_pad always produce).  0: unsupported. */
 int rodeo_cuda_supported(int ode, int n_state, int n_meas, int interrogate);
 
 /* Creates a problem on the CURRENT CUDA device.  The descriptor's host arrays are copied. */
@@ -118,6 +126,10 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *desc, rodeo_problem **ou
 int rodeo_cuda_problem_destroy(rodeo_problem *p);
 /* Overwrite one of the prior / measurement arrays (host pointer, column-major). */
 int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *host_values);
+
+/* Which kernel family the handle currently uses (it is re-selected whenever a field is set). */
+int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t *registers,
+                            int32_t *hist_doubles_per_step);
 
 /* ---- workspace (filter history streamed through HBM between the two passes) ------ */
 /* Bytes of history one system needs for this problem. */

@@ -36,6 +36,7 @@ struct rodeo_problem {
   double tmin, tmax;
   std::vector<double> W, Q, c, R;  // column-major host copies
   const KernelSet *ks;
+  int flags = 0;
   void *ws = nullptr;
   size_t ws_bytes = 0;
   size_t ws_limit = (size_t)48 << 30;
@@ -53,6 +54,39 @@ struct rodeo_problem {
 static const int kOdeMeas[4] = {1, 2, 3, 5};
 static const int kOdeTheta[4] = {0, 3, 3, 6};
 
+// Q, R block diagonal with m blocks of size n/m and row a of W supported inside block a?
+static bool is_block_diagonal(const rodeo_problem *p) {
+  const int n = p->n, m = p->m;
+  if (n % m) return false;
+  const int bs = n / m;
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++)
+      if (i / bs != j / bs && (p->Q[i + (size_t)j * n] != 0.0 || p->R[i + (size_t)j * n] != 0.0)) return false;
+  for (int j = 0; j < n; j++)
+    for (int a = 0; a < m; a++)
+      if (j / bs != a && p->W[a + (size_t)j * m] != 0.0) return false;
+  return true;
+}
+
+// Pick the kernel family for the current (Q, R, W): block-diagonal when the structure is
+// there (and not disabled by RODEO_FLAG_FORCE_DENSE), dense otherwise.
+static int select_kernel_set(rodeo_problem *p) {
+  const KernelSet *dense = find_kernel_set(p->ode, p->n, false), *bd = find_kernel_set(p->ode, p->n, true);
+  const bool structured = is_block_diagonal(p);
+  const KernelSet *ks = nullptr;
+  if (bd && structured && !(p->flags & RODEO_FLAG_FORCE_DENSE)) ks = bd;
+  else if (dense) ks = dense;
+  if (!ks) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "no compiled kernel for ode=%d n_state=%d n_meas=%d%s (see rodeo_cuda_supported)", p->ode, p->n,
+             p->m, bd ? " with a prior that is not block diagonal" : "");
+    return fail(RODEO_E_UNSUPPORTED, buf);
+  }
+  p->ks = ks;
+  return RODEO_OK;
+}
+
 extern "C" {
 
 int rodeo_cuda_abi_version(void) { return RODEO_CUDA_ABI_VERSION; }
@@ -61,9 +95,12 @@ const char *rodeo_cuda_last_error(void) { return g_err.c_str(); }
 int rodeo_cuda_ode_n_meas(int ode) { return (ode >= 0 && ode < 4) ? kOdeMeas[ode] : RODEO_E_INVALID; }
 int rodeo_cuda_ode_n_theta(int ode) { return (ode >= 0 && ode < 4) ? kOdeTheta[ode] : RODEO_E_INVALID; }
 
+// 1: a dense kernel set exists (any Q, R, W); 2: only a block-diagonal set exists (the prior
+// must be block diagonal with n_meas blocks and W row a inside block a); 3: both; 0: none.
 int rodeo_cuda_supported(int ode, int n_state, int n_meas, int interrogate) {
-  const KernelSet *k = find_kernel_set(ode, n_state);
-  return (k && k->m == n_meas && interrogate >= 0 && interrogate <= 2) ? 1 : 0;
+  if (interrogate < 0 || interrogate > 2) return 0;
+  const KernelSet *d = find_kernel_set(ode, n_state, false), *b = find_kernel_set(ode, n_state, true);
+  return ((d && d->m == n_meas) ? 1 : 0) | ((b && b->m == n_meas) ? 2 : 0);
 }
 
 int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) {
@@ -75,14 +112,7 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) 
     return fail(RODEO_E_INVALID, "wgt_meas, wgt_state, mu_state, var_state must be set");
   if (d->ode < 0 || d->ode > 3) return fail(RODEO_E_INVALID, "unknown ode id");
   if (d->interrogate < 0 || d->interrogate > 2) return fail(RODEO_E_INVALID, "unknown interrogate id");
-  const KernelSet *ks = find_kernel_set(d->ode, d->n_state);
-  if (!ks || ks->m != d->n_meas) {
-    char buf[256];
-    snprintf(buf, sizeof buf,
-             "no compiled kernel for ode=%d n_state=%d n_meas=%d (see rodeo_cuda_supported)", d->ode,
-             d->n_state, d->n_meas);
-    return fail(RODEO_E_UNSUPPORTED, buf);
-  }
+  if (d->n_meas != kOdeMeas[d->ode]) return fail(RODEO_E_INVALID, "n_meas does not match the ode");
   int dev = 0;
   CK(cudaGetDevice(&dev));
   rodeo_problem *p = new rodeo_problem();
@@ -94,11 +124,16 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) 
   p->device = dev;
   p->tmin = d->tmin;
   p->tmax = d->tmax;
-  p->ks = ks;
+  p->flags = d->flags;
   p->W.assign(d->wgt_meas, d->wgt_meas + (size_t)p->m * p->n);
   p->Q.assign(d->wgt_state, d->wgt_state + (size_t)p->n * p->n);
   p->c.assign(d->mu_state, d->mu_state + p->n);
   p->R.assign(d->var_state, d->var_state + (size_t)p->n * p->n);
+  int rc = select_kernel_set(p);
+  if (rc) {
+    delete p;
+    return rc;
+  }
   *out = p;
   return RODEO_OK;
 }
@@ -129,6 +164,15 @@ int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *v) {
     case RODEO_FIELD_VAR_STATE: p->R.assign(v, v + (size_t)p->n * p->n); break;
     default: return fail(RODEO_E_INVALID, "unknown field");
   }
+  return select_kernel_set(p);   // the structure (hence the kernel family) may have changed
+}
+
+int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t *registers,
+                            int32_t *hist_doubles_per_step) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (blockdiag) *blockdiag = p->ks->blockdiag;
+  if (registers) *registers = p->ks->registers;
+  if (hist_doubles_per_step) *hist_doubles_per_step = p->ks->hist_elems;
   return RODEO_OK;
 }
 

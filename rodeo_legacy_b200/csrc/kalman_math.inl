@@ -2,17 +2,19 @@
 //
 // Included TWICE by kalman_tps.cuh, once per loop policy (the RD_UNROLL macro):
 //   namespace rodeo::reg  RD_UNROLL = "#pragma unroll"    every loop fully unrolled, all
-//                         matrices in registers (n_state <= 6)
+//                         matrices in registers
 //   namespace rodeo::loc  RD_UNROLL = "#pragma unroll 1"  loops rolled, matrices in local
-//                         memory (any n_state; slower)
+//                         memory (any n_state; slow -- the dense fallback for n_state > 6)
 // One thread owns one system: every matrix below is a private array of the calling thread.
 // Symmetric matrices (Sigma, R, Cholesky factors) are PACKED, upper triangle row-major:
-// element (i, j), i <= j, at i*(2n-i-1)/2 + j.  Dense matrices are row-major.
+// element (i, j), i <= j, at i*(2n-i-1)/2 + j.  Dense matrices are row-major.  Problem
+// constants (Q, c, R, W) are passed as pointers INTO the __grid_constant__ kernel parameter,
+// so after unrolling each coefficient is an immediate constant-bank operand.
 //
 // Arithmetic follows the reference's KalmanTV (rodeo/eigen/KalmanTV.h): predict :280-294,
 // update :324-357, smooth_mv :447-467, smooth_sim :503-533, state_sim :619-628, with the
 // probde interrogation of rodeo/eigen/KalmanTVODE.h:333-341.  Only the summation order
-// and the use of symmetry differ (results agree to FP64 rounding).
+// and the use of symmetry / block structure differ (results agree to FP64 rounding).
 
 // In-place lower Cholesky of a packed symmetric matrix (right-looking):
 // on exit A(i, j), i >= j holds L(i, j) and invd[j] = 1 / L(j, j).
@@ -59,22 +61,22 @@ RD_UNROLL
 }
 
 // mu_pred = Q mu + c                                         (KalmanTV.h:287-288)
-template <int n, int m>
-RD_HD void predict_mean(const Prior<n, m> &P, const double *mu, double *mup) {
+template <int n>
+RD_HD void predict_mean(const double *Q, const double *c, const double *mu, double *mup) {
 RD_UNROLL
   for (int i = 0; i < n; i++) {
-    double s = P.c[i];
+    double s = c[i];
 RD_UNROLL
-    for (int k = 0; k < n; k++) s += P.Q[i * n + k] * mu[k];
+    for (int k = 0; k < n; k++) s += Q[i * n + k] * mu[k];
     mup[i] = s;
   }
 }
 
 // Sp = Q S Q^T + R (packed)                                  (KalmanTV.h:290-292)
-// If T != nullptr the full product T = Q S (row-major n x n) is also returned
-// (it is the smoother's Q Sigma_f^T, KalmanTV.h:456).
-template <int n, int m, bool KEEP_T>
-RD_HD void predict_var(const Prior<n, m> &P, const double *S, double *Sp, double *T) {
+// With KEEP_T the full product T = Q S (row-major n x n) is also returned (it is the
+// smoother's Q Sigma_f^T, KalmanTV.h:456).
+template <int n, bool KEEP_T>
+RD_HD void predict_var(const double *Q, const double *R, const double *S, double *Sp, double *T) {
 RD_UNROLL
   for (int i = 0; i < n; i++) {
     double Ti[n];
@@ -82,26 +84,26 @@ RD_UNROLL
     for (int k = 0; k < n; k++) {
       double s = 0.0;
 RD_UNROLL
-      for (int l = 0; l < n; l++) s += P.Q[i * n + l] * S[sidx<n>(l, k)];
+      for (int l = 0; l < n; l++) s += Q[i * n + l] * S[sidx<n>(l, k)];
       Ti[k] = s;
       if (KEEP_T) T[i * n + k] = s;
     }
 RD_UNROLL
     for (int j = i; j < n; j++) {
-      double s = P.R[sidx<n>(i, j)];
+      double s = R[sidx<n>(i, j)];
 RD_UNROLL
-      for (int k = 0; k < n; k++) s += Ti[k] * P.Q[j * n + k];
+      for (int k = 0; k < n; k++) s += Ti[k] * Q[j * n + k];
       Sp[sidx<n>(i, j)] = s;
     }
   }
 }
 
-// Measurement update with the probde / schobert interrogation variance:
+// Dense measurement update with the probde / schobert interrogation variance:
 //   A = W Sp; H = A W^T (probde) or 0 (schobert); S = A W^T + H; K~ = S^{-1} A;
 //   mu_f = mu_p + K~^T (y - W mu_p); Sf = Sp - K~^T A.
-// (KalmanTVODE.h:336-339, KalmanTV.h:332-354).  Sp is updated in place to Sf, mup to muf.
+// (KalmanTVODE.h:336-339, KalmanTV.h:332-354).  S (Sp) and mu (mup) are updated in place.
 template <int n, int m>
-RD_HD int update(const Prior<n, m> &P, double *mu, double *S, const double *y, bool zero_H) {
+RD_HD int update_dense(const double *W, double *mu, double *S, const double *y, bool zero_H) {
   double A[m * n];
 RD_UNROLL
   for (int a = 0; a < m; a++)
@@ -109,7 +111,7 @@ RD_UNROLL
     for (int j = 0; j < n; j++) {
       double s = 0.0;
 RD_UNROLL
-      for (int k = 0; k < n; k++) s += P.W[a * n + k] * S[sidx<n>(k, j)];
+      for (int k = 0; k < n; k++) s += W[a * n + k] * S[sidx<n>(k, j)];
       A[a * n + j] = s;
     }
   double Sm[Sym<m>::size], invd[m];
@@ -119,7 +121,7 @@ RD_UNROLL
     for (int b = a; b < m; b++) {
       double s = 0.0;
 RD_UNROLL
-      for (int j = 0; j < n; j++) s += A[a * n + j] * P.W[b * n + j];
+      for (int j = 0; j < n; j++) s += A[a * n + j] * W[b * n + j];
       Sm[sidx<m>(a, b)] = zero_H ? s : s + s;
     }
   int fail = chol_packed<m>(Sm, invd);
@@ -128,7 +130,7 @@ RD_UNROLL
   for (int a = 0; a < m; a++) {
     double s = 0.0;
 RD_UNROLL
-    for (int k = 0; k < n; k++) s += P.W[a * n + k] * mu[k];
+    for (int k = 0; k < n; k++) s += W[a * n + k] * mu[k];
     e[a] = y[a] - s;
   }
   // K = S^{-1} A column by column; consume each column immediately
@@ -142,7 +144,7 @@ RD_UNROLL
 RD_UNROLL
     for (int a = 0; a < m; a++) s += kj[a] * e[a];
     mu[j] = s;
-    // Sf(i, j) for i <= j: Sp(i, j) - sum_a K(a, i) A(a, j) = Sp(i,j) - sum_a A(a,i) K(a,j)
+    // Sf(i, j), i <= j: Sp(i, j) - sum_a K(a, i) A(a, j) = Sp(i, j) - sum_a A(a, i) K(a, j)
 RD_UNROLL
     for (int i = 0; i <= j; i++) {
       double v = S[sidx<n>(i, j)];
@@ -150,6 +152,38 @@ RD_UNROLL
       for (int a = 0; a < m; a++) v -= A[a * n + i] * kj[a];
       S[sidx<n>(i, j)] = v;
     }
+  }
+  return fail;
+}
+
+// The same update for ONE diagonal block with a scalar measurement  y_a = w^T x_a:
+//   A = w^T Sp; s = A w (+ A w under probde); K = A / s; mu_f = mu_p + K (y_a - w^T mu_p);
+//   Sf = Sp - A^T K.   The m x m Cholesky of the dense update degenerates to one division.
+template <int p>
+RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool zero_H) {
+  double A[p];
+  double s = 0.0, e = ya;
+RD_UNROLL
+  for (int j = 0; j < p; j++) {
+    double v = 0.0;
+RD_UNROLL
+    for (int k = 0; k < p; k++) v += w[k] * S[sidx<p>(k, j)];
+    A[j] = v;
+  }
+RD_UNROLL
+  for (int j = 0; j < p; j++) {
+    s += A[j] * w[j];
+    e -= w[j] * mu[j];
+  }
+  if (!zero_H) s = s + s;
+  const int fail = (s > 0.0) ? 0 : 1;
+  const double inv = 1.0 / s;
+RD_UNROLL
+  for (int j = 0; j < p; j++) {
+    const double kj = A[j] * inv;
+    mu[j] += kj * e;
+RD_UNROLL
+    for (int i = 0; i <= j; i++) S[sidx<p>(i, j)] -= A[i] * kj;
   }
   return fail;
 }
@@ -169,3 +203,134 @@ RD_UNROLL
   return fail;
 }
 
+// ---- smoother, one n-dimensional (block of a) system --------------------------------------
+// History elements are read through (rec_mu, rec_S): element i at ptr[i * kTile].
+
+// Terminal time index N (KalmanODE.pyx:445-449, 410-414); zt = z[:, N-1] (this block's rows).
+template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+RD_HD int smooth_terminal(const double *rec_mu, const double *rec_S, const double *zt_ptr, double *mus,
+                          double *Ss, double *x) {
+  constexpr int NS = Sym<n>::size;
+  double muf[n], Sf[NS];
+  int fail = 0;
+RD_UNROLL
+  for (int i = 0; i < n; i++) muf[i] = rec_mu[i * kTile];
+RD_UNROLL
+  for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * kTile];
+  if (DO_MEAN) {
+RD_UNROLL
+    for (int i = 0; i < n; i++) mus[i] = muf[i];
+  }
+  if (DO_VAR) {
+RD_UNROLL
+    for (int i = 0; i < NS; i++) Ss[i] = Sf[i];
+  }
+  if (DO_SIM) {
+    double zt[n];
+RD_UNROLL
+    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
+    fail = state_sim<n>(x, muf, Sf, zt);  // destroys Sf (not needed again)
+  }
+  return fail;
+}
+
+// One smoother step t+1 -> t (KalmanODE.pyx:452-461 / 417-425 / 381-392); zt_ptr = z[:, t-1].
+// The filtered covariance is re-read from the record where it is needed a second time instead
+// of being held in registers across the Cholesky / triangular solves.
+template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+RD_HD int smooth_step(const double *Q, const double *c, const double *R, const double *rec_mu,
+                      const double *rec_S, const double *zt_ptr, double *mus, double *Ss, double *x) {
+  constexpr int NS = Sym<n>::size;
+  const volatile double *rec_S2 = rec_S;  // second reads: do not keep Sigma_f live
+  double muf[n], mup[n], Sp[NS], T[n * n], invd[n];
+  {
+    double Sf[NS];
+RD_UNROLL
+    for (int i = 0; i < n; i++) muf[i] = rec_mu[i * kTile];
+RD_UNROLL
+    for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * kTile];
+    // predicted moments at t+1, recomputed exactly as the forward pass computed them
+    predict_mean<n>(Q, c, muf, mup);
+    predict_var<n, true>(Q, R, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
+  }
+  if (DO_VAR) {                              // D = Sigma_s(t+1) - Sigma_p(t+1)  (:460)
+RD_UNROLL
+    for (int i = 0; i < NS; i++) Ss[i] -= Sp[i];
+  }
+  int fail = chol_packed<n>(Sp, invd);       // LLT(Sigma_p)  (:457)
+RD_UNROLL
+  for (int j = 0; j < n; j++) chol_solve_vec<n>(Sp, invd, T + j, n);  // T~ (:458)
+  if (DO_MEAN) {                             // (:459, 463-464)
+    double dmu[n];
+RD_UNROLL
+    for (int k = 0; k < n; k++) dmu[k] = mus[k] - mup[k];
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double s = muf[i];
+RD_UNROLL
+      for (int k = 0; k < n; k++) s += T[k * n + i] * dmu[k];
+      mus[i] = s;
+    }
+  }
+  if (DO_SIM) {                              // KalmanTV.h:511-527
+    double dx[n], mt[n], V[NS], Sf[NS], zt[n];
+RD_UNROLL
+    for (int k = 0; k < n; k++) dx[k] = x[k] - mup[k];
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double s = muf[i];
+RD_UNROLL
+      for (int k = 0; k < n; k++) s += T[k * n + i] * dx[k];
+      mt[i] = s;
+    }
+RD_UNROLL
+    for (int i = 0; i < NS; i++) {
+      Sf[i] = rec_S2[i * kTile];
+      V[i] = Sf[i];
+    }
+    // V~ = Sigma_f - T~^T (Q Sigma_f): row k of Q Sigma_f is recomputed (T was overwritten)
+RD_UNROLL
+    for (int k = 0; k < n; k++) {
+      double Tk[n];
+RD_UNROLL
+      for (int j = 0; j < n; j++) {
+        double s = 0.0;
+RD_UNROLL
+        for (int l = 0; l < n; l++) s += Q[k * n + l] * Sf[sidx<n>(l, j)];
+        Tk[j] = s;
+      }
+RD_UNROLL
+      for (int i = 0; i < n; i++)
+RD_UNROLL
+        for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * Tk[j];
+    }
+RD_UNROLL
+    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
+    int f2 = state_sim<n>(x, mt, V, zt);
+    if (f2 && !fail) fail = f2;
+  }
+  if (DO_VAR) {                              // Sigma_s = Sigma_f + T~^T D T~  (:461-465)
+    double Sn[NS];
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double G[n];
+RD_UNROLL
+      for (int l = 0; l < n; l++) {
+        double s = 0.0;
+RD_UNROLL
+        for (int k = 0; k < n; k++) s += T[k * n + i] * Ss[sidx<n>(k, l)];
+        G[l] = s;
+      }
+RD_UNROLL
+      for (int j = i; j < n; j++) {
+        double s = rec_S2[sidx<n>(i, j) * kTile];
+RD_UNROLL
+        for (int l = 0; l < n; l++) s += G[l] * T[l * n + j];
+        Sn[sidx<n>(i, j)] = s;
+      }
+    }
+RD_UNROLL
+    for (int i = 0; i < NS; i++) Ss[i] = Sn[i];
+  }
+  return fail;
+}

@@ -58,9 +58,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 constexpr int kStagedWarps = 2;  // warps per CTA
 constexpr int kStagedThreads = kStagedWarps * 32;
 
-template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 struct StagedLayout {
-  static constexpr int NE = n + Sym<n>::size;
+  static constexpr int n = Fam::n, NE = Fam::NE;
   static constexpr int REC = NE * kTile;                                         // doubles per record
   static constexpr int OUTW = (DO_MEAN ? n : 0) + (DO_VAR ? n * n : 0) + (DO_SIM ? n : 0);
   static constexpr int ROW = (OUTW + 1) / 2 * 2;                                 // row stride (even)
@@ -99,11 +99,11 @@ __device__ __forceinline__ void flush_runs(const double *stage, double *out, lon
   }
 }
 
-template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 __global__ void __launch_bounds__(kStagedThreads)
-kalman_backward_staged(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
-  using L = StagedLayout<n, DO_MEAN, DO_VAR, DO_SIM>;
-  constexpr int m = Ode::n_meas, REC = L::REC, ROW = L::ROW;
+kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  using L = StagedLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  constexpr int n = Fam::n, REC = L::REC, ROW = L::ROW;
   constexpr int OFF_VAR = DO_MEAN ? n : 0, OFF_X = OFF_VAR + (DO_VAR ? n * n : 0);
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -133,8 +133,8 @@ kalman_backward_staged(const __grid_constant__ Prior<n, Ode::n_meas> P, const __
         bulk_g2s(ring + k * REC, hist_tile + (size_t)(N - 1 - k) * REC, kRecBytes, &bar[k]);
       }
   }
-  reg::SmoothState<n> st;
-  st.fail = 0;
+  double mus[n], Ss[Fam::NS], x[n];
+  int fail = 0;
   const double *zb = DO_SIM ? a.z + (valid ? b : b0) * a.z_stride : nullptr;
   double *row = stage + lane * ROW;
   uint32_t phase = 0;
@@ -145,10 +145,9 @@ kalman_backward_staged(const __grid_constant__ Prior<n, Ode::n_meas> P, const __
       phase ^= 1u << k;
       const double *rec = ring + k * REC + lane;
       const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
-      if (t == N)
-        reg::backward_terminal<n, DO_MEAN, DO_VAR, DO_SIM>(rec, zt, st);
-      else
-        reg::backward_step<n, m, DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, st);
+      const int f = (t == N) ? Fam::template bw_terminal<DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, mus, Ss, x)
+                             : Fam::template bw_step<DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, mus, Ss, x);
+      if (f && !fail) fail = f;
       __syncwarp();  // every lane is done with ring slot k
       if (lane == 0 && t - 3 >= 0) {
         mbar_arrive_expect_tx(&bar[k], kRecBytes);
@@ -158,28 +157,28 @@ kalman_backward_staged(const __grid_constant__ Prior<n, Ode::n_meas> P, const __
 #pragma unroll
       for (int i = 0; i < n; i++) {
         const double v = valid ? a.x0[b * n + i] : 0.0;
-        if (DO_MEAN) st.mus[i] = v;
-        if (DO_SIM) st.x[i] = v;
+        if (DO_MEAN) mus[i] = v;
+        if (DO_SIM) x[i] = v;
       }
       if (DO_VAR) {
 #pragma unroll
-        for (int i = 0; i < Sym<n>::size; i++) st.Ss[i] = 0.0;
+        for (int i = 0; i < Fam::NS; i++) Ss[i] = 0.0;
       }
     }
     // ---- emit time index t through the staging tile ---------------------------------------
     if (DO_MEAN) {
 #pragma unroll
-      for (int i = 0; i < n; i++) row[i] = st.mus[i];
+      for (int i = 0; i < n; i++) row[i] = mus[i];
     }
     if (DO_VAR) {
 #pragma unroll
       for (int j = 0; j < n; j++)
 #pragma unroll
-        for (int i = 0; i < n; i++) row[OFF_VAR + j * n + i] = st.Ss[sidx<n>(i, j)];
+        for (int i = 0; i < n; i++) row[OFF_VAR + j * n + i] = Fam::var_at(Ss, i, j);
     }
     if (DO_SIM) {
 #pragma unroll
-      for (int i = 0; i < n; i++) row[OFF_X + i] = st.x[i];
+      for (int i = 0; i < n; i++) row[OFF_X + i] = x[i];
     }
     __syncwarp();
     if (DO_MEAN) flush_runs<n, 0, ROW>(stage, a.mu_out, b0, a.B, T1, t, lane);
@@ -187,18 +186,18 @@ kalman_backward_staged(const __grid_constant__ Prior<n, Ode::n_meas> P, const __
     if (DO_SIM) flush_runs<n, OFF_X, ROW>(stage, a.x_out, b0, a.B, T1, t, lane);
     __syncwarp();
   }
-  if (valid && a.status && st.fail && a.status[b] == 0) a.status[b] = st.fail;
+  if (valid && a.status && fail && a.status[b] == 0) a.status[b] = fail;
 }
 
-template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  using L = StagedLayout<n, DO_MEAN, DO_VAR, DO_SIM>;
-  auto kern = kalman_backward_staged<Ode, n, DO_MEAN, DO_VAR, DO_SIM>;
+  using L = StagedLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  auto kern = kalman_backward_staged<Fam, DO_MEAN, DO_VAR, DO_SIM>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
   if (e != cudaSuccess) return e;
   const long n_tiles = (a.B + kTile - 1) / kTile;
   const unsigned grid = (unsigned)((n_tiles + kStagedWarps - 1) / kStagedWarps);
-  kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(make_prior<n, Ode::n_meas>(h), a);
+  kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(make_prior<Fam>(h), a);
   return cudaGetLastError();
 }
 

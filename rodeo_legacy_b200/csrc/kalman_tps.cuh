@@ -67,29 +67,34 @@ namespace loc {
 
 namespace rodeo {
 
-// Loop-policy selector: Impl<true> = registers / fully unrolled, Impl<false> = rolled.
+// Family selector: Fam<UNROLL, BD, Ode, K> is the dense family with n_state = K (BD = false)
+// or the block-diagonal family with block size K (BD = true), in the register (UNROLL) or
+// rolled loop policy.
+template <bool UNROLL, bool BD, class Ode, int K>
+struct FamSel;
+template <class Ode, int K>
+struct FamSel<true, false, Ode, K> { using type = reg::DenseFam<Ode, K>; };
+template <class Ode, int K>
+struct FamSel<true, true, Ode, K> { using type = reg::BdFam<Ode, K>; };
+template <class Ode, int K>
+struct FamSel<false, false, Ode, K> { using type = loc::DenseFam<Ode, K>; };
+template <class Ode, int K>
+struct FamSel<false, true, Ode, K> { using type = loc::BdFam<Ode, K>; };
+
 template <bool UNROLL>
-struct Impl;
+struct Bodies;
 template <>
-struct Impl<true> {
-  template <class Ode, int n, int IG>
-  RD_HD static void forward(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
-    reg::forward_body<Ode, n, IG>(P, a, b);
-  }
-  template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
-  RD_HD static void backward(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
-    reg::backward_body<Ode, n, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
+struct Bodies<true> {
+  template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+  RD_HD static void backward(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
+    reg::backward_body<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
   }
 };
 template <>
-struct Impl<false> {
-  template <class Ode, int n, int IG>
-  RD_HD static void forward(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
-    loc::forward_body<Ode, n, IG>(P, a, b);
-  }
-  template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
-  RD_HD static void backward(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
-    loc::backward_body<Ode, n, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
+struct Bodies<false> {
+  template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+  RD_HD static void backward(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
+    loc::backward_body<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
   }
 };
 

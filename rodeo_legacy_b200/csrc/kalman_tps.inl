@@ -1,51 +1,173 @@
-// kalman_tps.inl -- thread-per-system forward / backward bodies (see kalman_tps.cuh).
-template <class Ode, int n, int IG>
-RD_HD void forward_body(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
-  constexpr int m = Ode::n_meas, NS = Sym<n>::size, NE = n + NS;
-  constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
-  double mu[n], S[NS], th[NT];
+// kalman_tps.inl -- thread-per-system forward / backward bodies (see kalman_tps.cuh), for the
+// two problem families:
+//   DenseFam<Ode, n>   general dense Q, R, W                     (history NE = n + n(n+1)/2)
+//   BdFam<Ode, p>      block-diagonal Q, R with nb = n_meas blocks of size p, W row a inside
+//                      block a (kalman_common.cuh)               (history NE = n + nb p(p+1)/2)
+// A family provides: forward<IG>() -- the whole forward filter of one system; bw_terminal /
+// bw_step -- the smoother recursion on a history record; var_at -- element (i, j) of the
+// carried smoothed covariance.
+
+template <class Ode_, int n_>
+struct DenseFam {
+  using Ode = Ode_;
+  static constexpr int n = n_, m = Ode::n_meas, NS = Sym<n_>::size, NE = n_ + Sym<n_>::size;
+  using PriorT = Prior<n_, Ode_::n_meas>;
+
+  template <int IG>
+  RD_HD static void forward(const PriorT &P, const SolveArgs &a, long b) {
+    constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+    double mu[n], S[NS], th[NT];
 RD_UNROLL
-  for (int i = 0; i < n; i++) mu[i] = a.x0[b * n + i];
+    for (int i = 0; i < n; i++) mu[i] = a.x0[b * n + i];
 RD_UNROLL
-  for (int i = 0; i < NS; i++) S[i] = 0.0;
+    for (int i = 0; i < NS; i++) S[i] = 0.0;
 RD_UNROLL
-  for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
-  const int N = P.n_eval;
-  const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
-  int fail = 0;
-  for (int t = 0; t < N; t++) {
-    double mup[n], Sp[NS], y[m];
-    predict_mean<n, m>(P, mu, mup);
-    predict_var<n, m, false>(P, S, Sp, nullptr);
-    const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
-    if (IG == IG_CHKREBTII) {  // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
-      double xs[n], V[NS], zt[n];
+    for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
+    const int N = P.n_eval;
+    const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
+    int fail = 0;
+    for (int t = 0; t < N; t++) {
+      double mup[n], Sp[NS], y[m];
+      predict_mean<n>(P.Q, P.c, mu, mup);
+      predict_var<n, false>(P.Q, P.R, S, Sp, nullptr);
+      const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
+      if (IG == IG_CHKREBTII) {  // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
+        double xs[n], V[NS], zt[n];
 RD_UNROLL
-      for (int i = 0; i < NS; i++) V[i] = Sp[i];
+        for (int i = 0; i < NS; i++) V[i] = Sp[i];
 RD_UNROLL
-      for (int i = 0; i < n; i++) zt[i] = zb[(long)t * n + i];
-      int f = state_sim<n>(xs, mup, V, zt);
+        for (int i = 0; i < n; i++) zt[i] = zb[(long)t * n + i];
+        int f = state_sim<n>(xs, mup, V, zt);
+        if (f && !fail) fail = f;
+        Ode::template eval<n>(xs, tt, th, y);
+      } else {
+        Ode::template eval<n>(mup, tt, th, y);
+      }
+      int f = update_dense<n, m>(P.W, mup, Sp, y, IG == IG_SCHOBERT);
       if (f && !fail) fail = f;
-      Ode::template eval<n>(xs, tt, th, y);
-    } else {
-      Ode::template eval<n>(mup, tt, th, y);
-    }
-    int f = update<n, m>(P, mup, Sp, y, IG == IG_SCHOBERT);
-    if (f && !fail) fail = f;
-    double *h = a.hist + hist_offset(b, t, N, NE);
+      double *h = a.hist + hist_offset(b, t, N, NE);
 RD_UNROLL
-    for (int i = 0; i < n; i++) {
-      mu[i] = mup[i];
-      h[i * kTile] = mup[i];
-    }
+      for (int i = 0; i < n; i++) {
+        mu[i] = mup[i];
+        h[i * kTile] = mup[i];
+      }
 RD_UNROLL
-    for (int i = 0; i < NS; i++) {
-      S[i] = Sp[i];
-      h[(n + i) * kTile] = Sp[i];
+      for (int i = 0; i < NS; i++) {
+        S[i] = Sp[i];
+        h[(n + i) * kTile] = Sp[i];
+      }
     }
+    if (a.status) a.status[b] = fail;
   }
-  if (a.status) a.status[b] = fail;
-}
+
+  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  RD_HD static int bw_terminal(const PriorT &, const double *rec, const double *zt, double *mus, double *Ss,
+                               double *x) {
+    return smooth_terminal<n, DO_MEAN, DO_VAR, DO_SIM>(rec, rec + n * kTile, zt, mus, Ss, x);
+  }
+  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  RD_HD static int bw_step(const PriorT &P, const double *rec, const double *zt, double *mus, double *Ss,
+                           double *x) {
+    return smooth_step<n, DO_MEAN, DO_VAR, DO_SIM>(P.Q, P.c, P.R, rec, rec + n * kTile, zt, mus, Ss, x);
+  }
+  RD_HD static double var_at(const double *Ss, int i, int j) { return Ss[sidx<n>(i, j)]; }
+};
+
+template <class Ode_, int p_>
+struct BdFam {
+  using Ode = Ode_;
+  static constexpr int p = p_, nb = Ode::n_meas, n = p_ * Ode_::n_meas, m = Ode::n_meas;
+  static constexpr int PS = Sym<p_>::size, NS = Ode_::n_meas * Sym<p_>::size, NE = n + NS;
+  using PriorT = PriorBD<p_, Ode_::n_meas>;
+
+  template <int IG>
+  RD_HD static void forward(const PriorT &P, const SolveArgs &a, long b) {
+    constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+    double mu[n], S[NS], th[NT];
+RD_UNROLL
+    for (int i = 0; i < n; i++) mu[i] = a.x0[b * n + i];
+RD_UNROLL
+    for (int i = 0; i < NS; i++) S[i] = 0.0;
+RD_UNROLL
+    for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
+    const int N = P.n_eval;
+    const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
+    int fail = 0;
+    for (int t = 0; t < N; t++) {
+      double mup[n], Sp[NS], y[m];
+RD_UNROLL
+      for (int blk = 0; blk < nb; blk++) {
+        predict_mean<p>(P.Q[blk], P.c + blk * p, mu + blk * p, mup + blk * p);
+        predict_var<p, false>(P.Q[blk], P.R[blk], S + blk * PS, Sp + blk * PS, nullptr);
+      }
+      const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
+      if (IG == IG_CHKREBTII) {  // chol of a block-diagonal matrix is the blocks' chol
+        double xs[n];
+RD_UNROLL
+        for (int blk = 0; blk < nb; blk++) {
+          double V[PS], zt[p];
+RD_UNROLL
+          for (int i = 0; i < PS; i++) V[i] = Sp[blk * PS + i];
+RD_UNROLL
+          for (int i = 0; i < p; i++) zt[i] = zb[(long)t * n + blk * p + i];
+          int f = state_sim<p>(xs + blk * p, mup + blk * p, V, zt);
+          if (f && !fail) fail = f;
+        }
+        Ode::template eval<n>(xs, tt, th, y);
+      } else {
+        Ode::template eval<n>(mup, tt, th, y);
+      }
+      double *h = a.hist + hist_offset(b, t, N, NE);
+RD_UNROLL
+      for (int blk = 0; blk < nb; blk++) {
+        int f = update_block<p>(P.w[blk], mup + blk * p, Sp + blk * PS, y[blk], IG == IG_SCHOBERT);
+        if (f && !fail) fail = blk + 1;
+      }
+RD_UNROLL
+      for (int i = 0; i < n; i++) {
+        mu[i] = mup[i];
+        h[i * kTile] = mup[i];
+      }
+RD_UNROLL
+      for (int i = 0; i < NS; i++) {
+        S[i] = Sp[i];
+        h[(n + i) * kTile] = Sp[i];
+      }
+    }
+    if (a.status) a.status[b] = fail;
+  }
+
+  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  RD_HD static int bw_terminal(const PriorT &, const double *rec, const double *zt, double *mus, double *Ss,
+                               double *x) {
+    int fail = 0;
+RD_UNROLL
+    for (int blk = 0; blk < nb; blk++) {
+      int f = smooth_terminal<p, DO_MEAN, DO_VAR, DO_SIM>(rec + blk * p * kTile, rec + (n + blk * PS) * kTile,
+                                                          DO_SIM ? zt + blk * p : nullptr, mus + blk * p,
+                                                          Ss + blk * PS, x + blk * p);
+      if (f && !fail) fail = blk * p + f;
+    }
+    return fail;
+  }
+  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  RD_HD static int bw_step(const PriorT &P, const double *rec, const double *zt, double *mus, double *Ss,
+                           double *x) {
+    int fail = 0;
+RD_UNROLL
+    for (int blk = 0; blk < nb; blk++) {
+      int f = smooth_step<p, DO_MEAN, DO_VAR, DO_SIM>(P.Q[blk], P.c + blk * p, P.R[blk], rec + blk * p * kTile,
+                                                      rec + (n + blk * PS) * kTile,
+                                                      DO_SIM ? zt + blk * p : nullptr, mus + blk * p,
+                                                      Ss + blk * PS, x + blk * p);
+      if (f && !fail) fail = blk * p + f;
+    }
+    return fail;
+  }
+  RD_HD static double var_at(const double *Ss, int i, int j) {
+    return (i / p == j / p) ? Ss[(i / p) * PS + sidx<p>(i % p, j % p)] : 0.0;
+  }
+};
 
 // Gaussian log-density pieces accumulated over observed components at one data time.
 template <int n>
@@ -62,156 +184,18 @@ RD_HD double loglik_terms(const SolveArgs &a, int d, const double *X) {
   return lp;
 }
 
-// ---- backward pass ---------------------------------------------------------------------
-// State carried from time index t+1 to t.
-template <int n>
-struct SmoothState {
-  double mus[n];            // smoothed mean            (DO_MEAN)
-  double Ss[Sym<n>::size];  // smoothed covariance      (DO_VAR)
-  double x[n];              // posterior draw           (DO_SIM)
-  int fail;
-};
-
-// Terminal time index N (KalmanODE.pyx:445-449, 410-414).  `rec` points at this system's
-// history record for time index N (element e at rec[e * kTile]); zt = z[:, N-1].
-template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
-RD_HD void backward_terminal(const double *rec, const double *zt_ptr, SmoothState<n> &st) {
-  constexpr int NS = Sym<n>::size;
-  double muf[n], Sf[NS];
-RD_UNROLL
-  for (int i = 0; i < n; i++) muf[i] = rec[i * kTile];
-RD_UNROLL
-  for (int i = 0; i < NS; i++) Sf[i] = rec[(n + i) * kTile];
-  if (DO_MEAN) {
-RD_UNROLL
-    for (int i = 0; i < n; i++) st.mus[i] = muf[i];
-  }
-  if (DO_VAR) {
-RD_UNROLL
-    for (int i = 0; i < NS; i++) st.Ss[i] = Sf[i];
-  }
-  if (DO_SIM) {
-    double zt[n];
-RD_UNROLL
-    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
-    int f = state_sim<n>(st.x, muf, Sf, zt);  // destroys Sf (not needed again)
-    if (f && !st.fail) st.fail = f;
-  }
-}
-
-// One smoother step t+1 -> t (KalmanODE.pyx:452-461 / 417-425 / 381-392).  `rec` is the
-// history record of time index t; zt_ptr = z[:, t-1].  The filtered covariance is re-read
-// from `rec` where it is needed a second time instead of being held in registers.
-template <int n, int m, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
-RD_HD void backward_step(const Prior<n, m> &P, const double *rec, const double *zt_ptr,
-                         SmoothState<n> &st) {
-  constexpr int NS = Sym<n>::size;
-  const volatile double *rec2 = rec;  // second reads: do not keep Sigma_f live across the step
-  double muf[n], mup[n], Sp[NS], T[n * n], invd[n];
-  {
-    double Sf[NS];
-RD_UNROLL
-    for (int i = 0; i < n; i++) muf[i] = rec[i * kTile];
-RD_UNROLL
-    for (int i = 0; i < NS; i++) Sf[i] = rec[(n + i) * kTile];
-    // predicted moments at t+1, recomputed exactly as the forward pass computed them
-    predict_mean<n, m>(P, muf, mup);
-    predict_var<n, m, true>(P, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
-  }
-  if (DO_VAR) {                              // D = Sigma_s(t+1) - Sigma_p(t+1)  (:460)
-RD_UNROLL
-    for (int i = 0; i < NS; i++) st.Ss[i] -= Sp[i];
-  }
-  int f = chol_packed<n>(Sp, invd);          // LLT(Sigma_p)  (:457)
-  if (f && !st.fail) st.fail = f;
-RD_UNROLL
-  for (int j = 0; j < n; j++) chol_solve_vec<n>(Sp, invd, T + j, n);  // T~ (:458)
-  if (DO_MEAN) {                             // (:459, 463-464)
-    double dmu[n];
-RD_UNROLL
-    for (int k = 0; k < n; k++) dmu[k] = st.mus[k] - mup[k];
-RD_UNROLL
-    for (int i = 0; i < n; i++) {
-      double s = muf[i];
-RD_UNROLL
-      for (int k = 0; k < n; k++) s += T[k * n + i] * dmu[k];
-      st.mus[i] = s;
-    }
-  }
-  if (DO_SIM) {                              // KalmanTV.h:511-527
-    double dx[n], mt[n], V[NS], Sf[NS], zt[n];
-RD_UNROLL
-    for (int k = 0; k < n; k++) dx[k] = st.x[k] - mup[k];
-RD_UNROLL
-    for (int i = 0; i < n; i++) {
-      double s = muf[i];
-RD_UNROLL
-      for (int k = 0; k < n; k++) s += T[k * n + i] * dx[k];
-      mt[i] = s;
-    }
-RD_UNROLL
-    for (int i = 0; i < NS; i++) {
-      Sf[i] = rec2[(n + i) * kTile];
-      V[i] = Sf[i];
-    }
-    // V~ = Sigma_f - T~^T (Q Sigma_f): row k of Q Sigma_f is recomputed (T was overwritten)
-RD_UNROLL
-    for (int k = 0; k < n; k++) {
-      double Tk[n];
-RD_UNROLL
-      for (int j = 0; j < n; j++) {
-        double s = 0.0;
-RD_UNROLL
-        for (int l = 0; l < n; l++) s += P.Q[k * n + l] * Sf[sidx<n>(l, j)];
-        Tk[j] = s;
-      }
-RD_UNROLL
-      for (int i = 0; i < n; i++)
-RD_UNROLL
-        for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * Tk[j];
-    }
-RD_UNROLL
-    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
-    int f2 = state_sim<n>(st.x, mt, V, zt);
-    if (f2 && !st.fail) st.fail = f2;
-  }
-  if (DO_VAR) {                              // Sigma_s = Sigma_f + T~^T D T~  (:461-465)
-    double Sn[NS];
-RD_UNROLL
-    for (int i = 0; i < n; i++) {
-      double G[n];
-RD_UNROLL
-      for (int l = 0; l < n; l++) {
-        double s = 0.0;
-RD_UNROLL
-        for (int k = 0; k < n; k++) s += T[k * n + i] * st.Ss[sidx<n>(k, l)];
-        G[l] = s;
-      }
-RD_UNROLL
-      for (int j = i; j < n; j++) {
-        double s = rec2[(n + sidx<n>(i, j)) * kTile];
-RD_UNROLL
-        for (int l = 0; l < n; l++) s += G[l] * T[l * n + j];
-        Sn[sidx<n>(i, j)] = s;
-      }
-    }
-RD_UNROLL
-    for (int i = 0; i < NS; i++) st.Ss[i] = Sn[i];
-  }
-}
-
 // Generic backward pass: plain global loads and direct (per-thread) global stores.  Used by
-// the rolled family, by every log-likelihood kernel and by tests/hostsim; the register family's
-// solve_mv / solve_sim / solve kernels use the shared-memory staged version in
+// the rolled family, by every log-likelihood kernel and by tests/hostsim; the register
+// families' solve_mv / solve_sim / solve kernels use the shared-memory staged version in
 // kalman_staged.cuh.  DO_MEAN / DO_VAR: smooth_mv; DO_SIM: smooth_sim; LOGLIK: no per-step
 // output, accumulate the thinned log-likelihood of the mean (DO_MEAN) or draw (DO_SIM).
-template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
-RD_HD void backward_body(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, long b) {
-  constexpr int m = Ode::n_meas, NS = Sym<n>::size, NE = n + NS;
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+RD_HD void backward_body(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
+  constexpr int n = Fam::n, NE = Fam::NE;
   const int N = P.n_eval;
   const long T1 = (long)N + 1;
-  SmoothState<n> st;
-  st.fail = 0;
+  double mus[n], Ss[Fam::NS], x[n];
+  int fail = 0;
   double lp = 0.0;
   int d = LOGLIK ? a.n_obs_times - 1 : -1;
   const double *zb = DO_SIM ? a.z + b * a.z_stride : nullptr;
@@ -221,28 +205,27 @@ RD_HD void backward_body(const Prior<n, Ode::n_meas> &P, const SolveArgs &a, lon
   for (int t = N; t >= 1; t--) {
     const double *rec = a.hist + hist_offset(b, t - 1, N, NE);
     const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
-    if (t == N)
-      backward_terminal<n, DO_MEAN, DO_VAR, DO_SIM>(rec, zt, st);
-    else
-      backward_step<n, m, DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, st);
+    int f = (t == N) ? Fam::template bw_terminal<DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, mus, Ss, x)
+                     : Fam::template bw_step<DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, mus, Ss, x);
+    if (f && !fail) fail = f;
     if (!LOGLIK) {
       if (DO_MEAN) {
 RD_UNROLL
-        for (int i = 0; i < n; i++) mu_o[(long)t * n + i] = st.mus[i];
+        for (int i = 0; i < n; i++) mu_o[(long)t * n + i] = mus[i];
       }
       if (DO_SIM) {
 RD_UNROLL
-        for (int i = 0; i < n; i++) x_o[(long)t * n + i] = st.x[i];
+        for (int i = 0; i < n; i++) x_o[(long)t * n + i] = x[i];
       }
       if (DO_VAR) {
 RD_UNROLL
         for (int j = 0; j < n; j++)
 RD_UNROLL
-          for (int i = 0; i < n; i++) var_o[((long)t * n + j) * n + i] = st.Ss[sidx<n>(i, j)];
+          for (int i = 0; i < n; i++) var_o[((long)t * n + j) * n + i] = Fam::var_at(Ss, i, j);
       }
     } else {
       while (d >= 0 && a.thin_index[d] == t) {
-        lp += loglik_terms<n>(a, d, DO_SIM ? st.x : st.mus);
+        lp += loglik_terms<n>(a, d, DO_SIM ? x : mus);
         d--;
       }
     }
@@ -271,5 +254,5 @@ RD_UNROLL
     const double cst = -0.91893853320467274178 - log(a.gamma);
     a.loglik[b] = lp + cst * (double)(a.n_obs_times * a.n_obs_comp);
   }
-  if (a.status && st.fail && a.status[b] == 0) a.status[b] = st.fail;
+  if (a.status && fail && a.status[b] == 0) a.status[b] = fail;
 }

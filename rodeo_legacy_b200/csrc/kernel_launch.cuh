@@ -7,8 +7,7 @@ namespace rodeo {
 constexpr int kThreadsPerBlock = 64;
 
 template <int n, int m>
-inline Prior<n, m> make_prior(const HostPrior &h) {
-  Prior<n, m> P;
+inline void fill_prior(Prior<n, m> &P, const HostPrior &h) {
   for (int i = 0; i < n; i++) {
     P.c[i] = h.c[i];
     for (int j = 0; j < n; j++) {
@@ -21,6 +20,30 @@ inline Prior<n, m> make_prior(const HostPrior &h) {
   P.tmin = h.tmin;
   P.tmax = h.tmax;
   P.n_eval = h.n_eval;
+}
+
+template <int p, int nb>
+inline void fill_prior(PriorBD<p, nb> &P, const HostPrior &h) {
+  const int n = p * nb;
+  for (int b = 0; b < nb; b++) {
+    for (int i = 0; i < p; i++) {
+      P.w[b][i] = h.W[b + (size_t)(b * p + i) * nb];
+      for (int j = 0; j < p; j++) {
+        P.Q[b][i * p + j] = h.Q[(b * p + i) + (size_t)(b * p + j) * n];
+        if (i <= j) P.R[b][sidx<p>(i, j)] = h.R[(b * p + i) + (size_t)(b * p + j) * n];
+      }
+    }
+  }
+  for (int i = 0; i < n; i++) P.c[i] = h.c[i];
+  P.tmin = h.tmin;
+  P.tmax = h.tmax;
+  P.n_eval = h.n_eval;
+}
+
+template <class Fam>
+inline typename Fam::PriorT make_prior(const HostPrior &h) {
+  typename Fam::PriorT P;
+  fill_prior(P, h);
   return P;
 }
 
@@ -28,58 +51,61 @@ inline Prior<n, m> make_prior(const HostPrior &h) {
 #include "kalman_staged.cuh"
 namespace rodeo {
 
-template <class Ode, int n, int IG, bool UNROLL>
+template <class Fam, int IG>
 __global__ void __launch_bounds__(kThreadsPerBlock)
-kalman_forward(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
+kalman_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) Impl<UNROLL>::template forward<Ode, n, IG>(P, a, b);
+  if (b < a.B) Fam::template forward<IG>(P, a, b);
 }
 
-template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK, bool UNROLL>
+template <class Fam, bool UNROLL, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 __global__ void __launch_bounds__(kThreadsPerBlock)
-kalman_backward(const __grid_constant__ Prior<n, Ode::n_meas> P, const __grid_constant__ SolveArgs a) {
+kalman_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) Impl<UNROLL>::template backward<Ode, n, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
+  if (b < a.B) Bodies<UNROLL>::template backward<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
 }
 
 inline dim3 grid_for(long B) { return dim3((unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock)); }
 
-template <class Ode, int n, int IG, bool UNROLL>
+template <class Fam, int IG>
 cudaError_t launch_forward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  kalman_forward<Ode, n, IG, UNROLL><<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(
-      make_prior<n, Ode::n_meas>(h), a);
+  kalman_forward<Fam, IG><<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
   return cudaGetLastError();
 }
 
-template <class Ode, int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK, bool UNROLL>
+template <class Fam, bool UNROLL, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 cudaError_t launch_backward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  kalman_backward<Ode, n, DO_MEAN, DO_VAR, DO_SIM, LOGLIK, UNROLL>
-      <<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<n, Ode::n_meas>(h), a);
+  kalman_backward<Fam, UNROLL, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>
+      <<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
   return cudaGetLastError();
 }
 
-template <class Ode, int n, bool UNROLL>
+// K = n_state for the dense family, block size p for the block-diagonal family.
+template <class Ode, int K, bool BD, bool UNROLL>
 KernelSet make_kernel_set(const char *name) {
+  using Fam = typename FamSel<UNROLL, BD, Ode, K>::type;
   KernelSet k;
   k.ode = Ode::id;
-  k.n = n;
+  k.n = Fam::n;
   k.m = Ode::n_meas;
+  k.blockdiag = BD;
+  k.registers = UNROLL;
   k.name = name;
-  k.forward[IG_PROBDE] = launch_forward<Ode, n, IG_PROBDE, UNROLL>;
-  k.forward[IG_SCHOBERT] = launch_forward<Ode, n, IG_SCHOBERT, UNROLL>;
-  k.forward[IG_CHKREBTII] = launch_forward<Ode, n, IG_CHKREBTII, UNROLL>;
-  if constexpr (UNROLL) {  // register family: history and outputs staged through shared memory
-    k.backward[BK_MV] = launch_backward_staged<Ode, n, true, true, false>;
-    k.backward[BK_SIM] = launch_backward_staged<Ode, n, false, false, true>;
-    k.backward[BK_BOTH] = launch_backward_staged<Ode, n, true, true, true>;
+  k.forward[IG_PROBDE] = launch_forward<Fam, IG_PROBDE>;
+  k.forward[IG_SCHOBERT] = launch_forward<Fam, IG_SCHOBERT>;
+  k.forward[IG_CHKREBTII] = launch_forward<Fam, IG_CHKREBTII>;
+  if constexpr (UNROLL) {  // register families: history and outputs staged through shared memory
+    k.backward[BK_MV] = launch_backward_staged<Fam, true, true, false>;
+    k.backward[BK_SIM] = launch_backward_staged<Fam, false, false, true>;
+    k.backward[BK_BOTH] = launch_backward_staged<Fam, true, true, true>;
   } else {
-    k.backward[BK_MV] = launch_backward<Ode, n, true, true, false, false, UNROLL>;
-    k.backward[BK_SIM] = launch_backward<Ode, n, false, false, true, false, UNROLL>;
-    k.backward[BK_BOTH] = launch_backward<Ode, n, true, true, true, false, UNROLL>;
+    k.backward[BK_MV] = launch_backward<Fam, UNROLL, true, true, false, false>;
+    k.backward[BK_SIM] = launch_backward<Fam, UNROLL, false, false, true, false>;
+    k.backward[BK_BOTH] = launch_backward<Fam, UNROLL, true, true, true, false>;
   }
-  k.backward[BK_LL_MEAN] = launch_backward<Ode, n, true, false, false, true, UNROLL>;
-  k.backward[BK_LL_DRAW] = launch_backward<Ode, n, false, false, true, true, UNROLL>;
-  k.hist_elems = n + Sym<n>::size;
+  k.backward[BK_LL_MEAN] = launch_backward<Fam, UNROLL, true, false, false, true>;
+  k.backward[BK_LL_DRAW] = launch_backward<Fam, UNROLL, false, false, true, true>;
+  k.hist_elems = Fam::NE;
   return k;
 }
 

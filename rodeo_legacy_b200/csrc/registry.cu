@@ -3,28 +3,32 @@
 
 namespace rodeo {
 
-void register_chkrebtii(KernelSet *, int *);
-void register_fitz(KernelSet *, int *);
-void register_lorenz(KernelSet *, int *);
-void register_mseir(KernelSet *, int *);
+#define RODEO_REG(name) void register_##name(KernelSet *, int *);
+RODEO_REG(chkrebtii_dense) RODEO_REG(chkrebtii_bd) RODEO_REG(fitz_dense) RODEO_REG(fitz_bd)
+RODEO_REG(lorenz_dense) RODEO_REG(lorenz_bd) RODEO_REG(mseir_dense) RODEO_REG(mseir_bd)
+#undef RODEO_REG
 
-static KernelSet g_sets[32];
+static KernelSet g_sets[64];
 static int g_count = -1;
 
 static void init_sets() {
   if (g_count >= 0) return;
   int c = 0;
-  register_chkrebtii(g_sets, &c);
-  register_fitz(g_sets, &c);
-  register_lorenz(g_sets, &c);
-  register_mseir(g_sets, &c);
+  register_chkrebtii_dense(g_sets, &c);
+  register_chkrebtii_bd(g_sets, &c);
+  register_fitz_dense(g_sets, &c);
+  register_fitz_bd(g_sets, &c);
+  register_lorenz_dense(g_sets, &c);
+  register_lorenz_bd(g_sets, &c);
+  register_mseir_dense(g_sets, &c);
+  register_mseir_bd(g_sets, &c);
   g_count = c;
 }
 
-const KernelSet *find_kernel_set(int ode, int n) {
+const KernelSet *find_kernel_set(int ode, int n, bool blockdiag) {
   init_sets();
   for (int i = 0; i < g_count; i++)
-    if (g_sets[i].ode == ode && g_sets[i].n == n) return &g_sets[i];
+    if (g_sets[i].ode == ode && g_sets[i].n == n && g_sets[i].blockdiag == blockdiag) return &g_sets[i];
   return nullptr;
 }
 int kernel_set_count() {

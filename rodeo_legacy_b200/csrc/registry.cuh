@@ -1,4 +1,4 @@
-// registry.cuh -- table of compiled (ode, n_state) kernel sets and their launchers.
+// registry.cuh -- table of compiled kernel sets and their launchers.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -6,7 +6,7 @@
 
 namespace rodeo {
 
-// Everything the host side needs to fill a Prior<n, m> without knowing n, m statically.
+// Everything the host side needs to fill a Prior / PriorBD without knowing n, m statically.
 struct HostPrior {
   int n, m, n_eval;
   double tmin, tmax;
@@ -19,13 +19,15 @@ typedef cudaError_t (*launch_fn)(const HostPrior &, const SolveArgs &, cudaStrea
 
 struct KernelSet {
   int ode, n, m;
+  bool blockdiag;                 // block-diagonal family (needs structured Q, R, W) or dense
+  bool registers;                 // fully unrolled register kernels (else rolled / local memory)
   const char *name;
   launch_fn forward[3];           // by interrogation variant
   launch_fn backward[BK_COUNT];   // by BackwardKind
   int hist_elems;                 // doubles of history per system per step
 };
 
-const KernelSet *find_kernel_set(int ode, int n);
+const KernelSet *find_kernel_set(int ode, int n, bool blockdiag);
 int kernel_set_count();
 const KernelSet *kernel_set_at(int i);
 

@@ -16,6 +16,8 @@ Differences, all forced by batching on a GPU:
   * NumPy in -> NumPy out through the host-buffer entry point; torch CUDA tensors in ->
     torch CUDA tensors out through the device-pointer entry point (nothing leaves HBM).
   * ``var[..., 0, :, :]`` is zeros (the compiled reference backends leave it uninitialised).
+  * ``force_dense=True`` keeps the general dense kernels even when the prior is block diagonal
+    (the block-diagonal family is an exact specialisation: zeros stay zeros).
   * ``solve_mv`` never touches the RNG; ``solve_sim`` / ``solve`` fill an all-zero
     ``z_state`` from ``rand_mat`` (global NumPy RNG) exactly like the reference (:285-286).
 """
@@ -73,7 +75,7 @@ def _ptr(t):
 
 class KalmanODE:
     def __init__(self, W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state,
-                 z_state=None, interrogate="probde", device=None):
+                 z_state=None, interrogate="probde", device=None, force_dense=False):
         self._lib = _lib.load()                      # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
@@ -102,7 +104,8 @@ class KalmanODE:
             self.z_state = z_state
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
-        desc = _lib.ProblemDesc(n, m, self.n_eval, self._ode, self._ig, 0, self.tmin, self.tmax,
+        desc = _lib.ProblemDesc(n, m, self.n_eval, self._ode, self._ig, int(bool(force_dense)),
+                                self.tmin, self.tmax,
                                 self._wgt_meas.ctypes.data, self._wgt_state.ctypes.data,
                                 self._mu_state.ctypes.data, self._var_state.ctypes.data)
         h = ctypes.c_void_p()
@@ -190,6 +193,16 @@ class KalmanODE:
 
     def set_workspace_limit(self, nbytes):
         _lib.check(self._lib.rodeo_cuda_set_workspace_limit(self._h, int(nbytes)))
+
+    @property
+    def kernel_family(self):
+        """('blockdiag' | 'dense', 'registers' | 'rolled'): the kernel family in use.  The
+        block-diagonal family is selected automatically when wgt_state / var_state are block
+        diagonal with n_meas equal blocks and row a of wgt_meas lies inside block a (what
+        ibm_init / car_init + indep_init + zero_pad produce); ``force_dense=True`` disables it."""
+        bd, rg, _ = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(self._lib.rodeo_cuda_problem_info(self._h, ctypes.byref(bd), ctypes.byref(rg), ctypes.byref(_)))
+        return ("blockdiag" if bd.value else "dense", "registers" if rg.value else "rolled")
 
     @property
     def history_bytes_per_system(self):

@@ -15,7 +15,7 @@ c_int_p = ctypes.POINTER(ctypes.c_int32)
 
 class ProblemDesc(ctypes.Structure):
     _fields_ = [("n_state", ctypes.c_int32), ("n_meas", ctypes.c_int32), ("n_eval", ctypes.c_int32),
-                ("ode", ctypes.c_int32), ("interrogate", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("ode", ctypes.c_int32), ("interrogate", ctypes.c_int32), ("flags", ctypes.c_int32),
                 ("tmin", ctypes.c_double), ("tmax", ctypes.c_double),
                 ("wgt_meas", ctypes.c_void_p), ("wgt_state", ctypes.c_void_p),
                 ("mu_state", ctypes.c_void_p), ("var_state", ctypes.c_void_p)]
@@ -32,6 +32,7 @@ SYMBOLS = [
     ("rodeo_cuda_problem_create", _I, [ctypes.POINTER(ProblemDesc), ctypes.POINTER(_V)]),
     ("rodeo_cuda_problem_destroy", _I, [_V]),
     ("rodeo_cuda_problem_set", _I, [_V, _I, _V]),
+    ("rodeo_cuda_problem_info", _I, [_V, c_int_p, c_int_p, c_int_p]),
     ("rodeo_cuda_history_bytes_per_system", _Z, [_V]),
     ("rodeo_cuda_set_workspace_limit", _I, [_V, _Z]),
     ("rodeo_cuda_reserve", _I, [_V, _L]),

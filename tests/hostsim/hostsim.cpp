@@ -17,8 +17,7 @@ struct HostPrior {
 };
 
 template <int n, int m>
-static Prior<n, m> make_prior(const HostPrior &h) {
-  Prior<n, m> P;
+static void fill_prior(Prior<n, m> &P, const HostPrior &h) {
   for (int i = 0; i < n; i++) {
     P.c[i] = h.c[i];
     for (int j = 0; j < n; j++) {
@@ -31,26 +30,43 @@ static Prior<n, m> make_prior(const HostPrior &h) {
   P.tmin = h.tmin;
   P.tmax = h.tmax;
   P.n_eval = h.n_eval;
-  return P;
 }
 
-template <class Ode, int n, bool UNROLL>
+template <int p, int nb>
+static void fill_prior(PriorBD<p, nb> &P, const HostPrior &h) {
+  const int n = p * nb;
+  for (int b = 0; b < nb; b++)
+    for (int i = 0; i < p; i++) {
+      P.w[b][i] = h.W[b + (size_t)(b * p + i) * nb];
+      for (int j = 0; j < p; j++) {
+        P.Q[b][i * p + j] = h.Q[(b * p + i) + (size_t)(b * p + j) * n];
+        if (i <= j) P.R[b][sidx<p>(i, j)] = h.R[(b * p + i) + (size_t)(b * p + j) * n];
+      }
+    }
+  for (int i = 0; i < n; i++) P.c[i] = h.c[i];
+  P.tmin = h.tmin;
+  P.tmax = h.tmax;
+  P.n_eval = h.n_eval;
+}
+
+template <class Fam, bool UNROLL>
 static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
-  auto P = make_prior<n, Ode::n_meas>(h);
-  std::vector<double> hist((size_t)h.n_eval * (n + Sym<n>::size) * ((a.B + 31) / 32 * 32));
+  typename Fam::PriorT P;
+  fill_prior(P, h);
+  std::vector<double> hist((size_t)h.n_eval * Fam::NE * ((a.B + 31) / 32 * 32));
   a.hist = hist.data();
   for (long b = 0; b < a.B; b++) {
-    if (ig == 0) Impl<UNROLL>::template forward<Ode, n, IG_PROBDE>(P, a, b);
-    else if (ig == 1) Impl<UNROLL>::template forward<Ode, n, IG_SCHOBERT>(P, a, b);
-    else Impl<UNROLL>::template forward<Ode, n, IG_CHKREBTII>(P, a, b);
+    if (ig == 0) Fam::template forward<IG_PROBDE>(P, a, b);
+    else if (ig == 1) Fam::template forward<IG_SCHOBERT>(P, a, b);
+    else Fam::template forward<IG_CHKREBTII>(P, a, b);
   }
   for (long b = 0; b < a.B; b++) {
     switch (kind) {
-      case 0: Impl<UNROLL>::template backward<Ode, n, true, true, false, false>(P, a, b); break;
-      case 1: Impl<UNROLL>::template backward<Ode, n, false, false, true, false>(P, a, b); break;
-      case 2: Impl<UNROLL>::template backward<Ode, n, true, true, true, false>(P, a, b); break;
-      case 3: Impl<UNROLL>::template backward<Ode, n, true, false, false, true>(P, a, b); break;
-      case 4: Impl<UNROLL>::template backward<Ode, n, false, false, true, true>(P, a, b); break;
+      case 0: Bodies<UNROLL>::template backward<Fam, true, true, false, false>(P, a, b); break;
+      case 1: Bodies<UNROLL>::template backward<Fam, false, false, true, false>(P, a, b); break;
+      case 2: Bodies<UNROLL>::template backward<Fam, true, true, true, false>(P, a, b); break;
+      case 3: Bodies<UNROLL>::template backward<Fam, true, false, false, true>(P, a, b); break;
+      case 4: Bodies<UNROLL>::template backward<Fam, false, false, true, true>(P, a, b); break;
       default: return -1;
     }
   }
@@ -59,7 +75,7 @@ static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
 
 extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, double tmax, const double *W,
                              const double *Q, const double *c, const double *R, int ig, int kind,
-                             int unroll, long B, const double *x0, const double *theta, const double *z,
+                             int unroll, int blockdiag, long B, const double *x0, const double *theta, const double *z,
                              long z_stride, double *x_out, double *mu_out, double *var_out, int *status,
                              const int *thin_index, int n_obs_times, const int *state_index,
                              int n_obs_comp, const double *Y, double gamma, double *loglik) {
@@ -82,12 +98,17 @@ extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, dou
   a.Y = Y;
   a.gamma = gamma;
   a.loglik = loglik;
-#define CASE(ODE, NN, ID)                                                     \
-  if (ode == ID && n == NN)                                                   \
-    return unroll ? run<ODE, NN, true>(h, ig, kind, a) : run<ODE, NN, false>(h, ig, kind, a);
-  CASE(OdeChkrebtii, 4, 0)
-  CASE(OdeFitz, 6, 1)
-  CASE(OdeLorenz63, 9, 2)
-  CASE(OdeMseir, 15, 3)
+#define CASE(ODE, NN, PP, ID)                                                             \
+  if (ode == ID && n == NN) {                                                             \
+    if (blockdiag)                                                                        \
+      return unroll ? run<reg::BdFam<ODE, PP>, true>(h, ig, kind, a)                      \
+                    : run<loc::BdFam<ODE, PP>, false>(h, ig, kind, a);                    \
+    return unroll ? run<reg::DenseFam<ODE, NN>, true>(h, ig, kind, a)                     \
+                  : run<loc::DenseFam<ODE, NN>, false>(h, ig, kind, a);                   \
+  }
+  CASE(OdeChkrebtii, 4, 4, 0)
+  CASE(OdeFitz, 6, 3, 1)
+  CASE(OdeLorenz63, 9, 3, 2)
+  CASE(OdeMseir, 15, 3, 3)
   return -2;
 }

@@ -34,14 +34,20 @@ def test_registry_and_error_strings_without_gpu():
     assert [lib.rodeo_cuda_ode_n_theta(i) for i in range(4)] == [0, 3, 3, 6]
     assert lib.rodeo_cuda_ode_n_meas(9) == -1
     for ode, n, m in [(0, 4, 1), (1, 6, 2), (2, 9, 3), (3, 15, 5)]:
-        assert lib.rodeo_cuda_supported(ode, n, m, 0) == 1
+        assert lib.rodeo_cuda_supported(ode, n, m, 0) == 3      # dense and block-diagonal sets
+    assert lib.rodeo_cuda_supported(2, 12, 3, 0) == 2           # block-diagonal only (p = 4)
     assert lib.rodeo_cuda_supported(1, 7, 2, 0) == 0
     assert lib.rodeo_cuda_supported(1, 6, 3, 0) == 0
     # invalid descriptor is rejected before any CUDA call
     h = ctypes.c_void_p()
     assert lib.rodeo_cuda_problem_create(None, ctypes.byref(h)) == -1
     assert b"null" in lib.rodeo_cuda_last_error()
-    d = _lib.ProblemDesc(7, 2, 10, 1, 0, 0, 0.0, 1.0, 1, 1, 1, 1)
+    import numpy as np
+    W = np.zeros((2, 7), order="F")
+    Q = np.asfortranarray(np.eye(7))
+    c = np.zeros(7)
+    d = _lib.ProblemDesc(7, 2, 10, 1, 0, 0, 0.0, 1.0, W.ctypes.data, Q.ctypes.data, c.ctypes.data,
+                         Q.ctypes.data)
     assert lib.rodeo_cuda_problem_create(ctypes.byref(d), ctypes.byref(h)) == -2
     assert b"no compiled kernel" in lib.rodeo_cuda_last_error()
 

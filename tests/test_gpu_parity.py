@@ -28,10 +28,13 @@ GOLDEN = [("chkrebtii_n100", 1e-10, 1e-8, 1e-5, None), ("chkrebtii_n200", 1e-10,
           ("lorenz_car_n600", 1e-7, 1e-6, 1e-7, None), ("mseir_n1000", 1e-10, 1e-8, 1e-7, None)]
 
 
+@pytest.mark.parametrize("force_dense", [False, True], ids=["auto", "dense"])
 @pytest.mark.parametrize("name,mtol,vtol,xtol,hor", GOLDEN)
-def test_golden_vectors_host_and_device_paths(name, mtol, vtol, xtol, hor):
+def test_golden_vectors_host_and_device_paths(name, mtol, vtol, xtol, hor, force_dense):
     g = load_golden(name)
-    k = _kode_from_golden(g, name, z_state=np.asfortranarray(g["z"]))
+    k = _kode_from_golden(g, name, z_state=np.asfortranarray(g["z"]), force_dense=force_dense)
+    # every golden prior is block diagonal: "auto" must pick that family, "dense" must not
+    assert k.kernel_family[0] == ("dense" if force_dense else "blockdiag")
     batched = g["mu"].ndim == 3
     B = g["mu"].shape[0] if batched else 1
     x0 = np.tile(g["x0"], (B, 1)) if batched else np.asfortranarray(g["x0"])
@@ -64,15 +67,16 @@ def test_golden_vectors_host_and_device_paths(name, mtol, vtol, xtol, hor):
     np.testing.assert_array_equal(xd.cpu().numpy(), x)
 
 
+@pytest.mark.parametrize("force_dense", [False, True], ids=["auto", "dense"])
 @pytest.mark.parametrize("maker,B,mtol,vtol,xtol", [
     (wl.fitz_batch, 1500, 1e-10, 1e-9, 1e-9),
     (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7),
     (lambda B: wl.lorenz_batch(B, N=500, tmax=2.0), 130, 1e-9, 1e-7, 1e-8)])
-def test_seeded_batch_against_oracle(maker, B, mtol, vtol, xtol):
+def test_seeded_batch_against_oracle(maker, B, mtol, vtol, xtol, force_dense):
     w, x0, theta = maker(B)
     rng = np.random.default_rng(42)
     z = np.asfortranarray(rng.standard_normal((len(w["x0"]), w["N"])))
-    k = wl.make_kode(w, z_state=z)
+    k = wl.make_kode(w, z_state=z, force_dense=force_dense)
     ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
     x, mu, var = k.solve(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda())
     x, mu, var = x.cpu().numpy(), mu.cpu().numpy(), var.cpu().numpy()
@@ -83,12 +87,13 @@ def test_seeded_batch_against_oracle(maker, B, mtol, vtol, xtol):
     np.testing.assert_array_equal(var, np.swapaxes(var, -1, -2))     # exactly symmetric
 
 
-def test_per_system_draws_and_ragged_chunks():
+@pytest.mark.parametrize("force_dense", [False, True], ids=["auto", "dense"])
+def test_per_system_draws_and_ragged_chunks(force_dense):
     """z per system; batch not a multiple of anything; workspace limit forcing 3 chunks."""
     w, x0, theta = wl.fitz_batch(2500, seed=9)
     rng = np.random.default_rng(1)
     z = rng.standard_normal((2500, 6, 400))
-    k = wl.make_kode(w, z_state=z)
+    k = wl.make_kode(w, z_state=z, force_dense=force_dense)
     k.set_workspace_limit(1024 * k.history_bytes_per_system)          # 1024 systems per chunk
     x = k.solve_sim(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda()).cpu().numpy()
     assert k.launch_count == 6
@@ -100,12 +105,13 @@ def test_per_system_draws_and_ragged_chunks():
     np.testing.assert_array_equal(xh, x)
 
 
-def test_fitz_full_size_properties():
+@pytest.mark.parametrize("force_dense", [False, True], ids=["auto", "dense"])
+def test_fitz_full_size_properties(force_dense):
     """BASELINE config 2 (65,536 theta draws, n_eval 400, solve_mv) through properties that
     do not need the oracle at full size, plus an oracle spot-check of 48 systems."""
     B = 65536
     w, x0, theta = wl.fitz_batch(B)
-    k = wl.make_kode(w)
+    k = wl.make_kode(w, force_dense=force_dense)
     x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
     mu, var = k.solve_mv(x0d, theta=thd)
     torch.cuda.synchronize()
@@ -128,16 +134,23 @@ def test_fitz_full_size_properties():
     ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], None, oracle.MODE_MV)
     assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
     assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-9
+    if not force_dense:      # the two families agree with each other to rounding as well
+        kd = wl.make_kode(w, force_dense=True)
+        mud, vard = kd.solve_mv(x0d[:4096], theta=thd[:4096])
+        assert float((mud - mu[:4096]).abs().max()) < 1e-10
+        assert float((vard - var[:4096]).abs().max()) < 1e-12 * float(var.abs().max()) + 1e-22
     # smoothed variance never exceeds the filtered one at the end point, and is PSD-diagonal
     assert bool((torch.diagonal(var[0], dim1=-2, dim2=-1) >= 0).all())
 
 
 @pytest.mark.parametrize("maker,B,mode", [
-    (lambda B: wl.lorenz_batch(B), 1024, "sim"),
-    (lambda B: wl.mseir_batch(B), 2048, "mv")])
-def test_wide_state_configs_at_full_length(maker, B, mode):
-    """BASELINE configs 3 and 4 at their full n_eval (5000 / 1000) on a reduced batch, with
-    an oracle spot-check; batch-size independence is covered by permutation equivariance."""
+    (lambda B: wl.lorenz_batch(B), 16384, "sim"),
+    (lambda B: wl.mseir_batch(B), 32768, "mv")])
+def test_wide_state_configs_at_full_size(maker, B, mode):
+    """BASELINE configs 3 (Lorenz63, 16,384 x0, n_eval 5000, solve_sim) and 4 (MSEIR, 32,768
+    theta, n_eval 1000, solve_mv) at FULL size, with an oracle spot-check and the
+    size-independent properties (finite, status clean, covariance theta-invariant,
+    permutation equivariance)."""
     w, x0, theta = maker(B)
     n = len(w["x0"])
     np.random.seed(2)
@@ -154,14 +167,65 @@ def test_wide_state_configs_at_full_length(maker, B, mode):
         assert traj_err(got[:, :2501], ref["x"][:, :2501]).max() < 1e-8
         assert traj_err(got, ref["x"]).max() < 1e-3
         perm = torch.arange(B - 1, -1, -1, device="cuda")
-        assert bool((k.solve_sim(x0d[perm], theta=thd[perm]) == x[perm]).all())
+        x = x[perm]
+        assert bool((k.solve_sim(x0d[perm], theta=thd[perm]) == x).all())
     else:
-        mu, var = k.solve_mv(x0d, theta=thd)
+        mu, var = k.solve_mv(x0d, theta=thd)          # 63 GB of variance output at full size
         assert bool(torch.isfinite(mu).all()) and int(k.status.abs().sum()) == 0
-        assert bool((var == var[0:1]).all())
+        for lo in range(0, B, 4096):                  # chunked compare: no 63 GB temporaries
+            assert bool((var[lo:lo + 4096] == var[0:1]).all())
         ref = oracle.solve_batch(po, x0[pick], theta[pick], None, oracle.MODE_MV)
         assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
         assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+
+
+@pytest.mark.parametrize("maker,B,mode", [
+    (lambda B: wl.lorenz_batch(B, N=1000, tmax=4.0), 256, "sim"),
+    (lambda B: wl.mseir_batch(B, N=250), 256, "mv")])
+def test_wide_state_dense_fallback(maker, B, mode):
+    """The dense (rolled, local-memory) kernels for n_state 9 and 15: slower, any Q / R / W."""
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(8).standard_normal((n, w["N"])))
+    k = wl.make_kode(w, z_state=z, force_dense=True)
+    assert k.kernel_family == ("dense", "rolled")
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    pick = [0, 100, 255]
+    po = wl.make_oracle_problem(w)
+    if mode == "sim":
+        x = k.solve_sim(x0d, theta=thd)
+        ref = oracle.solve_batch(po, x0[pick], theta[pick], z, oracle.MODE_SIM)
+        assert traj_err(x[pick].cpu().numpy(), ref["x"]).max() < 1e-8
+    else:
+        mu, var = k.solve_mv(x0d, theta=thd)
+        ref = oracle.solve_batch(po, x0[pick], theta[pick], None, oracle.MODE_MV)
+        assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
+        assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+
+
+def test_dense_prior_uses_dense_family():
+    """A prior that is NOT block diagonal (random SPD R, dense Q) must run on the dense
+    kernels automatically and still match the oracle."""
+    w, x0, theta = wl.fitz_batch(300, seed=2)
+    rng = np.random.default_rng(12)
+    A = rng.standard_normal((6, 6))
+    w = dict(w)
+    w["R"] = np.asfortranarray(w["R"] + 1e-9 * (A @ A.T))
+    w["Q"] = np.asfortranarray(w["Q"] + 1e-3 * rng.standard_normal((6, 6)))
+    w["W"] = np.asfortranarray(w["W"] + 1e-2 * rng.standard_normal((2, 6)))
+    w["c"] = 1e-3 * rng.standard_normal(6)
+    z = np.asfortranarray(rng.standard_normal((6, 400)))
+    k = wl.make_kode(w, z_state=z)
+    assert k.kernel_family == ("dense", "registers")
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+    x, mu, var = k.solve(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda())
+    assert traj_err(mu.cpu().numpy(), ref["mu"]).max() < 1e-9
+    assert var_err(var.cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+    assert traj_err(x.cpu().numpy(), ref["x"]).max() < 1e-8
+    # setting a structured prior back re-selects the block-diagonal family
+    w0 = wl.fitz()
+    k.wgt_state, k.var_state, k.wgt_meas, k.mu_state = w0["Q"], w0["R"], w0["W"], w0["c"]
+    assert k.kernel_family[0] == "blockdiag"
 
 
 def test_loglik_matches_oracle_and_sharded_sweep_layout():

@@ -26,41 +26,45 @@ def _setup(name, B=3):
     return g, ode, p, x0, theta
 
 
+@pytest.mark.parametrize("blockdiag", [False, True], ids=["dense", "blockdiag"])
 @pytest.mark.parametrize("name,mtol,vtol,xtol", CASES)
-def test_bodies_match_oracle(name, mtol, vtol, xtol):
+def test_bodies_match_oracle(name, mtol, vtol, xtol, blockdiag):
     g, ode, p, x0, theta = _setup(name)
     ref = oracle.solve_batch(p, x0, theta, g["z"], oracle.MODE_BOTH)
     args = (ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, g["z"])
-    both = hostsim.solve(*args, kind="both")
+    both = hostsim.solve(*args, kind="both", blockdiag=blockdiag)
     assert not both["status"].any() and not ref["status"].any()
     assert traj_err(both["mu"], ref["mu"]).max() < mtol
     assert var_err(both["var"][:, 1:], ref["var"][:, 1:]).max() < vtol
     assert not both["var"][:, 0].any()
     assert traj_err(both["x"], ref["x"]).max() < xtol
-    mv = hostsim.solve(*args, kind="mv")
-    sim = hostsim.solve(*args, kind="sim")
+    mv = hostsim.solve(*args, kind="mv", blockdiag=blockdiag)
+    sim = hostsim.solve(*args, kind="sim", blockdiag=blockdiag)
     np.testing.assert_array_equal(mv["mu"], both["mu"])
     np.testing.assert_array_equal(mv["var"], both["var"])
     np.testing.assert_array_equal(sim["x"], both["x"])
 
 
-def test_per_system_z_and_loglik():
+@pytest.mark.parametrize("blockdiag", [False, True], ids=["dense", "blockdiag"])
+def test_per_system_z_and_loglik(blockdiag):
     g, ode, p, x0, theta = _setup("fitz_n400", B=4)
     rng = np.random.default_rng(3)
     z = rng.standard_normal((4, p.n, p.N))
     ref = oracle.solve_batch(p, x0, theta, z, oracle.MODE_BOTH)
     args = (ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, z)
-    sim = hostsim.solve(*args, kind="sim")
+    sim = hostsim.solve(*args, kind="sim", blockdiag=blockdiag)
     assert traj_err(sim["x"], ref["x"]).max() < 1e-9
     ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
     for kind, key in (("ll_mean", "mu"), ("ll_draw", "x")):
-        r = hostsim.solve(*args, kind=kind, thin_index=ind, state_index=[0, 3], Y=Y, gamma=gam)
+        r = hostsim.solve(*args, kind=kind, thin_index=ind, state_index=[0, 3], Y=Y, gamma=gam,
+                          blockdiag=blockdiag)
         want = [oracle.loglik(ref[key][b], ind, [0, 3], Y, gam) for b in range(4)]
         np.testing.assert_allclose(r["loglik"], want, rtol=1e-9)
 
 
+@pytest.mark.parametrize("blockdiag", [False, True], ids=["dense", "blockdiag"])
 @pytest.mark.parametrize("ig,name", [(1, "schobert"), (2, "chkrebtii")])
-def test_interrogation_variants(ig, name):
+def test_interrogation_variants(ig, name, blockdiag):
     g, ode, p, x0, theta = _setup("fitz_n400", B=2)
     po = oracle.Problem(ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], interrogate=name)
     # schobert (H = 0) leaves Sigma_f singular, so its sampling pass is degenerate (the
@@ -70,7 +74,7 @@ def test_interrogation_variants(ig, name):
     ref = oracle.solve_batch(po, x0, theta, g["z"], mode)
     assert np.isfinite(ref["mu"]).all()
     r = hostsim.solve(ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, g["z"],
-                      kind=kind, ig=ig)
+                      kind=kind, ig=ig, blockdiag=blockdiag)
     assert traj_err(r["mu"], ref["mu"]).max() < 1e-9
     if ig == 1:   # measured components have exactly zero variance: compare on the global scale
         assert np.abs(r["var"] - ref["var"]).max() < 1e-9 * np.abs(ref["var"]).max()
