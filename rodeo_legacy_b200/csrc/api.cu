@@ -113,15 +113,13 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) 
   if (d->ode < 0 || d->ode > 3) return fail(RODEO_E_INVALID, "unknown ode id");
   if (d->interrogate < 0 || d->interrogate > 2) return fail(RODEO_E_INVALID, "unknown interrogate id");
   if (d->n_meas != kOdeMeas[d->ode]) return fail(RODEO_E_INVALID, "n_meas does not match the ode");
-  int dev = 0;
-  CK(cudaGetDevice(&dev));
   rodeo_problem *p = new rodeo_problem();
   p->n = d->n_state;
   p->m = d->n_meas;
   p->N = d->n_eval;
   p->ode = d->ode;
   p->ig = d->interrogate;
-  p->device = dev;
+  p->device = 0;
   p->tmin = d->tmin;
   p->tmax = d->tmax;
   p->flags = d->flags;
@@ -129,10 +127,15 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) 
   p->Q.assign(d->wgt_state, d->wgt_state + (size_t)p->n * p->n);
   p->c.assign(d->mu_state, d->mu_state + p->n);
   p->R.assign(d->var_state, d->var_state + (size_t)p->n * p->n);
-  int rc = select_kernel_set(p);
+  int rc = select_kernel_set(p);   // before any CUDA call: unsupported shapes fail the same way everywhere
   if (rc) {
     delete p;
     return rc;
+  }
+  cudaError_t ce = cudaGetDevice(&p->device);
+  if (ce != cudaSuccess) {
+    delete p;
+    return cuda_fail(ce, "cudaGetDevice");
   }
   *out = p;
   return RODEO_OK;
