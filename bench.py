@@ -42,8 +42,8 @@ def workload_config(extra=None):
     c = {"workload": "fitzhugh-nagumo solve_mv, n_state 6, n_meas 2, n_eval 400, "
                      "65536 theta draws per GPU (BASELINE configs[1])",
          "batch_per_gpu": BATCH, "n_eval": N_EVAL, "mode": "solve_mv", "prior": "ibm q=3, sigma 0.1",
-         "l2": "no flush: each step streams 5.7 GB of history and 8.8 GB of output per GPU, "
-               ">100x the 126 MB L2"}
+         "l2": "no flush: each step streams >3.7 GB of filter history (written, then read back) and "
+               "8.8 GB of output per GPU, >100x the 126 MB L2"}
     if extra:
         c.update(extra)
     return c
@@ -114,7 +114,9 @@ def cpu_baseline(seconds=10.0, chunk=1024, nthreads=0):
     oracle.build()
     w, x0, theta = wl.fitz_batch(chunk * 64, seed=0)
     p = wl.make_oracle_problem(w)
-    cores = oracle.max_threads() if nthreads <= 0 else nthreads
+    if nthreads <= 0:            # torchrun exports OMP_NUM_THREADS=1: ask for every usable core
+        nthreads = host_cores()
+    cores = nthreads
     oracle.solve_batch(p, x0[:max(cores, 8)], theta[:max(cores, 8)], None, oracle.MODE_MV, nthreads)
     done, t0 = 0, time.perf_counter()
     while True:
@@ -127,6 +129,13 @@ def cpu_baseline(seconds=10.0, chunk=1024, nthreads=0):
     return {"value": done / el, "unit": UNIT, "cores": int(cores), "kind": "port",
             "sample": f"{done} of the workload's solves (chunks of {chunk}), {el:.1f} s, "
                       "C port of the reference arithmetic, gcc -O3, OpenMP over systems"}, done, el
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args):
@@ -142,13 +151,13 @@ def run_reference(args):
     oracle.build()
     w, x0, theta = wl.fitz_batch(chunk, seed=0)
     p = wl.make_oracle_problem(w)
-    cores = oracle.max_threads()
+    cores = host_cores()         # explicit: torchrun exports OMP_NUM_THREADS=1
     for _ in range(max(1, min(args.warmup, 2))):
-        oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV)
+        oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV, cores)
     steps = max(1, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(steps):
-        oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV)
+        oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV, cores)
     el = time.perf_counter() - t0
     v = steps * chunk / el
     sample = (f"each step = {chunk} of the workload's 65536 solves; {steps} steps timed "

@@ -1,0 +1,232 @@
+// kalman_bdw.cuh -- backward (smoother) kernel of the block-diagonal family with one WARP PER
+// DIAGONAL BLOCK: a CTA of nb = n_meas warps owns one tile of 32 systems; lane = system,
+// warp = block.
+//
+// In the block-diagonal family the smoother decouples into nb independent p-dimensional
+// smoothers (kalman_common.cuh), so the blocks of one system need not share a thread.  Spreading
+// them over warps multiplies the resident parallelism by nb (MSEIR: 5x, Lorenz63: 3x) and cuts
+// the registers per thread to one p x p block's worth, which is what the wide-state configs
+// need: their batches (16,384 / 32,768 systems) are too small to fill 148 SMs with one thread
+// per system.
+//
+// Data movement is the staged scheme of kalman_staged.cuh at CTA scope:
+//   * history ring: ONE cp.async.bulk (TMA) per time index brings the tile's whole record
+//     (NE*32 doubles, contiguous in HBM) into a two-slot shared-memory ring two time indices
+//     ahead; completion on an mbarrier all warps wait on; each warp reads only its block's rows.
+//   * outputs: warps write their block's part of each system's output row into a staging tile
+//     (two tiles, alternating per pass), then ALL threads store the tile so that every system's
+//     contiguous run in out[b][t][...] is written by neighbouring threads (coalesced).  The
+//     variance goes out in passes of PB blocks' columns so the tile stays ~10 KB for any n.
+#pragma once
+#include <cstdint>
+
+#include "kalman_staged.cuh"
+
+namespace rodeo {
+
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+struct BdwLayout {
+  static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, NE = Fam::NE, PS = Fam::PS;
+  static constexpr int REC = NE * kTile;
+  static constexpr int VW = n * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0));   // "vector" pass width
+  static constexpr int COLW = p * n;                                       // one block's variance columns
+  static constexpr int PB = (48 / COLW) < 1 ? 1 : ((48 / COLW) > nb ? nb : (48 / COLW));
+  static constexpr int NPASS_VAR = DO_VAR ? (nb + PB - 1) / PB : 0;
+  static constexpr int TW0 = (DO_VAR && PB * COLW > VW) ? PB * COLW : VW;
+  static constexpr int TW = (TW0 + 1) / 2 * 2;                             // tile row stride (even)
+  static constexpr int THREADS = nb * 32;
+  static constexpr int SMEM_DOUBLES = 2 * REC + 2 * kTile * TW + 2;
+  static constexpr size_t smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
+  // resident CTAs per SM to aim for: as many as shared memory allows, registers capped at 128
+  static constexpr int BY_SMEM = (int)((227 * 1024) / smem_bytes);
+  static constexpr int BY_REGS = 65536 / (THREADS * 128);
+  static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
+};
+
+// Store columns [C0, C0+LEN) of every system's run of W doubles from the staging tile
+// (system s at tile[s*TW + OFF ..]) to out + ((b0+s)*T1 + t)*W + C0, cooperatively.
+template <int W, int C0, int LEN, int OFF, int TW, int NTHREADS>
+__device__ __forceinline__ void flush_part(const double *tile, double *out, long b0, long B, long T1, int t,
+                                           int tid) {
+  constexpr bool V2 = (W % 2 == 0) && (C0 % 2 == 0) && (LEN % 2 == 0) && (OFF % 2 == 0);
+  if (V2) {
+    constexpr int C = LEN / 2;
+#pragma unroll
+    for (int q0 = 0; q0 < kTile * C; q0 += NTHREADS) {
+      const int q = q0 + tid;
+      if (q < kTile * C) {
+        const int s = q / C, c = q - s * C;
+        if (b0 + s < B) {
+          const double2 v = *reinterpret_cast<const double2 *>(tile + s * TW + OFF + 2 * c);
+          *reinterpret_cast<double2 *>(out + ((b0 + s) * T1 + t) * W + C0 + 2 * c) = v;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q0 = 0; q0 < kTile * LEN; q0 += NTHREADS) {
+      const int q = q0 + tid;
+      if (q < kTile * LEN) {
+        const int s = q / LEN, c = q - s * LEN;
+        if (b0 + s < B) out[((b0 + s) * T1 + t) * W + C0 + c] = tile[s * TW + OFF + c];
+      }
+    }
+  }
+}
+
+// Per-warp work with the block index as a compile-time constant (so the block's Q, c, R are
+// immediate constant-bank operands): Blk<A>::run is selected by a warp-uniform switch.
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, int A>
+struct BdwBlock {
+  static constexpr int p = Fam::p, n = Fam::n, PS = Fam::PS;
+  __device__ __forceinline__ static int step(const typename Fam::PriorT &P, bool terminal, const double *rec,
+                                             const double *zt, double *mus, double *Ss, double *x) {
+    const double *rmu = rec + A * p * kTile, *rS = rec + (n + A * PS) * kTile;
+    const double *z = DO_SIM ? zt + A * p : nullptr;
+    if (terminal) return reg::smooth_terminal<p, DO_MEAN, DO_VAR, DO_SIM>(rmu, rS, z, mus, Ss, x);
+    return reg::smooth_step<p, DO_MEAN, DO_VAR, DO_SIM>(P.Q[A], P.c + A * p, P.R[A], rmu, rS, z, mus, Ss, x);
+  }
+};
+
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, int A = 0>
+__device__ __forceinline__ int bdw_dispatch(int blk, const typename Fam::PriorT &P, bool terminal,
+                                            const double *rec, const double *zt, double *mus, double *Ss,
+                                            double *x) {
+  if constexpr (A + 1 < Fam::nb) {
+    if (blk != A) return bdw_dispatch<Fam, DO_MEAN, DO_VAR, DO_SIM, A + 1>(blk, P, terminal, rec, zt, mus, Ss, x);
+  }
+  return BdwBlock<Fam, DO_MEAN, DO_VAR, DO_SIM, A>::step(P, terminal, rec, zt, mus, Ss, x);
+}
+
+// Variance pass G of a step: the warps of blocks [G*PB, G*PB + NBLK) write their columns of the
+// dense n x n output (own block's rows from Ss, zeros elsewhere) into tile (G+1)&1; after a CTA
+// barrier all threads store those columns of every system's run.  Recurses over G at compile
+// time so that every length and offset is a constant.
+template <class Fam, class L, int G>
+__device__ __forceinline__ void bdw_var_passes(double *tiles, const double *Ss, double *var_out, long b0, long B,
+                                               long T1, int t, int tid, int blk, int lane) {
+  constexpr int p = L::p, n = L::n, nb = L::nb, TW = L::TW;
+  if constexpr (G < L::NPASS_VAR) {
+    constexpr int FIRST = G * L::PB;
+    constexpr int NBLK = (nb - FIRST) < L::PB ? (nb - FIRST) : L::PB;
+    double *tl = tiles + ((G + 1) & 1) * kTile * TW;
+    if (blk >= FIRST && blk < FIRST + NBLK) {
+      double *row = tl + lane * TW + (blk - FIRST) * L::COLW;
+#pragma unroll
+      for (int jj = 0; jj < p; jj++) {
+#pragma unroll
+        for (int i = 0; i < n; i++) row[jj * n + i] = 0.0;
+      }
+      double *own = row + blk * p;  // this block's rows inside each of its columns
+#pragma unroll
+      for (int jj = 0; jj < p; jj++) {
+#pragma unroll
+        for (int ii = 0; ii < p; ii++) own[jj * n + ii] = Ss[sidx<p>(ii, jj)];
+      }
+    }
+    __syncthreads();
+    flush_part<n * n, FIRST * L::COLW, NBLK * L::COLW, 0, TW, L::THREADS>(tl, var_out, b0, B, T1, t, tid);
+    bdw_var_passes<Fam, L, G + 1>(tiles, Ss, var_out, b0, B, T1, t, tid, blk, lane);
+  }
+}
+
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+__global__ void __launch_bounds__(BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::THREADS,
+                                  BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::MINB)
+kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  using L = BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  constexpr int p = L::p, n = L::n, PS = L::PS, REC = L::REC, TW = L::TW, NT = L::THREADS;
+  extern __shared__ __align__(16) double smem[];
+  double *ring = smem;
+  double *tiles = ring + 2 * REC;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(tiles + 2 * kTile * TW);
+  const int tid = threadIdx.x, blk = tid / 32, lane = tid % 32;
+  const long tile = blockIdx.x;
+  const int N = P.n_eval;
+  const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
+  const bool valid = b < a.B;
+  const double *hist_tile = a.hist + (size_t)tile * N * REC;
+  constexpr uint32_t kRecBytes = REC * sizeof(double);
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+      if (N - 1 - k >= 0) {
+        mbar_arrive_expect_tx(&bar[k], kRecBytes);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)(N - 1 - k) * REC, kRecBytes, &bar[k]);
+      }
+  }
+  double mus[p], Ss[PS], x[p];
+  int fail = 0;
+  const double *zb = DO_SIM ? a.z + (valid ? b : b0) * a.z_stride : nullptr;
+  uint32_t phase = 0;
+  for (int t = N; t >= 0; t--) {
+    if (t >= 1) {
+      const int k = (N - t) & 1;
+      mbar_wait(&bar[k], (phase >> k) & 1u);
+      phase ^= 1u << k;
+      const double *rec = ring + k * REC + lane;
+      const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
+      const int f = bdw_dispatch<Fam, DO_MEAN, DO_VAR, DO_SIM>(blk, P, t == N, rec, zt, mus, Ss, x);
+      if (f && !fail) fail = blk * p + f;
+      __syncthreads();  // every warp is done with ring slot k (and with last step's tiles)
+      if (tid == 0 && t - 3 >= 0) {
+        mbar_arrive_expect_tx(&bar[k], kRecBytes);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)(t - 3) * REC, kRecBytes, &bar[k]);
+      }
+    } else {  // time index 0: the initial state is known, Sigma_0 = 0 (KalmanODE.pyx:445, 409)
+#pragma unroll
+      for (int i = 0; i < p; i++) {
+        const double v = valid ? a.x0[b * n + blk * p + i] : 0.0;
+        if (DO_MEAN) mus[i] = v;
+        if (DO_SIM) x[i] = v;
+      }
+      if (DO_VAR) {
+#pragma unroll
+        for (int i = 0; i < PS; i++) Ss[i] = 0.0;
+      }
+      __syncthreads();
+    }
+    // ---- pass 0: means and draws ----------------------------------------------------------
+    if (L::VW > 0) {
+      double *row = tiles + lane * TW;
+      if (DO_MEAN) {
+#pragma unroll
+        for (int i = 0; i < p; i++) row[blk * p + i] = mus[i];
+      }
+      if (DO_SIM) {
+#pragma unroll
+        for (int i = 0; i < p; i++) row[(DO_MEAN ? n : 0) + blk * p + i] = x[i];
+      }
+      __syncthreads();
+      if (DO_MEAN) flush_part<n, 0, n, 0, TW, NT>(tiles, a.mu_out, b0, a.B, T1, t, tid);
+      if (DO_SIM) flush_part<n, 0, n, (DO_MEAN ? n : 0), TW, NT>(tiles, a.x_out, b0, a.B, T1, t, tid);
+    }
+    // ---- variance passes: PB blocks' columns at a time, alternating tiles ---------------------
+    if (DO_VAR) bdw_var_passes<Fam, L, 0>(tiles, Ss, a.var_out, b0, a.B, T1, t, tid, blk, lane);
+  }
+  if (valid && a.status && fail) atomicCAS(a.status + b, 0, fail);
+}
+
+}  // namespace rodeo
+
+namespace rodeo {
+
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+cudaError_t launch_backward_bdw(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  using L = BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  auto kern = kalman_backward_bdw<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((a.B + kTile - 1) / kTile);
+  kern<<<grid, L::THREADS, L::smem_bytes, s>>>(make_prior<Fam>(h), a);
+  return cudaGetLastError();
+}
+
+}  // namespace rodeo
