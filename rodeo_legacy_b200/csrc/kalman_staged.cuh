@@ -66,6 +66,10 @@ struct StagedLayout {
   static constexpr int ROW = (OUTW + 1) / 2 * 2;                                 // row stride (even)
   static constexpr int WARP_DOUBLES = 2 * REC + kTile * ROW + 2;                 // + 2 mbarriers
   static constexpr size_t smem_bytes = (size_t)kStagedWarps * WARP_DOUBLES * sizeof(double);
+  // No min-blocks launch bound: capping registers (tried: 168 / 128 per thread for the
+  // block-diagonal family) makes ptxas spill inside the unrolled step and DOUBLED the kernel
+  // time on B200 (2.52 -> 5.12 ms, FN solve_mv); 254 registers and 8 warps / SM is faster.
+  static constexpr int MINB = 1;
 };
 
 // Store one output array from the staging tile: every system s of the tile owns a run of
@@ -100,7 +104,7 @@ __device__ __forceinline__ void flush_runs(const double *stage, double *out, lon
 }
 
 template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
-__global__ void __launch_bounds__(kStagedThreads)
+__global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::MINB)
 kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   using L = StagedLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
   constexpr int n = Fam::n, REC = L::REC, ROW = L::ROW;

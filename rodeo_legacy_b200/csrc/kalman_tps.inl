@@ -11,6 +11,7 @@ template <class Ode_, int n_>
 struct DenseFam {
   using Ode = Ode_;
   static constexpr int n = n_, m = Ode::n_meas, NS = Sym<n_>::size, NE = n_ + Sym<n_>::size;
+  static constexpr bool kBlockDiag = false;
   using PriorT = Prior<n_, Ode_::n_meas>;
 
   template <int IG>
@@ -78,6 +79,7 @@ struct BdFam {
   using Ode = Ode_;
   static constexpr int p = p_, nb = Ode::n_meas, n = p_ * Ode_::n_meas, m = Ode::n_meas;
   static constexpr int PS = Sym<p_>::size, NS = Ode_::n_meas * Sym<p_>::size, NE = n + NS;
+  static constexpr bool kBlockDiag = true;
   using PriorT = PriorBD<p_, Ode_::n_meas>;
 
   template <int IG>
