@@ -137,6 +137,14 @@ size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p);
 /* Upper bound for the handle-owned history workspace (default: 48 GiB).  A batch whose
  * history exceeds it is processed in chunks, transparently. */
 int rodeo_cuda_set_workspace_limit(rodeo_problem *p, size_t bytes);
+/* Checkpoint interval of the filter history: 1 stores the filtered moments of every time
+ * index; k = 2 or 4 stores every k-th and the backward pass re-runs the filter in between
+ * (bit-identical results, k-fold less history traffic and workspace); 0 (default) = auto: 2
+ * where a kernel exists for it.  Honoured by the thread-per-system register kernels with the
+ * probde interrogation; otherwise 1 is used.
+ * rodeo_cuda_get_checkpoint returns the interval actually in effect. */
+int rodeo_cuda_set_checkpoint(rodeo_problem *p, int interval);
+int rodeo_cuda_get_checkpoint(const rodeo_problem *p);
 /* Pre-allocate the workspace for batches up to max_batch (otherwise grown on demand). */
 int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch);
 

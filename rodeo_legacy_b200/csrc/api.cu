@@ -37,6 +37,7 @@ struct rodeo_problem {
   std::vector<double> W, Q, c, R;  // column-major host copies
   const KernelSet *ks;
   int flags = 0;
+  int ck = 0;                      // requested checkpoint interval of the filter history (0 = auto)
   void *ws = nullptr;
   size_t ws_bytes = 0;
   size_t ws_limit = (size_t)48 << 30;
@@ -179,9 +180,30 @@ int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t 
   return RODEO_OK;
 }
 
-size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
-  return p ? (size_t)p->N * p->ks->hist_elems * sizeof(double) : 0;
+// checkpoint interval actually used: the requested one where a kernel exists for it
+static int effective_ck(const rodeo_problem *p) {
+  // auto: interval 2 for the block-diagonal family (measured on B200: FN solve_mv 3.28 -> 2.85 ms,
+  // log-likelihood sweep 2.88 -> 2.30 ms; interval 4 is slower again), 1 for the dense family
+  // (its filter step is FP64-bound: re-running it took the backward kernel from 3.4 to 5.9 ms)
+  const int want = p->ck == 0 ? (p->ks->blockdiag ? 2 : 1) : p->ck;
+  if (want == 1 || p->ig != RODEO_INTERROGATE_PROBDE) return 1;
+  const int slot = ck_slot(want);
+  return (slot >= 0 && p->ks->backward[slot][BK_MV]) ? want : 1;
 }
+
+size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
+  return p ? (size_t)n_records(p->N, effective_ck(p)) * p->ks->hist_elems * sizeof(double) : 0;
+}
+
+int rodeo_cuda_set_checkpoint(rodeo_problem *p, int interval) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (interval != 0 && ck_slot(interval) < 0)
+    return fail(RODEO_E_INVALID, "checkpoint interval must be 0 (auto), 1, 2 or 4");
+  p->ck = interval;
+  return RODEO_OK;
+}
+
+int rodeo_cuda_get_checkpoint(const rodeo_problem *p) { return p ? effective_ck(p) : RODEO_E_INVALID; }
 
 int rodeo_cuda_set_workspace_limit(rodeo_problem *p, size_t bytes) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
@@ -252,6 +274,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   const int n = p->n, nth = kOdeTheta[p->ode];
   const long T1 = (long)p->N + 1;
   const long cap = chunk_capacity(p, batch);
+  const int ck = effective_ck(p), slot = ck_slot(ck);
   int rc = ensure_workspace(p, cap);
   if (rc) return rc;
   HostPrior hp{p->n, p->m, p->N, p->tmin, p->tmax, p->W.data(), p->Q.data(), p->c.data(), p->R.data()};
@@ -274,6 +297,8 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     a.z = z ? z + off * z_stride : nullptr;
     a.z_stride = z_stride;
     a.hist = (double *)p->ws;
+    a.ck = ck;
+    a.n_steps = p->N + 1;
     a.x_out = x_out ? x_out + off * T1 * n : nullptr;
     a.mu_out = mu_out ? mu_out + off * T1 * n : nullptr;
     a.var_out = var_out ? var_out + off * T1 * n * n : nullptr;
@@ -290,7 +315,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 0], stream));
     CK(p->ks->forward[p->ig](hp, a, stream));
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
-    CK(p->ks->backward[bk](hp, a, stream));
+    CK(p->ks->backward[slot][bk](hp, a, stream));
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
     p->launches += 2;
   }

@@ -13,6 +13,10 @@
 //   * history ring: ONE cp.async.bulk (TMA) per time index brings the tile's whole record
 //     (NE*32 doubles, contiguous in HBM) into a two-slot shared-memory ring two time indices
 //     ahead; completion on an mbarrier all warps wait on; each warp reads only its block's rows.
+//   * checkpointed history (SolveArgs::ck > 1) is NOT offered by this kernel: re-running the
+//     filter needs the blocks to exchange their predicted means through shared memory every
+//     step, and on B200 the extra CTA barriers cost more than the saved HBM traffic
+//     (measured: Lorenz63 5.7 -> 8.2 ms, MSEIR 17.9 -> 27.7 ms at interval 2).
 //   * outputs: warps write their block's part of each system's output row into a staging tile
 //     (two tiles, alternating per pass), then ALL threads store the tile so that every system's
 //     contiguous run in out[b][t][...] is written by neighbouring threads (coalesced).  The
@@ -83,8 +87,8 @@ struct BdwBlock {
                                              const double *zt, double *mus, double *Ss, double *x) {
     const double *rmu = rec + A * p * kTile, *rS = rec + (n + A * PS) * kTile;
     const double *z = DO_SIM ? zt + A * p : nullptr;
-    if (terminal) return reg::smooth_terminal<p, DO_MEAN, DO_VAR, DO_SIM>(rmu, rS, z, mus, Ss, x);
-    return reg::smooth_step<p, DO_MEAN, DO_VAR, DO_SIM>(P.Q[A], P.c + A * p, P.R[A], rmu, rS, z, mus, Ss, x);
+    if (terminal) return reg::smooth_terminal<p, kTile, DO_MEAN, DO_VAR, DO_SIM>(rmu, rS, z, mus, Ss, x);
+    return reg::smooth_step<p, kTile, DO_MEAN, DO_VAR, DO_SIM>(P.Q[A], P.c + A * p, P.R[A], rmu, rS, z, mus, Ss, x);
   }
 };
 
@@ -142,7 +146,7 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
   uint64_t *bar = reinterpret_cast<uint64_t *>(tiles + 2 * kTile * TW);
   const int tid = threadIdx.x, blk = tid / 32, lane = tid % 32;
   const long tile = blockIdx.x;
-  const int N = P.n_eval;
+  const int N = P.n_eval;   // checkpoint interval 1: record r holds time index N - r, R = N records
   const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
   const bool valid = b < a.B;
   const double *hist_tile = a.hist + (size_t)tile * N * REC;
@@ -157,9 +161,9 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
   if (tid == 0) {
 #pragma unroll
     for (int k = 0; k < 2; k++)
-      if (N - 1 - k >= 0) {
+      if (k < N) {
         mbar_arrive_expect_tx(&bar[k], kRecBytes);
-        bulk_g2s(ring + k * REC, hist_tile + (size_t)(N - 1 - k) * REC, kRecBytes, &bar[k]);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)k * REC, kRecBytes, &bar[k]);
       }
   }
   double mus[p], Ss[PS], x[p];
@@ -176,9 +180,9 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
       const int f = bdw_dispatch<Fam, DO_MEAN, DO_VAR, DO_SIM>(blk, P, t == N, rec, zt, mus, Ss, x);
       if (f && !fail) fail = blk * p + f;
       __syncthreads();  // every warp is done with ring slot k (and with last step's tiles)
-      if (tid == 0 && t - 3 >= 0) {
+      if (tid == 0 && N - t + 2 < N) {  // refill the slot with record r + 2 (time index t - 2)
         mbar_arrive_expect_tx(&bar[k], kRecBytes);
-        bulk_g2s(ring + k * REC, hist_tile + (size_t)(t - 3) * REC, kRecBytes, &bar[k]);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)(N - t + 2) * REC, kRecBytes, &bar[k]);
       }
     } else {  // time index 0: the initial state is known, Sigma_0 = 0 (KalmanODE.pyx:445, 409)
 #pragma unroll

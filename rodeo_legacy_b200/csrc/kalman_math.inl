@@ -204,19 +204,20 @@ RD_UNROLL
 }
 
 // ---- smoother, one n-dimensional (block of a) system --------------------------------------
-// History elements are read through (rec_mu, rec_S): element i at ptr[i * kTile].
+// History elements are read through (rec_mu, rec_S): element i at ptr[i * STRIDE] (STRIDE =
+// kTile for a record in the tiled history / shared-memory ring, 1 for a thread-private array).
 
 // Terminal time index N (KalmanODE.pyx:445-449, 410-414); zt = z[:, N-1] (this block's rows).
-template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 RD_HD int smooth_terminal(const double *rec_mu, const double *rec_S, const double *zt_ptr, double *mus,
                           double *Ss, double *x) {
   constexpr int NS = Sym<n>::size;
   double muf[n], Sf[NS];
   int fail = 0;
 RD_UNROLL
-  for (int i = 0; i < n; i++) muf[i] = rec_mu[i * kTile];
+  for (int i = 0; i < n; i++) muf[i] = rec_mu[i * STRIDE];
 RD_UNROLL
-  for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * kTile];
+  for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * STRIDE];
   if (DO_MEAN) {
 RD_UNROLL
     for (int i = 0; i < n; i++) mus[i] = muf[i];
@@ -237,7 +238,7 @@ RD_UNROLL
 // One smoother step t+1 -> t (KalmanODE.pyx:452-461 / 417-425 / 381-392); zt_ptr = z[:, t-1].
 // The filtered covariance is re-read from the record where it is needed a second time instead
 // of being held in registers across the Cholesky / triangular solves.
-template <int n, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 RD_HD int smooth_step(const double *Q, const double *c, const double *R, const double *rec_mu,
                       const double *rec_S, const double *zt_ptr, double *mus, double *Ss, double *x) {
   constexpr int NS = Sym<n>::size;
@@ -246,9 +247,9 @@ RD_HD int smooth_step(const double *Q, const double *c, const double *R, const d
   {
     double Sf[NS];
 RD_UNROLL
-    for (int i = 0; i < n; i++) muf[i] = rec_mu[i * kTile];
+    for (int i = 0; i < n; i++) muf[i] = rec_mu[i * STRIDE];
 RD_UNROLL
-    for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * kTile];
+    for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * STRIDE];
     // predicted moments at t+1, recomputed exactly as the forward pass computed them
     predict_mean<n>(Q, c, muf, mup);
     predict_var<n, true>(Q, R, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
@@ -285,7 +286,7 @@ RD_UNROLL
     }
 RD_UNROLL
     for (int i = 0; i < NS; i++) {
-      Sf[i] = rec_S2[i * kTile];
+      Sf[i] = rec_S2[i * STRIDE];
       V[i] = Sf[i];
     }
     // V~ = Sigma_f - T~^T (Q Sigma_f): row k of Q Sigma_f is recomputed (T was overwritten)
@@ -323,7 +324,7 @@ RD_UNROLL
       }
 RD_UNROLL
       for (int j = i; j < n; j++) {
-        double s = rec_S2[sidx<n>(i, j) * kTile];
+        double s = rec_S2[sidx<n>(i, j) * STRIDE];
 RD_UNROLL
         for (int l = 0; l < n; l++) s += G[l] * T[l * n + j];
         Sn[sidx<n>(i, j)] = s;

@@ -32,7 +32,9 @@ struct SolveArgs {
   const double *theta; // [B][n_theta] or nullptr
   const double *z;     // column-major (n x N) per system, or nullptr
   long z_stride;       // 0: shared, n*N: per system
-  double *hist;        // [ceil(B/32)][N][NE][32]
+  double *hist;        // [ceil(B/32)][R][NE][32], R = n_records(N, ck)
+  int ck;              // checkpoint interval: records exist for time indices N, N-ck, N-2ck, ... >= 1
+  int n_steps;         // N + 1 (time points per system in the outputs)
   double *x_out, *mu_out, *var_out;
   int *status;
   // thinned log-likelihood epilogue (examples/inference.py:54-56, 66-94)
@@ -85,16 +87,24 @@ template <bool UNROLL>
 struct Bodies;
 template <>
 struct Bodies<true> {
-  template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+  template <class Fam, int IG>
+  RD_HD static void forward(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
+    reg::forward_body<Fam, IG>(P, a, b);
+  }
+  template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
   RD_HD static void backward(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
-    reg::backward_body<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
+    reg::backward_body<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
   }
 };
 template <>
 struct Bodies<false> {
-  template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+  template <class Fam, int IG>
+  RD_HD static void forward(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
+    loc::forward_body<Fam, IG>(P, a, b);
+  }
+  template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
   RD_HD static void backward(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
-    loc::backward_body<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
+    loc::backward_body<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
   }
 };
 

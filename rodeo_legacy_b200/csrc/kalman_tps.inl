@@ -1,11 +1,18 @@
 // kalman_tps.inl -- thread-per-system forward / backward bodies (see kalman_tps.cuh), for the
 // two problem families:
-//   DenseFam<Ode, n>   general dense Q, R, W                     (history NE = n + n(n+1)/2)
+//   DenseFam<Ode, n>   general dense Q, R, W                     (record NE = n + n(n+1)/2)
 //   BdFam<Ode, p>      block-diagonal Q, R with nb = n_meas blocks of size p, W row a inside
-//                      block a (kalman_common.cuh)               (history NE = n + nb p(p+1)/2)
-// A family provides: forward<IG>() -- the whole forward filter of one system; bw_terminal /
-// bw_step -- the smoother recursion on a history record; var_at -- element (i, j) of the
-// carried smoothed covariance.
+//                      block a (kalman_common.cuh)               (record NE = n + nb p(p+1)/2)
+// A family provides: step<IG>() -- one filter step t -> t+1 on (mu, Sigma) held by the thread;
+// forward<IG>() -- the whole forward filter of one system, storing every CK-th filtered record;
+// bw_terminal / bw_step -- the smoother recursion on a record read with a given stride;
+// var_at -- element (i, j) of the carried smoothed covariance.
+//
+// Checkpointing (SolveArgs::ck = CK): only the filtered moments at time indices t with
+// (N - t) % CK == 0 are written to HBM (record r = (N - t) / CK).  The backward pass re-runs the
+// filter from each checkpoint for the CK-1 time indices above it -- the same code on the same
+// inputs, hence bit-identical moments -- trading cheap FP64 work for CK-fold less history
+// traffic.  CK = 1 stores everything.  CK > 1 is offered with the probde interrogation only.
 
 template <class Ode_, int n_>
 struct DenseFam {
@@ -14,62 +21,43 @@ struct DenseFam {
   static constexpr bool kBlockDiag = false;
   using PriorT = Prior<n_, Ode_::n_meas>;
 
+  // One filter step, time index t -> t+1 (KalmanODE.pyx:299-332): predict, interrogate, update.
   template <int IG>
-  RD_HD static void forward(const PriorT &P, const SolveArgs &a, long b) {
-    constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
-    double mu[n], S[NS], th[NT];
-RD_UNROLL
-    for (int i = 0; i < n; i++) mu[i] = a.x0[b * n + i];
-RD_UNROLL
-    for (int i = 0; i < NS; i++) S[i] = 0.0;
-RD_UNROLL
-    for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
-    const int N = P.n_eval;
-    const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
+  RD_HD static int step(const PriorT &P, int t, const double *th, const double *zb, double *mu, double *S) {
+    double mup[n], Sp[NS], y[m];
     int fail = 0;
-    for (int t = 0; t < N; t++) {
-      double mup[n], Sp[NS], y[m];
-      predict_mean<n>(P.Q, P.c, mu, mup);
-      predict_var<n, false>(P.Q, P.R, S, Sp, nullptr);
-      const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
-      if (IG == IG_CHKREBTII) {  // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
-        double xs[n], V[NS], zt[n];
+    predict_mean<n>(P.Q, P.c, mu, mup);
+    predict_var<n, false>(P.Q, P.R, S, Sp, nullptr);
+    const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / P.n_eval;
+    if (IG == IG_CHKREBTII) {  // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
+      double xs[n], V[NS], zt[n];
 RD_UNROLL
-        for (int i = 0; i < NS; i++) V[i] = Sp[i];
+      for (int i = 0; i < NS; i++) V[i] = Sp[i];
 RD_UNROLL
-        for (int i = 0; i < n; i++) zt[i] = zb[(long)t * n + i];
-        int f = state_sim<n>(xs, mup, V, zt);
-        if (f && !fail) fail = f;
-        Ode::template eval<n>(xs, tt, th, y);
-      } else {
-        Ode::template eval<n>(mup, tt, th, y);
-      }
-      int f = update_dense<n, m>(P.W, mup, Sp, y, IG == IG_SCHOBERT);
-      if (f && !fail) fail = f;
-      double *h = a.hist + hist_offset(b, t, N, NE);
-RD_UNROLL
-      for (int i = 0; i < n; i++) {
-        mu[i] = mup[i];
-        h[i * kTile] = mup[i];
-      }
-RD_UNROLL
-      for (int i = 0; i < NS; i++) {
-        S[i] = Sp[i];
-        h[(n + i) * kTile] = Sp[i];
-      }
+      for (int i = 0; i < n; i++) zt[i] = zb[(long)t * n + i];
+      fail = state_sim<n>(xs, mup, V, zt);
+      Ode::template eval<n>(xs, tt, th, y);
+    } else {
+      Ode::template eval<n>(mup, tt, th, y);
     }
-    if (a.status) a.status[b] = fail;
+    int f = update_dense<n, m>(P.W, mup, Sp, y, IG == IG_SCHOBERT);
+    if (f && !fail) fail = f;
+RD_UNROLL
+    for (int i = 0; i < n; i++) mu[i] = mup[i];
+RD_UNROLL
+    for (int i = 0; i < NS; i++) S[i] = Sp[i];
+    return fail;
   }
 
-  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  template <int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
   RD_HD static int bw_terminal(const PriorT &, const double *rec, const double *zt, double *mus, double *Ss,
                                double *x) {
-    return smooth_terminal<n, DO_MEAN, DO_VAR, DO_SIM>(rec, rec + n * kTile, zt, mus, Ss, x);
+    return smooth_terminal<n, STRIDE, DO_MEAN, DO_VAR, DO_SIM>(rec, rec + n * STRIDE, zt, mus, Ss, x);
   }
-  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  template <int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
   RD_HD static int bw_step(const PriorT &P, const double *rec, const double *zt, double *mus, double *Ss,
                            double *x) {
-    return smooth_step<n, DO_MEAN, DO_VAR, DO_SIM>(P.Q, P.c, P.R, rec, rec + n * kTile, zt, mus, Ss, x);
+    return smooth_step<n, STRIDE, DO_MEAN, DO_VAR, DO_SIM>(P.Q, P.c, P.R, rec, rec + n * STRIDE, zt, mus, Ss, x);
   }
   RD_HD static double var_at(const double *Ss, int i, int j) { return Ss[sidx<n>(i, j)]; }
 };
@@ -83,85 +71,65 @@ struct BdFam {
   using PriorT = PriorBD<p_, Ode_::n_meas>;
 
   template <int IG>
-  RD_HD static void forward(const PriorT &P, const SolveArgs &a, long b) {
-    constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
-    double mu[n], S[NS], th[NT];
-RD_UNROLL
-    for (int i = 0; i < n; i++) mu[i] = a.x0[b * n + i];
-RD_UNROLL
-    for (int i = 0; i < NS; i++) S[i] = 0.0;
-RD_UNROLL
-    for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
-    const int N = P.n_eval;
-    const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
+  RD_HD static int step(const PriorT &P, int t, const double *th, const double *zb, double *mu, double *S) {
+    double mup[n], Sp[NS], y[m];
     int fail = 0;
-    for (int t = 0; t < N; t++) {
-      double mup[n], Sp[NS], y[m];
 RD_UNROLL
-      for (int blk = 0; blk < nb; blk++) {
-        predict_mean<p>(P.Q[blk], P.c + blk * p, mu + blk * p, mup + blk * p);
-        predict_var<p, false>(P.Q[blk], P.R[blk], S + blk * PS, Sp + blk * PS, nullptr);
-      }
-      const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
-      if (IG == IG_CHKREBTII) {  // chol of a block-diagonal matrix is the blocks' chol
-        double xs[n];
-RD_UNROLL
-        for (int blk = 0; blk < nb; blk++) {
-          double V[PS], zt[p];
-RD_UNROLL
-          for (int i = 0; i < PS; i++) V[i] = Sp[blk * PS + i];
-RD_UNROLL
-          for (int i = 0; i < p; i++) zt[i] = zb[(long)t * n + blk * p + i];
-          int f = state_sim<p>(xs + blk * p, mup + blk * p, V, zt);
-          if (f && !fail) fail = f;
-        }
-        Ode::template eval<n>(xs, tt, th, y);
-      } else {
-        Ode::template eval<n>(mup, tt, th, y);
-      }
-      double *h = a.hist + hist_offset(b, t, N, NE);
-RD_UNROLL
-      for (int blk = 0; blk < nb; blk++) {
-        int f = update_block<p>(P.w[blk], mup + blk * p, Sp + blk * PS, y[blk], IG == IG_SCHOBERT);
-        if (f && !fail) fail = blk + 1;
-      }
-RD_UNROLL
-      for (int i = 0; i < n; i++) {
-        mu[i] = mup[i];
-        h[i * kTile] = mup[i];
-      }
-RD_UNROLL
-      for (int i = 0; i < NS; i++) {
-        S[i] = Sp[i];
-        h[(n + i) * kTile] = Sp[i];
-      }
+    for (int blk = 0; blk < nb; blk++) {
+      predict_mean<p>(P.Q[blk], P.c + blk * p, mu + blk * p, mup + blk * p);
+      predict_var<p, false>(P.Q[blk], P.R[blk], S + blk * PS, Sp + blk * PS, nullptr);
     }
-    if (a.status) a.status[b] = fail;
+    const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / P.n_eval;
+    if (IG == IG_CHKREBTII) {  // chol of a block-diagonal matrix is the blocks' chol
+      double xs[n];
+RD_UNROLL
+      for (int blk = 0; blk < nb; blk++) {
+        double V[PS], zt[p];
+RD_UNROLL
+        for (int i = 0; i < PS; i++) V[i] = Sp[blk * PS + i];
+RD_UNROLL
+        for (int i = 0; i < p; i++) zt[i] = zb[(long)t * n + blk * p + i];
+        int f = state_sim<p>(xs + blk * p, mup + blk * p, V, zt);
+        if (f && !fail) fail = f;
+      }
+      Ode::template eval<n>(xs, tt, th, y);
+    } else {
+      Ode::template eval<n>(mup, tt, th, y);
+    }
+RD_UNROLL
+    for (int blk = 0; blk < nb; blk++) {
+      int f = update_block<p>(P.w[blk], mup + blk * p, Sp + blk * PS, y[blk], IG == IG_SCHOBERT);
+      if (f && !fail) fail = blk + 1;
+    }
+RD_UNROLL
+    for (int i = 0; i < n; i++) mu[i] = mup[i];
+RD_UNROLL
+    for (int i = 0; i < NS; i++) S[i] = Sp[i];
+    return fail;
   }
 
-  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  template <int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
   RD_HD static int bw_terminal(const PriorT &, const double *rec, const double *zt, double *mus, double *Ss,
                                double *x) {
     int fail = 0;
 RD_UNROLL
     for (int blk = 0; blk < nb; blk++) {
-      int f = smooth_terminal<p, DO_MEAN, DO_VAR, DO_SIM>(rec + blk * p * kTile, rec + (n + blk * PS) * kTile,
-                                                          DO_SIM ? zt + blk * p : nullptr, mus + blk * p,
-                                                          Ss + blk * PS, x + blk * p);
+      int f = smooth_terminal<p, STRIDE, DO_MEAN, DO_VAR, DO_SIM>(
+          rec + blk * p * STRIDE, rec + (n + blk * PS) * STRIDE, DO_SIM ? zt + blk * p : nullptr, mus + blk * p,
+          Ss + blk * PS, x + blk * p);
       if (f && !fail) fail = blk * p + f;
     }
     return fail;
   }
-  template <bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+  template <int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
   RD_HD static int bw_step(const PriorT &P, const double *rec, const double *zt, double *mus, double *Ss,
                            double *x) {
     int fail = 0;
 RD_UNROLL
     for (int blk = 0; blk < nb; blk++) {
-      int f = smooth_step<p, DO_MEAN, DO_VAR, DO_SIM>(P.Q[blk], P.c + blk * p, P.R[blk], rec + blk * p * kTile,
-                                                      rec + (n + blk * PS) * kTile,
-                                                      DO_SIM ? zt + blk * p : nullptr, mus + blk * p,
-                                                      Ss + blk * PS, x + blk * p);
+      int f = smooth_step<p, STRIDE, DO_MEAN, DO_VAR, DO_SIM>(
+          P.Q[blk], P.c + blk * p, P.R[blk], rec + blk * p * STRIDE, rec + (n + blk * PS) * STRIDE,
+          DO_SIM ? zt + blk * p : nullptr, mus + blk * p, Ss + blk * PS, x + blk * p);
       if (f && !fail) fail = blk * p + f;
     }
     return fail;
@@ -170,6 +138,38 @@ RD_UNROLL
     return (i / p == j / p) ? Ss[(i / p) * PS + sidx<p>(i % p, j % p)] : 0.0;
   }
 };
+
+// Whole forward filter of one system; stores the filtered record of every time index t with
+// (N - t) % ck == 0 as record r = (N - t) / ck.
+template <class Fam, int IG>
+RD_HD void forward_body(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
+  using Ode = typename Fam::Ode;
+  constexpr int n = Fam::n, NS = Fam::NS, NE = Fam::NE;
+  constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+  double mu[n], S[NS], th[NT];
+RD_UNROLL
+  for (int i = 0; i < n; i++) mu[i] = a.x0[b * n + i];
+RD_UNROLL
+  for (int i = 0; i < NS; i++) S[i] = 0.0;
+RD_UNROLL
+  for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
+  const int N = P.n_eval, ck = a.ck, R = n_records(N, ck);
+  const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
+  int fail = 0;
+  for (int t = 0; t < N; t++) {
+    int f = Fam::template step<IG>(P, t, th, zb, mu, S);
+    if (f && !fail) fail = f;
+    const int back = N - (t + 1);                 // distance of time index t+1 from the end
+    if (back % ck == 0) {
+      double *h = a.hist + hist_offset(b, back / ck, R, NE);
+RD_UNROLL
+      for (int i = 0; i < n; i++) h[i * kTile] = mu[i];
+RD_UNROLL
+      for (int i = 0; i < NS; i++) h[(n + i) * kTile] = S[i];
+    }
+  }
+  if (a.status) a.status[b] = fail;
+}
 
 // Gaussian log-density pieces accumulated over observed components at one data time.
 template <int n>
@@ -186,72 +186,138 @@ RD_HD double loglik_terms(const SolveArgs &a, int d, const double *X) {
   return lp;
 }
 
+// Deliver the smoothed quantities of time index t: per-step outputs in the reference's return
+// layout, or the thinned log-likelihood accumulation.
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+RD_HD void emit_time(const SolveArgs &a, long b, int t, const double *mus, const double *Ss, const double *x,
+                     double &lp, int &d) {
+  constexpr int n = Fam::n;
+  if (!LOGLIK) {
+    const long T1 = (long)a.n_steps;
+    if (DO_MEAN) {
+      double *o = a.mu_out + (b * T1 + t) * n;
+RD_UNROLL
+      for (int i = 0; i < n; i++) o[i] = mus[i];
+    }
+    if (DO_SIM) {
+      double *o = a.x_out + (b * T1 + t) * n;
+RD_UNROLL
+      for (int i = 0; i < n; i++) o[i] = x[i];
+    }
+    if (DO_VAR) {
+      double *o = a.var_out + (b * T1 + t) * n * n;
+RD_UNROLL
+      for (int j = 0; j < n; j++)
+RD_UNROLL
+        for (int i = 0; i < n; i++) o[j * n + i] = Fam::var_at(Ss, i, j);
+    }
+  } else {
+    while (d >= 0 && a.thin_index[d] == t) {
+      lp += loglik_terms<n>(a, d, DO_SIM ? x : mus);
+      d--;
+    }
+  }
+}
+
 // Generic backward pass: plain global loads and direct (per-thread) global stores.  Used by
 // the rolled family, by every log-likelihood kernel and by tests/hostsim; the register
-// families' solve_mv / solve_sim / solve kernels use the shared-memory staged version in
-// kalman_staged.cuh.  DO_MEAN / DO_VAR: smooth_mv; DO_SIM: smooth_sim; LOGLIK: no per-step
-// output, accumulate the thinned log-likelihood of the mean (DO_MEAN) or draw (DO_SIM).
-template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+// families' solve_mv / solve_sim / solve kernels use the shared-memory staged versions
+// (kalman_staged.cuh, kalman_bdw.cuh).  DO_MEAN / DO_VAR: smooth_mv; DO_SIM: smooth_sim;
+// LOGLIK: no per-step output, accumulate the thinned log-likelihood of the mean (DO_MEAN) or
+// draw (DO_SIM).  CK: checkpoint interval the forward pass used (a.ck == CK).
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 RD_HD void backward_body(const typename Fam::PriorT &P, const SolveArgs &a, long b) {
-  constexpr int n = Fam::n, NE = Fam::NE;
-  const int N = P.n_eval;
-  const long T1 = (long)N + 1;
-  double mus[n], Ss[Fam::NS], x[n];
+  using Ode = typename Fam::Ode;
+  constexpr int n = Fam::n, NS = Fam::NS, NE = Fam::NE;
+  constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+  const int N = P.n_eval, R = n_records(N, CK);
+  double mus[n], Ss[NS], x[n], th[NT];
   int fail = 0;
   double lp = 0.0;
   int d = LOGLIK ? a.n_obs_times - 1 : -1;
   const double *zb = DO_SIM ? a.z + b * a.z_stride : nullptr;
-  double *mu_o = (DO_MEAN && !LOGLIK) ? a.mu_out + b * T1 * n : nullptr;
-  double *var_o = (DO_VAR && !LOGLIK) ? a.var_out + b * T1 * n * n : nullptr;
-  double *x_o = (DO_SIM && !LOGLIK) ? a.x_out + b * T1 * n : nullptr;
-  for (int t = N; t >= 1; t--) {
-    const double *rec = a.hist + hist_offset(b, t - 1, N, NE);
-    const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
-    int f = (t == N) ? Fam::template bw_terminal<DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, mus, Ss, x)
-                     : Fam::template bw_step<DO_MEAN, DO_VAR, DO_SIM>(P, rec, zt, mus, Ss, x);
-    if (f && !fail) fail = f;
-    if (!LOGLIK) {
-      if (DO_MEAN) {
+  if (CK > 1) {
 RD_UNROLL
-        for (int i = 0; i < n; i++) mu_o[(long)t * n + i] = mus[i];
-      }
-      if (DO_SIM) {
-RD_UNROLL
-        for (int i = 0; i < n; i++) x_o[(long)t * n + i] = x[i];
-      }
-      if (DO_VAR) {
-RD_UNROLL
-        for (int j = 0; j < n; j++)
-RD_UNROLL
-          for (int i = 0; i < n; i++) var_o[((long)t * n + j) * n + i] = Fam::var_at(Ss, i, j);
-      }
+    for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
+  }
+  {  // terminal time index N = record 0
+    const double *rec = a.hist + hist_offset(b, 0, R, NE);
+    fail = Fam::template bw_terminal<kTile, DO_MEAN, DO_VAR, DO_SIM>(P, rec, DO_SIM ? zb + (long)(N - 1) * n : nullptr,
+                                                                     mus, Ss, x);
+    emit_time<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(a, b, N, mus, Ss, x, lp, d);
+  }
+  int r = 1;
+  for (int t_hi = N; t_hi > 1;) {   // times t_hi-1 .. max(t_hi-CK, 1) are smoothed in this group
+    const int base = t_hi - CK;      // checkpointed time index of the group, if >= 1
+    if (CK == 1) {
+      const double *rec = a.hist + hist_offset(b, r, R, NE);
+      int f = Fam::template bw_step<kTile, DO_MEAN, DO_VAR, DO_SIM>(P, rec, DO_SIM ? zb + (long)(base - 1) * n : nullptr,
+                                                                    mus, Ss, x);
+      if (f && !fail) fail = f;
+      emit_time<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(a, b, base, mus, Ss, x, lp, d);
     } else {
-      while (d >= 0 && a.thin_index[d] == t) {
-        lp += loglik_terms<n>(a, d, DO_SIM ? x : mus);
-        d--;
+      // start of the re-run: the checkpoint (time base >= 1) or the known initial state (time 0)
+      constexpr int NSCR = CK > 1 ? (CK - 1) * NE : 1;
+      double cur[NE], scratch[NSCR];
+      const int t0 = base >= 1 ? base : 0;
+      const int nfwd = t_hi - 1 - t0;  // recomputed time indices t0+1 .. t_hi-1
+      if (base >= 1) {
+        const double *rec = a.hist + hist_offset(b, r, R, NE);
+RD_UNROLL
+        for (int i = 0; i < NE; i++) cur[i] = rec[i * kTile];
+      } else {
+RD_UNROLL
+        for (int i = 0; i < n; i++) cur[i] = a.x0[b * n + i];
+RD_UNROLL
+        for (int i = 0; i < NS; i++) cur[n + i] = 0.0;
+      }
+      {
+        double fm[n], fS[NS];
+RD_UNROLL
+        for (int i = 0; i < n; i++) fm[i] = cur[i];
+RD_UNROLL
+        for (int i = 0; i < NS; i++) fS[i] = cur[n + i];
+RD_UNROLL
+        for (int j = 0; j < CK - 1; j++) {
+          if (j < nfwd) {
+            Fam::template step<IG_PROBDE>(P, t0 + j, th, nullptr, fm, fS);
+RD_UNROLL
+            for (int i = 0; i < n; i++) scratch[j * NE + i] = fm[i];
+RD_UNROLL
+            for (int i = 0; i < NS; i++) scratch[j * NE + n + i] = fS[i];
+          }
+        }
+      }
+RD_UNROLL
+      for (int j = CK - 2; j >= 0; j--) {
+        if (j < nfwd) {
+          const int t = t0 + j + 1;
+          int f = Fam::template bw_step<1, DO_MEAN, DO_VAR, DO_SIM>(P, scratch + j * NE,
+                                                                    DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
+          if (f && !fail) fail = f;
+          emit_time<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(a, b, t, mus, Ss, x, lp, d);
+        }
+      }
+      if (base >= 1) {
+        int f = Fam::template bw_step<1, DO_MEAN, DO_VAR, DO_SIM>(P, cur, DO_SIM ? zb + (long)(base - 1) * n : nullptr,
+                                                                  mus, Ss, x);
+        if (f && !fail) fail = f;
+        emit_time<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(a, b, base, mus, Ss, x, lp, d);
       }
     }
+    t_hi = base >= 1 ? base : 1;
+    r++;
   }
   // time index 0: the initial state is known (KalmanODE.pyx:445, 409); Sigma_0 = 0
-  if (!LOGLIK) {
-RD_UNROLL
-    for (int i = 0; i < n; i++) {
-      double v = a.x0[b * n + i];
-      if (DO_MEAN) mu_o[i] = v;
-      if (DO_SIM) x_o[i] = v;
-    }
-    if (DO_VAR) {
-RD_UNROLL
-      for (int i = 0; i < n * n; i++) var_o[i] = 0.0;
-    }
-  } else {
-    double x0v[n];
+  {
+    double x0v[n], S0[NS];
 RD_UNROLL
     for (int i = 0; i < n; i++) x0v[i] = a.x0[b * n + i];
-    while (d >= 0 && a.thin_index[d] == 0) {
-      lp += loglik_terms<n>(a, d, x0v);
-      d--;
-    }
+RD_UNROLL
+    for (int i = 0; i < NS; i++) S0[i] = 0.0;
+    emit_time<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(a, b, 0, x0v, S0, x0v, lp, d);
+  }
+  if (LOGLIK) {
     // constant of the normal density: -(log sqrt(2 pi) + log gamma) per observation
     const double cst = -0.91893853320467274178 - log(a.gamma);
     a.loglik[b] = lp + cst * (double)(a.n_obs_times * a.n_obs_comp);

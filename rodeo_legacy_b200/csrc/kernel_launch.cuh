@@ -52,33 +52,60 @@ inline typename Fam::PriorT make_prior(const HostPrior &h) {
 #include "kalman_bdw.cuh"
 namespace rodeo {
 
-template <class Fam, int IG>
+template <class Fam, bool UNROLL, int IG>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) Fam::template forward<IG>(P, a, b);
+  if (b < a.B) Bodies<UNROLL>::template forward<Fam, IG>(P, a, b);
 }
 
-template <class Fam, bool UNROLL, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+template <class Fam, bool UNROLL, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < a.B) Bodies<UNROLL>::template backward<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
+  if (b < a.B) Bodies<UNROLL>::template backward<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
 }
 
 inline dim3 grid_for(long B) { return dim3((unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock)); }
 
-template <class Fam, int IG>
+template <class Fam, bool UNROLL, int IG>
 cudaError_t launch_forward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  kalman_forward<Fam, IG><<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
+  kalman_forward<Fam, UNROLL, IG><<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
   return cudaGetLastError();
 }
 
-template <class Fam, bool UNROLL, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+template <class Fam, bool UNROLL, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 cudaError_t launch_backward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  kalman_backward<Fam, UNROLL, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>
+  kalman_backward<Fam, UNROLL, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>
       <<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
   return cudaGetLastError();
+}
+
+// backward launchers of one family for checkpoint interval CK (slot CKI of the table)
+template <class Fam, class Ode, bool BD, bool UNROLL, int CK, int CKI>
+void fill_backward(KernelSet &k) {
+  if constexpr (UNROLL && BD && Ode::n_meas >= 3) {
+    // block-diagonal with >= 3 blocks: one warp per diagonal block, CTA per tile (measured:
+    // 2.1x on MSEIR, 1.9x on Lorenz63 over thread-per-system; 8 % slower at 2 blocks).
+    // Full history only (checkpoint interval 1): see kalman_bdw.cuh.
+    if constexpr (CK == 1) {
+      k.backward[CKI][BK_MV] = launch_backward_bdw<Fam, true, true, false>;
+      k.backward[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
+      k.backward[CKI][BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
+    } else {
+      return;   // leaves this slot empty: the API falls back to interval 1 for this family
+    }
+  } else if constexpr (UNROLL) {  // registers: history and outputs staged through shared memory
+    k.backward[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
+    k.backward[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
+    k.backward[CKI][BK_BOTH] = launch_backward_staged<Fam, CK, true, true, true>;
+  } else {
+    k.backward[CKI][BK_MV] = launch_backward<Fam, UNROLL, CK, true, true, false, false>;
+    k.backward[CKI][BK_SIM] = launch_backward<Fam, UNROLL, CK, false, false, true, false>;
+    k.backward[CKI][BK_BOTH] = launch_backward<Fam, UNROLL, CK, true, true, true, false>;
+  }
+  k.backward[CKI][BK_LL_MEAN] = launch_backward<Fam, UNROLL, CK, true, false, false, true>;
+  k.backward[CKI][BK_LL_DRAW] = launch_backward<Fam, UNROLL, CK, false, false, true, true>;
 }
 
 // K = n_state for the dense family, block size p for the block-diagonal family.
@@ -92,26 +119,16 @@ KernelSet make_kernel_set(const char *name) {
   k.blockdiag = BD;
   k.registers = UNROLL;
   k.name = name;
-  k.forward[IG_PROBDE] = launch_forward<Fam, IG_PROBDE>;
-  k.forward[IG_SCHOBERT] = launch_forward<Fam, IG_SCHOBERT>;
-  k.forward[IG_CHKREBTII] = launch_forward<Fam, IG_CHKREBTII>;
-  if constexpr (UNROLL && BD && Ode::n_meas >= 3) {
-    // block-diagonal with >= 3 blocks: one warp per diagonal block, CTA per tile (measured:
-    // 2.1x on MSEIR, 1.9x on Lorenz63 over thread-per-system; 8 % slower at 2 blocks)
-    k.backward[BK_MV] = launch_backward_bdw<Fam, true, true, false>;
-    k.backward[BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
-    k.backward[BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
-  } else if constexpr (UNROLL) {  // dense registers: history and outputs staged through shared memory
-    k.backward[BK_MV] = launch_backward_staged<Fam, true, true, false>;
-    k.backward[BK_SIM] = launch_backward_staged<Fam, false, false, true>;
-    k.backward[BK_BOTH] = launch_backward_staged<Fam, true, true, true>;
-  } else {
-    k.backward[BK_MV] = launch_backward<Fam, UNROLL, true, true, false, false>;
-    k.backward[BK_SIM] = launch_backward<Fam, UNROLL, false, false, true, false>;
-    k.backward[BK_BOTH] = launch_backward<Fam, UNROLL, true, true, true, false>;
+  k.forward[IG_PROBDE] = launch_forward<Fam, UNROLL, IG_PROBDE>;
+  k.forward[IG_SCHOBERT] = launch_forward<Fam, UNROLL, IG_SCHOBERT>;
+  k.forward[IG_CHKREBTII] = launch_forward<Fam, UNROLL, IG_CHKREBTII>;
+  for (int c = 0; c < kNumCk; c++)
+    for (int b = 0; b < BK_COUNT; b++) k.backward[c][b] = nullptr;
+  fill_backward<Fam, Ode, BD, UNROLL, 1, 0>(k);
+  if constexpr (UNROLL) {  // checkpointed history for the register families only
+    fill_backward<Fam, Ode, BD, UNROLL, 2, 1>(k);
+    fill_backward<Fam, Ode, BD, UNROLL, 4, 2>(k);
   }
-  k.backward[BK_LL_MEAN] = launch_backward<Fam, UNROLL, true, false, false, true>;
-  k.backward[BK_LL_DRAW] = launch_backward<Fam, UNROLL, false, false, true, true>;
   k.hist_elems = Fam::NE;
   return k;
 }

@@ -15,6 +15,9 @@ struct HostPrior {
 
 enum BackwardKind { BK_MV = 0, BK_SIM = 1, BK_BOTH = 2, BK_LL_MEAN = 3, BK_LL_DRAW = 4, BK_COUNT = 5 };
 
+constexpr int kNumCk = 3;                       // checkpoint intervals 1, 2, 4
+inline int ck_slot(int ck) { return ck == 1 ? 0 : ck == 2 ? 1 : ck == 4 ? 2 : -1; }
+
 typedef cudaError_t (*launch_fn)(const HostPrior &, const SolveArgs &, cudaStream_t);
 
 struct KernelSet {
@@ -23,7 +26,7 @@ struct KernelSet {
   bool registers;                 // fully unrolled register kernels (else rolled / local memory)
   const char *name;
   launch_fn forward[3];           // by interrogation variant
-  launch_fn backward[BK_COUNT];   // by BackwardKind
+  launch_fn backward[kNumCk][BK_COUNT];  // by checkpoint slot and BackwardKind (nullptr: not compiled)
   int hist_elems;                 // doubles of history per system per step
 };
 

@@ -75,7 +75,7 @@ def _ptr(t):
 
 class KalmanODE:
     def __init__(self, W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state,
-                 z_state=None, interrogate="probde", device=None, force_dense=False):
+                 z_state=None, interrogate="probde", device=None, force_dense=False, checkpoint=0):
         self._lib = _lib.load()                      # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
@@ -112,6 +112,8 @@ class KalmanODE:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.rodeo_cuda_problem_create(ctypes.byref(desc), ctypes.byref(h)))
         self._h = h
+        if checkpoint != 0:
+            self.checkpoint = checkpoint
         self._z_dev = None          # cached device copy of the shared z
         self._ll_cache = {}
 
@@ -203,6 +205,18 @@ class KalmanODE:
         bd, rg, _ = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _lib.check(self._lib.rodeo_cuda_problem_info(self._h, ctypes.byref(bd), ctypes.byref(rg), ctypes.byref(_)))
         return ("blockdiag" if bd.value else "dense", "registers" if rg.value else "rolled")
+
+    @property
+    def checkpoint(self):
+        """Checkpoint interval of the filter history in effect (set 0 = auto, 1, 2 or 4; reads
+        back the interval actually used): with k > 1 only every
+        k-th filtered record goes to HBM and the smoother re-runs the filter in between
+        (bit-identical results, k-fold less history traffic)."""
+        return int(self._lib.rodeo_cuda_get_checkpoint(self._h))
+
+    @checkpoint.setter
+    def checkpoint(self, interval):
+        _lib.check(self._lib.rodeo_cuda_set_checkpoint(self._h, int(interval)))
 
     @property
     def history_bytes_per_system(self):

@@ -49,33 +49,43 @@ static void fill_prior(PriorBD<p, nb> &P, const HostPrior &h) {
   P.n_eval = h.n_eval;
 }
 
-template <class Fam, bool UNROLL>
-static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
-  typename Fam::PriorT P;
-  fill_prior(P, h);
-  std::vector<double> hist((size_t)h.n_eval * Fam::NE * ((a.B + 31) / 32 * 32));
-  a.hist = hist.data();
-  for (long b = 0; b < a.B; b++) {
-    if (ig == 0) Fam::template forward<IG_PROBDE>(P, a, b);
-    else if (ig == 1) Fam::template forward<IG_SCHOBERT>(P, a, b);
-    else Fam::template forward<IG_CHKREBTII>(P, a, b);
-  }
+template <class Fam, bool UNROLL, int CK>
+static int run_ck(const typename Fam::PriorT &P, int kind, const SolveArgs &a) {
   for (long b = 0; b < a.B; b++) {
     switch (kind) {
-      case 0: Bodies<UNROLL>::template backward<Fam, true, true, false, false>(P, a, b); break;
-      case 1: Bodies<UNROLL>::template backward<Fam, false, false, true, false>(P, a, b); break;
-      case 2: Bodies<UNROLL>::template backward<Fam, true, true, true, false>(P, a, b); break;
-      case 3: Bodies<UNROLL>::template backward<Fam, true, false, false, true>(P, a, b); break;
-      case 4: Bodies<UNROLL>::template backward<Fam, false, false, true, true>(P, a, b); break;
+      case 0: Bodies<UNROLL>::template backward<Fam, CK, true, true, false, false>(P, a, b); break;
+      case 1: Bodies<UNROLL>::template backward<Fam, CK, false, false, true, false>(P, a, b); break;
+      case 2: Bodies<UNROLL>::template backward<Fam, CK, true, true, true, false>(P, a, b); break;
+      case 3: Bodies<UNROLL>::template backward<Fam, CK, true, false, false, true>(P, a, b); break;
+      case 4: Bodies<UNROLL>::template backward<Fam, CK, false, false, true, true>(P, a, b); break;
       default: return -1;
     }
   }
   return 0;
 }
 
+template <class Fam, bool UNROLL>
+static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
+  typename Fam::PriorT P;
+  fill_prior(P, h);
+  std::vector<double> hist((size_t)n_records(h.n_eval, a.ck) * Fam::NE * ((a.B + 31) / 32 * 32));
+  a.hist = hist.data();
+  for (long b = 0; b < a.B; b++) {
+    if (ig == 0) Bodies<UNROLL>::template forward<Fam, IG_PROBDE>(P, a, b);
+    else if (ig == 1) Bodies<UNROLL>::template forward<Fam, IG_SCHOBERT>(P, a, b);
+    else Bodies<UNROLL>::template forward<Fam, IG_CHKREBTII>(P, a, b);
+  }
+  if (a.ck == 1) return run_ck<Fam, UNROLL, 1>(P, kind, a);
+  if (ig != 0) return -3;
+  if (a.ck == 2) return run_ck<Fam, UNROLL, 2>(P, kind, a);
+  if (a.ck == 3) return run_ck<Fam, UNROLL, 3>(P, kind, a);
+  if (a.ck == 4) return run_ck<Fam, UNROLL, 4>(P, kind, a);
+  return -4;
+}
+
 extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, double tmax, const double *W,
                              const double *Q, const double *c, const double *R, int ig, int kind,
-                             int unroll, int blockdiag, long B, const double *x0, const double *theta, const double *z,
+                             int unroll, int blockdiag, int ck, long B, const double *x0, const double *theta, const double *z,
                              long z_stride, double *x_out, double *mu_out, double *var_out, int *status,
                              const int *thin_index, int n_obs_times, const int *state_index,
                              int n_obs_comp, const double *Y, double gamma, double *loglik) {
@@ -83,6 +93,8 @@ extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, dou
   SolveArgs a;
   memset(&a, 0, sizeof a);
   a.B = B;
+  a.ck = ck;
+  a.n_steps = n_eval + 1;
   a.x0 = x0;
   a.theta = theta;
   a.z = z;

@@ -338,3 +338,46 @@ def test_interrogation_variants_on_gpu(name, force_dense):
         assert traj_err(mu, ref["mu"]).max() < 1e-9
         assert traj_err(x, ref["x"]).max() < 1e-8
         assert var_err(var[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+
+
+@pytest.mark.parametrize("ck", [2, 4])
+@pytest.mark.parametrize("maker,B,N", [
+    (wl.fitz_batch, 1000, 400), (wl.fitz_batch, 70, 7), (wl.fitz_batch, 40, 2), (wl.fitz_batch, 33, 1),
+    (lambda B: wl.lorenz_batch(B, N=301, tmax=1.2), 100, 301),
+    (lambda B: wl.mseir_batch(B, N=150), 64, 150)])
+def test_checkpointed_history_is_bit_identical(maker, B, N, ck):
+    """checkpoint = k stores every k-th filtered record and re-runs the filter inside the
+    smoother: outputs must equal the checkpoint = 1 outputs bit for bit (solve, loglik), for
+    n_eval that is / is not a multiple of k, on both register families."""
+    w, x0, theta = maker(B)
+    if w["N"] != N:                      # shorten the FitzHugh-Nagumo grid
+        w = dict(w, N=N, tmax=w["tmax"] * N / w["N"])
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(4).standard_normal((n, N)))
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    for force_dense in ([False, True] if n <= 6 else [False]):
+        k1 = wl.make_kode(w, z_state=z, force_dense=force_dense, checkpoint=1)
+        kk = wl.make_kode(w, z_state=z, force_dense=force_dense, checkpoint=ck)
+        assert k1.checkpoint == 1
+        if n > 6:       # warp-per-block kernels keep the full history (kalman_bdw.cuh)
+            assert kk.checkpoint == 1
+            continue
+        assert kk.checkpoint == ck
+        assert wl.make_kode(w, force_dense=force_dense).checkpoint == (1 if force_dense else 2)   # auto
+        assert kk.history_bytes_per_system < k1.history_bytes_per_system or N <= 2
+        for a, b in zip(k1.solve(x0d, theta=thd), kk.solve(x0d, theta=thd)):
+            assert bool((a == b).all())
+        mu1, var1 = k1.solve_mv(x0d, theta=thd)
+        muk, vark = kk.solve_mv(x0d, theta=thd)
+        assert bool((mu1 == muk).all()) and bool((var1 == vark).all())
+        assert bool((k1.solve_sim(x0d, theta=thd) == kk.solve_sim(x0d, theta=thd)).all())
+        if n == 6:
+            ind = np.unique(np.clip(np.arange(0, N + 1, max(1, N // 7)), 0, N))
+            Y = np.random.default_rng(1).standard_normal((len(ind), 2))
+            for draw in (False, True):
+                l1 = k1.loglik(x0d, thd, Y, ind, [0, 3], 0.3, use_draw=draw)
+                lk = kk.loglik(x0d, thd, Y, ind, [0, 3], 0.3, use_draw=draw)
+                assert bool((l1 == lk).all())
+    # other interrogation methods silently keep the full history
+    ks = wl.make_kode(w, z_state=z, interrogate="schobert", checkpoint=ck)
+    assert ks.checkpoint == 1

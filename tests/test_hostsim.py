@@ -82,3 +82,29 @@ def test_interrogation_variants(ig, name, blockdiag):
         assert var_err(r["var"][:, 1:], ref["var"][:, 1:]).max() < 1e-8
     if ig == 2:
         assert traj_err(r["x"], ref["x"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("ck", [2, 3, 4])
+@pytest.mark.parametrize("blockdiag", [False, True], ids=["dense", "blockdiag"])
+@pytest.mark.parametrize("name,N", [("fitz_n400", None), ("chkrebtii_n200", None), ("fitz_n400", 7), ("fitz_n400", 1),
+                                    ("fitz_n400", 2)])
+def test_checkpointed_history_gives_identical_results(name, N, blockdiag, ck):
+    """Storing every ck-th filtered record and re-running the filter in the backward pass must
+    give bit-identical outputs to storing everything (same code, same inputs), for n_eval that
+    is and is not a multiple of ck, including the degenerate n_eval = 1, 2."""
+    g, ode, p, x0, theta = _setup(name, B=2)
+    N = int(g["N"]) if N is None else N
+    tmax = p.tmax * N / int(g["N"])
+    z = g["z"][:, :N]
+    args = (ode, g["W"], p.tmin, tmax, N, g["Q"], g["c"], g["R"], x0, theta, z)
+    full = hostsim.solve(*args, kind="both", blockdiag=blockdiag)
+    chk = hostsim.solve(*args, kind="both", blockdiag=blockdiag, ck=ck)
+    for key in ("mu", "var", "x"):
+        np.testing.assert_array_equal(chk[key], full[key])
+    if name.startswith("fitz"):
+        ind = np.unique(np.clip(np.arange(0, N + 1, max(1, N // 5)), 0, N))
+        Y = np.zeros((len(ind), 2))
+        a = hostsim.solve(*args, kind="ll_draw", blockdiag=blockdiag, thin_index=ind, state_index=[0, 3], Y=Y, gamma=0.3)
+        b = hostsim.solve(*args, kind="ll_draw", blockdiag=blockdiag, ck=ck, thin_index=ind, state_index=[0, 3], Y=Y,
+                          gamma=0.3)
+        np.testing.assert_array_equal(a["loglik"], b["loglik"])
