@@ -270,7 +270,9 @@ def main():
     if not args.no_e2e:
         del mu, var
         torch.cuda.empty_cache()
-        Be = B
+        # several ranks share one host: keep the pinned footprint of the e2e leg modest there
+        # (throughput is PCIe-bound per GPU and does not depend on the batch size)
+        Be = B if world == 1 else min(B, 16384)
         out_bytes = Be * (N_EVAL + 1) * (N_STATE + N_STATE * N_STATE) * 8
         while Be > 4096 and not host_memory_ok(out_bytes * max(1, min(world, 8))):
             Be //= 2
