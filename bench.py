@@ -330,6 +330,59 @@ def main():
         del kd
         torch.cuda.empty_cache()
 
+    # ---- shared-covariance mode on the same workload: a DIFFERENT amount of work per system
+    # (covariances once per prior, mean recursions per system; var returned as one shared array),
+    # reported on its own line with its own byte count -- never against the general-mode roofline
+    shared = None
+    if world == 1 and not args.dense:
+        try:
+            del mu, var
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        ks = wl.make_kode(w, shared_cov=True)
+        for _ in range(3):
+            ks.solve_mv(x0d, theta=thd)
+        torch.cuda.synchronize()
+        ks.set_timing(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ns = args.steps
+        s0.record()
+        for _ in range(ns):
+            ks.solve_mv(x0d, theta=thd)
+        s1.record()
+        torch.cuda.synchronize()
+        sms = s0.elapsed_time(s1) / ns
+        sf, sb = ks.last_kernel_ms()
+        sc_bytes = N_EVAL * 8 * 3 * N_STATE * B          # mu_filt written + read, mu_smooth written
+        shared = {"mode": "shared covariance (SURVEY F5): tables cached per prior, mean recursions per system, "
+                          "var = one (N+1,n,n) array for the batch",
+                  "value": B / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms, "forward_kernel_ms": sf,
+                  "backward_kernel_ms": sb, "steps": ns,
+                  "algorithmic_bytes_per_step": sc_bytes, "achieved_GBps": sc_bytes / (sms * 1e-3) / 1e9,
+                  "frac_of_hbm_peak": sc_bytes / (sms * 1e-3) / 1e9 / peaks()[0]}
+        if not args.no_e2e:
+            Bs = B
+            pin = lambda *s_: torch.empty(s_, dtype=torch.float64, pin_memory=True)
+            x0p, thp = pin(Bs, N_STATE), pin(Bs, 3)
+            x0p.copy_(torch.from_numpy(x0))
+            thp.copy_(torch.from_numpy(theta))
+            mup, varp = pin(Bs, N_EVAL + 1, N_STATE), pin(N_EVAL + 1, N_STATE, N_STATE)
+            ks.solve_mv_into(x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                ks.solve_mv_into(x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy())
+            el = time.perf_counter() - t0
+            shared["e2e"] = {"value": Bs * args.e2e_steps / el, "unit": UNIT,
+                             "h2d_bytes_per_step": Bs * (N_STATE + 3) * 8,
+                             "d2h_bytes_per_step": Bs * (N_EVAL + 1) * N_STATE * 8
+                                                   + (N_EVAL + 1) * N_STATE * N_STATE * 8 + Bs * 4,
+                             "ms_per_step": 1e3 * el / args.e2e_steps}
+            del mup, varp
+        del ks
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -359,7 +412,7 @@ def main():
                          "kernel_ms": bwd_ms, "forward_kernel_ms": fwd_ms,
                          "forward_achieved": fwd_gbs,
                          "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak},
-            "kernel_family": family, "dense_path": dense,
+            "kernel_family": family, "dense_path": dense, "shared_covariance_path": shared,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "status_nonzero": status_bad,
         }

@@ -145,6 +145,18 @@ int rodeo_cuda_set_workspace_limit(rodeo_problem *p, size_t bytes);
  * rodeo_cuda_get_checkpoint returns the interval actually in effect. */
 int rodeo_cuda_set_checkpoint(rodeo_problem *p, int interval);
 int rodeo_cuda_get_checkpoint(const rodeo_problem *p);
+/* Shared-covariance mode.  One handle has one prior (Q, c, R, W), so the covariance path
+ * (Sigma_pred / filt / smooth, Kalman and smoother gains, sampling Cholesky factors) is the same
+ * for every system of a batch: it does not depend on theta, x0 or the ODE (rodeo/eigen/KalmanTV.h
+ * never reads a mean when producing a variance).  With this mode on, those are computed ONCE per
+ * prior into device tables and the batch kernels run the mean recursions only; `var_out` of
+ * rodeo_cuda_solve / rodeo_cuda_solve_host then receives ONE (n_eval+1, n_state, n_state) array
+ * that holds for all systems, instead of one per system.  Means, draws and log-likelihoods agree
+ * with the general mode to FP64 rounding.  Off by default: it is a different amount of work per
+ * system than the general mode and is benchmarked separately.  RODEO_E_UNSUPPORTED for kernel
+ * families without it (rolled dense n > 6) and for the chkrebtii interrogation. */
+int rodeo_cuda_set_shared_cov(rodeo_problem *p, int enabled);
+int rodeo_cuda_get_shared_cov(const rodeo_problem *p);
 /* Pre-allocate the workspace for batches up to max_batch (otherwise grown on demand). */
 int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch);
 

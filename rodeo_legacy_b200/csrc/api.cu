@@ -38,6 +38,13 @@ struct rodeo_problem {
   const KernelSet *ks;
   int flags = 0;
   int ck = 0;                      // requested checkpoint interval of the filter history (0 = auto)
+  // shared-covariance mode (kalman_sc.inl): tables cached per (prior, N), rebuilt after problem_set
+  bool shared = false;
+  double *tab = nullptr;
+  size_t tab_bytes = 0;
+  bool tab_valid = false;
+  int tab_fail = 0;
+  int *tab_fail_dev = nullptr;
   void *ws = nullptr;
   size_t ws_bytes = 0;
   size_t ws_limit = (size_t)48 << 30;
@@ -146,6 +153,8 @@ int rodeo_cuda_problem_destroy(rodeo_problem *p) {
   if (!p) return RODEO_OK;
   cudaSetDevice(p->device);
   if (p->ws) cudaFree(p->ws);
+  if (p->tab) cudaFree(p->tab);
+  if (p->tab_fail_dev) cudaFree(p->tab_fail_dev);
   for (int i = 0; i < 8; i++)
     if (p->hbuf[i]) cudaFree(p->hbuf[i]);
   for (auto e : p->ev) cudaEventDestroy(e);
@@ -168,7 +177,10 @@ int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *v) {
     case RODEO_FIELD_VAR_STATE: p->R.assign(v, v + (size_t)p->n * p->n); break;
     default: return fail(RODEO_E_INVALID, "unknown field");
   }
-  return select_kernel_set(p);   // the structure (hence the kernel family) may have changed
+  p->tab_valid = false;          // the covariance tables depend on Q, R, W
+  int rc = select_kernel_set(p); // the structure (hence the kernel family) may have changed
+  if (rc == RODEO_OK && p->shared && !p->ks->sc_forward) p->shared = false;
+  return rc;
 }
 
 int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t *registers,
@@ -192,8 +204,21 @@ static int effective_ck(const rodeo_problem *p) {
 }
 
 size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
-  return p ? (size_t)n_records(p->N, effective_ck(p)) * p->ks->hist_elems * sizeof(double) : 0;
+  if (!p) return 0;
+  if (p->shared) return (size_t)p->N * p->n * sizeof(double);   // filtered means only
+  return (size_t)n_records(p->N, effective_ck(p)) * p->ks->hist_elems * sizeof(double);
 }
+
+int rodeo_cuda_set_shared_cov(rodeo_problem *p, int enabled) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (enabled && (!p->ks->sc_forward || p->ig == RODEO_INTERROGATE_CHKREBTII))
+    return fail(RODEO_E_UNSUPPORTED,
+                "shared-covariance mode needs a register kernel family and the probde or schobert interrogation");
+  p->shared = enabled != 0;
+  return RODEO_OK;
+}
+
+int rodeo_cuda_get_shared_cov(const rodeo_problem *p) { return p ? (p->shared ? 1 : 0) : RODEO_E_INVALID; }
 
 int rodeo_cuda_set_checkpoint(rodeo_problem *p, int interval) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
@@ -266,6 +291,31 @@ struct LoglikSpec {
   double *out = nullptr;
 };
 
+// Shared-covariance mode: (re)build the gain / Cholesky / variance tables for the current prior.
+static int ensure_tables(rodeo_problem *p, const HostPrior &hp, cudaStream_t stream) {
+  if (p->tab_valid) return RODEO_OK;
+  const size_t need = (size_t)p->ks->sc_table_doubles(p->N) * sizeof(double);
+  if (need > p->tab_bytes) {
+    if (p->tab) cudaFree(p->tab);
+    p->tab = nullptr;
+    p->tab_bytes = 0;
+    if (cudaMalloc((void **)&p->tab, need) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(RODEO_E_NOMEM, "shared-covariance tables could not be allocated");
+    }
+    p->tab_bytes = need;
+  }
+  if (!p->tab_fail_dev) CK(cudaMalloc((void **)&p->tab_fail_dev, sizeof(int)));
+  CK(cudaMemsetAsync(p->tab, 0, need, stream));
+  CK(cudaMemsetAsync(p->tab_fail_dev, 0, sizeof(int), stream));
+  CK(p->ks->sc_tables(hp, p->ig == RODEO_INTERROGATE_SCHOBERT, p->tab, p->tab_fail_dev, stream));
+  CK(cudaMemcpyAsync(&p->tab_fail, p->tab_fail_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));   // one-off per prior: the failure flag travels in SolveArgs
+  p->launches += 1;
+  p->tab_valid = true;
+  return RODEO_OK;
+}
+
 // One pass over `batch` systems in chunks: forward kernel then backward kernel per chunk.
 static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const double *x0,
                       const double *theta, const double *z, long z_stride, double *x_out,
@@ -278,6 +328,12 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   int rc = ensure_workspace(p, cap);
   if (rc) return rc;
   HostPrior hp{p->n, p->m, p->N, p->tmin, p->tmax, p->W.data(), p->Q.data(), p->c.data(), p->R.data()};
+  if (p->shared) {
+    if ((rc = ensure_tables(p, hp, stream))) return rc;
+    if (var_out)   // ONE (N+1, n, n) array serves the whole batch in this mode
+      CK(cudaMemcpyAsync(var_out, p->tab + p->ks->sc_table_var_offset(p->N), (size_t)T1 * n * n * sizeof(double),
+                         cudaMemcpyDeviceToDevice, stream));
+  }
   const long n_chunks = (batch + cap - 1) / cap;
   if (p->timing) {
     while ((long)p->ev.size() < 3 * n_chunks) {
@@ -301,7 +357,9 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     a.n_steps = p->N + 1;
     a.x_out = x_out ? x_out + off * T1 * n : nullptr;
     a.mu_out = mu_out ? mu_out + off * T1 * n : nullptr;
-    a.var_out = var_out ? var_out + off * T1 * n * n : nullptr;
+    a.var_out = (var_out && !p->shared) ? var_out + off * T1 * n * n : nullptr;
+    a.tab = p->shared ? p->tab : nullptr;
+    a.tab_fail = p->shared ? p->tab_fail : 0;
     a.status = status ? status + off : nullptr;
     if (ll) {
       a.thin_index = ll->thin_index;
@@ -313,9 +371,9 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
       a.loglik = ll->out + off;
     }
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 0], stream));
-    CK(p->ks->forward[p->ig](hp, a, stream));
+    CK(p->shared ? p->ks->sc_forward(hp, a, stream) : p->ks->forward[p->ig](hp, a, stream));
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
-    CK(p->ks->backward[slot][bk](hp, a, stream));
+    CK(p->shared ? p->ks->sc_backward[bk](hp, a, stream) : p->ks->backward[slot][bk](hp, a, stream));
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
     p->launches += 2;
   }
@@ -405,7 +463,8 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
     }
   }
   const bool mv = mode & RODEO_MODE_MV, sim = mode & RODEO_MODE_SIM;
-  const size_t out_per = (size_t)T1 * n * sizeof(double) * ((mv ? 1 + n : 0) + (sim ? 1 : 0));
+  const bool pervar = mv && !p->shared;   // per-system variance output (general mode)
+  const size_t out_per = (size_t)T1 * n * sizeof(double) * ((mv ? 1 : 0) + (pervar ? n : 0) + (sim ? 1 : 0));
   // output staging: two buffers of at most 2 GiB each, and never more systems than a history chunk
   long hc = (long)std::max<size_t>(1, ((size_t)2 << 30) / out_per);
   hc = std::min(hc, chunk_capacity(p, (long)batch));
@@ -420,6 +479,7 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
   if ((rc = ensure_buf(p, 3, (size_t)hc * sizeof(int)))) return rc;
   if ((rc = ensure_buf(p, 4, (size_t)hc * out_per))) return rc;
   if ((rc = ensure_buf(p, 5, (size_t)hc * out_per))) return rc;
+  if (mv && p->shared && (rc = ensure_buf(p, 6, (size_t)T1 * n * n * sizeof(double)))) return rc;
   if (need_z && !z_batch_stride)
     CK(cudaMemcpyAsync(p->hbuf[2], z, z_elems * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
   BackwardKind bk = mode == RODEO_MODE_MV ? BK_MV : mode == RODEO_MODE_SIM ? BK_SIM : BK_BOTH;
@@ -429,8 +489,9 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
     const int slot = (int)(ci & 1);
     double *ob = (double *)p->hbuf[4 + slot];
     double *d_mu = mv ? ob : nullptr;
-    double *d_var = mv ? ob + (size_t)B * T1 * n : nullptr;
-    double *d_x = sim ? ob + (mv ? (size_t)B * T1 * n * (1 + n) : 0) : nullptr;
+    double *d_var = pervar ? ob + (size_t)B * T1 * n : nullptr;
+    double *d_x = sim ? ob + (mv ? (size_t)B * T1 * n * (pervar ? 1 + n : 1) : 0) : nullptr;
+    if (mv && p->shared && ci == 0) d_var = (double *)p->hbuf[6];   // the single shared variance array
     // inputs of this chunk (the previous chunk's kernels are ordered before us on s_compute)
     CK(cudaMemcpyAsync(p->hbuf[0], x0 + off * n, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
     if (nth) CK(cudaMemcpyAsync(p->hbuf[1], theta + off * nth, (size_t)B * nth * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
@@ -446,7 +507,10 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
     CK(cudaStreamWaitEvent(p->s_copy, p->e_done[slot], 0));
     if (mv) {
       CK(cudaMemcpyAsync(mu_out + off * T1 * n, d_mu, (size_t)B * T1 * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
-      CK(cudaMemcpyAsync(var_out + off * T1 * n * n, d_var, (size_t)B * T1 * n * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
+      if (pervar)
+        CK(cudaMemcpyAsync(var_out + off * T1 * n * n, d_var, (size_t)B * T1 * n * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
+      else if (ci == 0)
+        CK(cudaMemcpyAsync(var_out, d_var, (size_t)T1 * n * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
     }
     if (sim) CK(cudaMemcpyAsync(x_out + off * T1 * n, d_x, (size_t)B * T1 * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
     CK(cudaEventRecord(p->e_copied[slot], p->s_copy));

@@ -103,7 +103,8 @@ RD_UNROLL
 //   mu_f = mu_p + K~^T (y - W mu_p); Sf = Sp - K~^T A.
 // (KalmanTVODE.h:336-339, KalmanTV.h:332-354).  S (Sp) and mu (mup) are updated in place.
 template <int n, int m>
-RD_HD int update_dense(const double *W, double *mu, double *S, const double *y, bool zero_H) {
+RD_HD int update_dense(const double *W, double *mu, double *S, const double *y, bool zero_H,
+                       double *dumpK = nullptr) {
   double A[m * n];
 RD_UNROLL
   for (int a = 0; a < m; a++)
@@ -140,6 +141,10 @@ RD_UNROLL
 RD_UNROLL
     for (int a = 0; a < m; a++) kj[a] = A[a * n + j];
     chol_solve_vec<m>(Sm, invd, kj, 1);
+    if (dumpK) {                       // shared-covariance tables: K~ (m x n, row-major)
+RD_UNROLL
+      for (int a = 0; a < m; a++) dumpK[a * n + j] = kj[a];
+    }
     double s = mu[j];
 RD_UNROLL
     for (int a = 0; a < m; a++) s += kj[a] * e[a];
@@ -160,7 +165,8 @@ RD_UNROLL
 //   A = w^T Sp; s = A w (+ A w under probde); K = A / s; mu_f = mu_p + K (y_a - w^T mu_p);
 //   Sf = Sp - A^T K.   The m x m Cholesky of the dense update degenerates to one division.
 template <int p>
-RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool zero_H) {
+RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool zero_H,
+                       double *dumpK = nullptr) {
   double A[p];
   double s = 0.0, e = ya;
 RD_UNROLL
@@ -181,6 +187,7 @@ RD_UNROLL
 RD_UNROLL
   for (int j = 0; j < p; j++) {
     const double kj = A[j] * inv;
+    if (dumpK) dumpK[j] = kj;
     mu[j] += kj * e;
 RD_UNROLL
     for (int i = 0; i <= j; i++) S[sidx<p>(i, j)] -= A[i] * kj;
@@ -210,7 +217,7 @@ RD_UNROLL
 // Terminal time index N (KalmanODE.pyx:445-449, 410-414); zt = z[:, N-1] (this block's rows).
 template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 RD_HD int smooth_terminal(const double *rec_mu, const double *rec_S, const double *zt_ptr, double *mus,
-                          double *Ss, double *x) {
+                          double *Ss, double *x, double *dumpL = nullptr) {
   constexpr int NS = Sym<n>::size;
   double muf[n], Sf[NS];
   int fail = 0;
@@ -230,7 +237,11 @@ RD_UNROLL
     double zt[n];
 RD_UNROLL
     for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
-    fail = state_sim<n>(x, muf, Sf, zt);  // destroys Sf (not needed again)
+    fail = state_sim<n>(x, muf, Sf, zt);  // destroys Sf (not needed again): now chol_lower
+    if (dumpL) {
+RD_UNROLL
+      for (int i = 0; i < NS; i++) dumpL[i] = Sf[i];
+    }
   }
   return fail;
 }
@@ -240,7 +251,8 @@ RD_UNROLL
 // of being held in registers across the Cholesky / triangular solves.
 template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 RD_HD int smooth_step(const double *Q, const double *c, const double *R, const double *rec_mu,
-                      const double *rec_S, const double *zt_ptr, double *mus, double *Ss, double *x) {
+                      const double *rec_S, const double *zt_ptr, double *mus, double *Ss, double *x,
+                      double *dumpT = nullptr, double *dumpL = nullptr) {
   constexpr int NS = Sym<n>::size;
   const volatile double *rec_S2 = rec_S;  // second reads: do not keep Sigma_f live
   double muf[n], mup[n], Sp[NS], T[n * n], invd[n];
@@ -261,6 +273,10 @@ RD_UNROLL
   int fail = chol_packed<n>(Sp, invd);       // LLT(Sigma_p)  (:457)
 RD_UNROLL
   for (int j = 0; j < n; j++) chol_solve_vec<n>(Sp, invd, T + j, n);  // T~ (:458)
+  if (dumpT) {                               // shared-covariance tables: the smoother gain
+RD_UNROLL
+    for (int i = 0; i < n * n; i++) dumpT[i] = T[i];
+  }
   if (DO_MEAN) {                             // (:459, 463-464)
     double dmu[n];
 RD_UNROLL
@@ -309,6 +325,10 @@ RD_UNROLL
     for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
     int f2 = state_sim<n>(x, mt, V, zt);
     if (f2 && !fail) fail = f2;
+    if (dumpL) {                             // V now holds chol_lower(V~)
+RD_UNROLL
+      for (int i = 0; i < NS; i++) dumpL[i] = V[i];
+    }
   }
   if (DO_VAR) {                              // Sigma_s = Sigma_f + T~^T D T~  (:461-465)
     double Sn[NS];

@@ -1,0 +1,133 @@
+// kalman_sc.cuh -- CUDA kernels of the shared-covariance mode (bodies: kalman_sc.inl).
+//   kalman_sc_tables     one thread per diagonal block (or one thread, dense): covariance
+//                        recursion -> gain / Cholesky tables + the (N+1, n, n) variance output
+//   kalman_sc_forward    thread per system, mean-only filter, streams mu_filt (n doubles / step)
+//   kalman_sc_backward   warp per 32-system tile, mean-only smoother / sampler; next record
+//                        prefetched into registers, outputs through a shared-memory staging tile
+//   kalman_sc_loglik     mean-only smoother accumulating the thinned log-likelihood
+#pragma once
+#include "kalman_staged.cuh"
+
+namespace rodeo {
+
+constexpr int kThreadsPerBlockSc = 128;
+
+template <class Fam>
+__global__ void kalman_sc_tables(const __grid_constant__ typename Fam::PriorT P, int zero_H, double *tab,
+                                 int *fail_out) {
+  const int u = threadIdx.x;
+  if (u < Fam::kBlocks) {
+    const int f = reg::sc_tables_unit<Fam>(P, zero_H != 0, tab, u);
+    if (f) atomicCAS(fail_out, 0, u * Fam::kBlockSize + f);
+  }
+}
+
+template <class Fam>
+__global__ void __launch_bounds__(kThreadsPerBlockSc)
+kalman_sc_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < a.B) reg::sc_forward_body<Fam>(P, a, b);
+}
+
+template <class Fam, bool DO_MEAN, bool DO_SIM>
+__global__ void __launch_bounds__(kThreadsPerBlockSc)
+kalman_sc_loglik(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < a.B) reg::sc_backward_body<Fam, DO_MEAN, DO_SIM, true>(P, a, b);
+}
+
+constexpr int kScWarps = 4;
+
+template <class Fam, bool DO_MEAN, bool DO_SIM>
+__global__ void __launch_bounds__(kScWarps * 32)
+kalman_sc_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  constexpr int n = Fam::n;
+  constexpr int OUTW = n * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0)), ROW = (OUTW + 1) / 2 * 2;
+  __shared__ __align__(16) double smem[kScWarps * kTile * ROW];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long tile = (long)blockIdx.x * kScWarps + warp;
+  if (tile * kTile >= a.B) return;
+  double *stage = smem + warp * kTile * ROW;
+  const int N = P.n_eval;
+  const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
+  const bool valid = b < a.B;
+  const long bs = valid ? b : b0;
+  const double *zb = DO_SIM ? a.z + bs * a.z_stride : nullptr;
+  const double *hist = a.hist + hist_offset(bs - (bs % kTile) + lane, 0, N, n);  // this lane's column, record 0
+  double mus[n], x[n], nxt[n];
+#pragma unroll
+  for (int i = 0; i < n; i++) nxt[i] = hist[i * kTile];
+  for (int t = N; t >= 0; t--) {
+    if (t >= 1) {
+      double cur[n];
+#pragma unroll
+      for (int i = 0; i < n; i++) cur[i] = nxt[i];
+      if (t >= 2) {  // prefetch the record of time index t-1
+        const double *h = hist + (long)(N - t + 1) * n * kTile;
+#pragma unroll
+        for (int i = 0; i < n; i++) nxt[i] = h[i * kTile];
+      }
+      const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
+      if (t == N)
+        reg::sc_backward_terminal<Fam, 1, DO_MEAN, DO_SIM>(P, a, cur, zt, mus, x);
+      else
+        reg::sc_backward_step<Fam, 1, DO_MEAN, DO_SIM>(P, a, t, cur, zt, mus, x);
+    } else {
+#pragma unroll
+      for (int i = 0; i < n; i++) {
+        const double v = valid ? a.x0[b * n + i] : 0.0;
+        mus[i] = v;
+        x[i] = v;
+      }
+    }
+    double *row = stage + lane * ROW;
+    if (DO_MEAN) {
+#pragma unroll
+      for (int i = 0; i < n; i++) row[i] = mus[i];
+    }
+    if (DO_SIM) {
+#pragma unroll
+      for (int i = 0; i < n; i++) row[(DO_MEAN ? n : 0) + i] = x[i];
+    }
+    __syncwarp();
+    if (DO_MEAN) flush_runs<n, 0, ROW>(stage, a.mu_out, b0, a.B, T1, t, lane);
+    if (DO_SIM) flush_runs<n, (DO_MEAN ? n : 0), ROW>(stage, a.x_out, b0, a.B, T1, t, lane);
+    __syncwarp();
+  }
+}
+
+
+// ---- launchers --------------------------------------------------------------------------------
+template <class Fam>
+cudaError_t launch_sc_tables(const HostPrior &h, int zero_H, double *tab, int *fail_out, cudaStream_t s) {
+  kalman_sc_tables<Fam><<<1, 32, 0, s>>>(make_prior<Fam>(h), zero_H, tab, fail_out);
+  return cudaGetLastError();
+}
+template <class Fam>
+long sc_table_doubles(int N) {
+  return reg::ScTab<Fam>::total(N);
+}
+template <class Fam>
+long sc_table_var_offset(int N) {
+  return reg::ScTab<Fam>::offVar(N);
+}
+template <class Fam>
+cudaError_t launch_sc_forward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  const unsigned grid = (unsigned)((a.B + kThreadsPerBlockSc - 1) / kThreadsPerBlockSc);
+  kalman_sc_forward<Fam><<<grid, kThreadsPerBlockSc, 0, s>>>(make_prior<Fam>(h), a);
+  return cudaGetLastError();
+}
+template <class Fam, bool DO_MEAN, bool DO_SIM, bool LOGLIK>
+cudaError_t launch_sc_backward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  if constexpr (LOGLIK) {
+    const unsigned grid = (unsigned)((a.B + kThreadsPerBlockSc - 1) / kThreadsPerBlockSc);
+    kalman_sc_loglik<Fam, DO_MEAN, DO_SIM><<<grid, kThreadsPerBlockSc, 0, s>>>(make_prior<Fam>(h), a);
+  } else {
+    const long n_tiles = (a.B + kTile - 1) / kTile;
+    const unsigned grid = (unsigned)((n_tiles + kScWarps - 1) / kScWarps);
+    kalman_sc_backward<Fam, DO_MEAN, DO_SIM><<<grid, kScWarps * 32, 0, s>>>(make_prior<Fam>(h), a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace rodeo

@@ -42,6 +42,8 @@ struct SolveArgs {
   const int *state_index; // [n_obs_comp]
   const double *Y;        // [n_obs_times][n_obs_comp]
   double *loglik;         // [B]
+  const double *tab;      // shared-covariance tables (kalman_sc.inl), or nullptr
+  int tab_fail;           // Cholesky failure code of the table pass (reported as every system's status)
   double gamma;
   int n_obs_times, n_obs_comp;
 };
@@ -55,6 +57,7 @@ namespace rodeo {
 namespace reg {
 #include "kalman_math.inl"
 #include "kalman_tps.inl"
+#include "kalman_sc.inl"
 }  // namespace reg
 }  // namespace rodeo
 #undef RD_UNROLL

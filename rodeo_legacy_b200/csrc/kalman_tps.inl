@@ -19,6 +19,7 @@ struct DenseFam {
   using Ode = Ode_;
   static constexpr int n = n_, m = Ode::n_meas, NS = Sym<n_>::size, NE = n_ + Sym<n_>::size;
   static constexpr bool kBlockDiag = false;
+  static constexpr int kBlocks = 1, kBlockSize = n_;
   using PriorT = Prior<n_, Ode_::n_meas>;
 
   // One filter step, time index t -> t+1 (KalmanODE.pyx:299-332): predict, interrogate, update.
@@ -68,6 +69,7 @@ struct BdFam {
   static constexpr int p = p_, nb = Ode::n_meas, n = p_ * Ode_::n_meas, m = Ode::n_meas;
   static constexpr int PS = Sym<p_>::size, NS = Ode_::n_meas * Sym<p_>::size, NE = n + NS;
   static constexpr bool kBlockDiag = true;
+  static constexpr int kBlocks = Ode_::n_meas, kBlockSize = p_;
   using PriorT = PriorBD<p_, Ode_::n_meas>;
 
   template <int IG>

@@ -50,6 +50,7 @@ inline typename Fam::PriorT make_prior(const HostPrior &h) {
 }  // namespace rodeo
 #include "kalman_staged.cuh"
 #include "kalman_bdw.cuh"
+#include "kalman_sc.cuh"
 namespace rodeo {
 
 template <class Fam, bool UNROLL, int IG>
@@ -130,6 +131,22 @@ KernelSet make_kernel_set(const char *name) {
     fill_backward<Fam, Ode, BD, UNROLL, 4, 2>(k);
   }
   k.hist_elems = Fam::NE;
+  k.sc_tables = nullptr;
+  k.sc_table_doubles = nullptr;
+  k.sc_table_var_offset = nullptr;
+  k.sc_forward = nullptr;
+  for (int b = 0; b < BK_COUNT; b++) k.sc_backward[b] = nullptr;
+  if constexpr (UNROLL) {  // shared-covariance mode for the register families
+    k.sc_tables = launch_sc_tables<Fam>;
+    k.sc_table_doubles = sc_table_doubles<Fam>;
+    k.sc_table_var_offset = sc_table_var_offset<Fam>;
+    k.sc_forward = launch_sc_forward<Fam>;
+    k.sc_backward[BK_MV] = launch_sc_backward<Fam, true, false, false>;
+    k.sc_backward[BK_SIM] = launch_sc_backward<Fam, false, true, false>;
+    k.sc_backward[BK_BOTH] = launch_sc_backward<Fam, true, true, false>;
+    k.sc_backward[BK_LL_MEAN] = launch_sc_backward<Fam, true, false, true>;
+    k.sc_backward[BK_LL_DRAW] = launch_sc_backward<Fam, false, true, true>;
+  }
   return k;
 }
 

@@ -28,6 +28,12 @@ struct KernelSet {
   launch_fn forward[3];           // by interrogation variant
   launch_fn backward[kNumCk][BK_COUNT];  // by checkpoint slot and BackwardKind (nullptr: not compiled)
   int hist_elems;                 // doubles of history per system per step
+  // shared-covariance mode (kalman_sc.cuh); all nullptr when not compiled for this set
+  cudaError_t (*sc_tables)(const HostPrior &, int zero_H, double *tab, int *fail_out, cudaStream_t);
+  long (*sc_table_doubles)(int N);
+  long (*sc_table_var_offset)(int N);
+  launch_fn sc_forward;
+  launch_fn sc_backward[BK_COUNT];
 };
 
 const KernelSet *find_kernel_set(int ode, int n, bool blockdiag);

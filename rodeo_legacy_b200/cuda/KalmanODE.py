@@ -75,7 +75,8 @@ def _ptr(t):
 
 class KalmanODE:
     def __init__(self, W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state,
-                 z_state=None, interrogate="probde", device=None, force_dense=False, checkpoint=0):
+                 z_state=None, interrogate="probde", device=None, force_dense=False, checkpoint=0,
+                 shared_cov=False):
         self._lib = _lib.load()                      # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
@@ -114,6 +115,8 @@ class KalmanODE:
         self._h = h
         if checkpoint != 0:
             self.checkpoint = checkpoint
+        if shared_cov:
+            self.shared_cov = True
         self._z_dev = None          # cached device copy of the shared z
         self._ll_cache = {}
 
@@ -207,6 +210,19 @@ class KalmanODE:
         return ("blockdiag" if bd.value else "dense", "registers" if rg.value else "rolled")
 
     @property
+    def shared_cov(self):
+        """Shared-covariance mode (off by default).  All systems solved by one KalmanODE object
+        share its prior, so their covariances are identical (they do not depend on theta, x0 or
+        the ODE).  With ``shared_cov = True`` they are computed once per prior and the batch
+        kernels run the mean recursions only; ``var`` is then returned as a read-only broadcast
+        view of ONE (N+1, n, n) array (same shape as in the general mode, no per-system copy)."""
+        return bool(self._lib.rodeo_cuda_get_shared_cov(self._h))
+
+    @shared_cov.setter
+    def shared_cov(self, enabled):
+        _lib.check(self._lib.rodeo_cuda_set_shared_cov(self._h, int(bool(enabled))))
+
+    @property
     def checkpoint(self):
         """Checkpoint interval of the filter history in effect (set 0 = auto, 1, 2 or 4; reads
         back the interval actually used): with k > 1 only every
@@ -297,12 +313,14 @@ class KalmanODE:
         on_dev, single, B, x0b, th, z, z_stride = self._prep(x0, W, theta, need_z)
         n, T = self.n_state, self.n_steps
         mv, sim = bool(mode & MODE_MV), bool(mode & MODE_SIM)
+        shared = self.shared_cov
+        vshape = (T, n, n) if shared else (B, T, n, n)     # shared: ONE array for the batch
         if on_dev:
             dev = x0b.device
             mk = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
             x = mk(B, T, n) if sim else None
             mu = mk(B, T, n) if mv else None
-            var = mk(B, T, n, n) if mv else None
+            var = mk(*vshape) if mv else None
             status = torch.zeros(B, dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
                 stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -315,13 +333,15 @@ class KalmanODE:
             else:
                 x = np.empty((B, T, n)) if sim else None
                 mu = np.empty((B, T, n)) if mv else None
-                var = np.empty((B, T, n, n)) if mv else None
+                var = np.empty(vshape) if mv else None
             status = np.zeros(B, dtype=np.int32)
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.rodeo_cuda_solve_host(
                     self._h, mode, B, _ptr(x0b), _ptr(th), _ptr(z), z_stride, _ptr(x), _ptr(mu),
                     _ptr(var), _ptr(status)))
         self.status = status
+        if shared and var is not None and out is None:     # broadcast view: same shape, no copies
+            var = var.unsqueeze(0).expand(B, T, n, n) if on_dev else np.broadcast_to(var, (B, T, n, n))
         if single:
             x, mu, var = (None if a is None else a[0] for a in (x, mu, var))
         return x, mu, var

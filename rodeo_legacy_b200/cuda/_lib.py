@@ -37,6 +37,8 @@ SYMBOLS = [
     ("rodeo_cuda_set_workspace_limit", _I, [_V, _Z]),
     ("rodeo_cuda_set_checkpoint", _I, [_V, _I]),
     ("rodeo_cuda_get_checkpoint", _I, [_V]),
+    ("rodeo_cuda_set_shared_cov", _I, [_V, _I]),
+    ("rodeo_cuda_get_shared_cov", _I, [_V]),
     ("rodeo_cuda_reserve", _I, [_V, _L]),
     ("rodeo_cuda_solve", _I, [_V, _I, _L, _V, _V, _V, _L, _V, _V, _V, _V, _V]),
     ("rodeo_cuda_solve_host", _I, [_V, _I, _L, _V, _V, _V, _L, _V, _V, _V, _V]),

@@ -35,7 +35,7 @@ def _p(a, t=_dp):
     return None if a is None else a.ctypes.data_as(t)
 
 
-def solve(ode, W, tmin, tmax, N, Q, c, R, x0, theta=None, z=None, kind="mv", ig=0, unroll=True, blockdiag=False, ck=1,
+def solve(ode, W, tmin, tmax, N, Q, c, R, x0, theta=None, z=None, kind="mv", ig=0, unroll=True, blockdiag=False, ck=1, shared_cov=False,
           thin_index=None, state_index=None, Y=None, gamma=1.0):
     W, Q, R = (np.asfortranarray(np.asarray(a, dtype=np.float64)) for a in (W, Q, R))
     c = np.ascontiguousarray(c, dtype=np.float64)
@@ -55,6 +55,8 @@ def solve(ode, W, tmin, tmax, N, Q, c, R, x0, theta=None, z=None, kind="mv", ig=
     x = np.full((B, N + 1, n), np.nan) if k in (1, 2) else None
     mu = np.full((B, N + 1, n), np.nan) if k in (0, 2) else None
     var = np.full((B, N + 1, n, n), np.nan) if k in (0, 2) else None
+    if shared_cov and var is not None:      # ONE variance array for the whole batch in this mode
+        var = np.full((1, N + 1, n, n), np.nan)
     ll = np.full(B, np.nan) if k >= 3 else None
     status = np.zeros(B, dtype=np.int32)
     ti = None if thin_index is None else np.ascontiguousarray(thin_index, dtype=np.int32)
@@ -63,7 +65,7 @@ def solve(ode, W, tmin, tmax, N, Q, c, R, x0, theta=None, z=None, kind="mv", ig=
     rc = lib().hostsim_solve(
         ctypes.c_int(ODE_IDS[ode]), ctypes.c_int(n), ctypes.c_int(m), ctypes.c_int(N),
         ctypes.c_double(tmin), ctypes.c_double(tmax), _p(W), _p(Q), _p(c), _p(R), ctypes.c_int(ig),
-        ctypes.c_int(k), ctypes.c_int(int(unroll)), ctypes.c_int(int(blockdiag)), ctypes.c_int(int(ck)), ctypes.c_long(B), _p(x0), _p(theta), _p(z),
+        ctypes.c_int(k), ctypes.c_int(int(unroll)), ctypes.c_int(int(blockdiag)), ctypes.c_int(int(ck)), ctypes.c_int(int(shared_cov)), ctypes.c_long(B), _p(x0), _p(theta), _p(z),
         ctypes.c_long(z_stride), _p(x), _p(mu), _p(var), _p(status, _ip), _p(ti, _ip),
         ctypes.c_int(0 if ti is None else len(ti)), _p(si, _ip),
         ctypes.c_int(0 if si is None else len(si)), _p(Yc), ctypes.c_double(gamma), _p(ll))

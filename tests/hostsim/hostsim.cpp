@@ -64,6 +64,38 @@ static int run_ck(const typename Fam::PriorT &P, int kind, const SolveArgs &a) {
   return 0;
 }
 
+// shared-covariance mode: tables once, then the mean-only bodies (register namespace only)
+template <class Fam>
+static int run_sc(const HostPrior &h, int ig, int kind, SolveArgs a, double *var_single) {
+  typename Fam::PriorT P;
+  fill_prior(P, h);
+  using T = reg::ScTab<Fam>;
+  const int N = h.n_eval, n = Fam::n;
+  std::vector<double> tab((size_t)T::total(N), 0.0);
+  int fail = 0;
+  for (int u = 0; u < Fam::kBlocks; u++) {
+    int f = reg::sc_tables_unit<Fam>(P, ig == 1, tab.data(), u);
+    if (f && !fail) fail = f;
+  }
+  if (var_single) memcpy(var_single, tab.data() + T::offVar(N), sizeof(double) * (N + 1) * n * n);
+  std::vector<double> hist((size_t)N * n * ((a.B + 31) / 32 * 32));
+  a.hist = hist.data();
+  a.tab = tab.data();
+  a.tab_fail = fail;
+  for (long b = 0; b < a.B; b++) reg::sc_forward_body<Fam>(P, a, b);
+  for (long b = 0; b < a.B; b++) {
+    switch (kind) {
+      case 0: reg::sc_backward_body<Fam, true, false, false>(P, a, b); break;
+      case 1: reg::sc_backward_body<Fam, false, true, false>(P, a, b); break;
+      case 2: reg::sc_backward_body<Fam, true, true, false>(P, a, b); break;
+      case 3: reg::sc_backward_body<Fam, true, false, true>(P, a, b); break;
+      case 4: reg::sc_backward_body<Fam, false, true, true>(P, a, b); break;
+      default: return -1;
+    }
+  }
+  return 0;
+}
+
 template <class Fam, bool UNROLL>
 static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
   typename Fam::PriorT P;
@@ -85,7 +117,7 @@ static int run(const HostPrior &h, int ig, int kind, SolveArgs a) {
 
 extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, double tmax, const double *W,
                              const double *Q, const double *c, const double *R, int ig, int kind,
-                             int unroll, int blockdiag, int ck, long B, const double *x0, const double *theta, const double *z,
+                             int unroll, int blockdiag, int ck, int shared_cov, long B, const double *x0, const double *theta, const double *z,
                              long z_stride, double *x_out, double *mu_out, double *var_out, int *status,
                              const int *thin_index, int n_obs_times, const int *state_index,
                              int n_obs_comp, const double *Y, double gamma, double *loglik) {
@@ -111,6 +143,11 @@ extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, dou
   a.gamma = gamma;
   a.loglik = loglik;
 #define CASE(ODE, NN, PP, ID)                                                             \
+  if (ode == ID && n == NN && shared_cov) {                                               \
+    if (ig == 2) return -5;                                                               \
+    return blockdiag ? run_sc<reg::BdFam<ODE, PP>>(h, ig, kind, a, var_out)               \
+                     : run_sc<reg::DenseFam<ODE, NN>>(h, ig, kind, a, var_out);           \
+  }                                                                                       \
   if (ode == ID && n == NN) {                                                             \
     if (blockdiag)                                                                        \
       return unroll ? run<reg::BdFam<ODE, PP>, true>(h, ig, kind, a)                      \

@@ -381,3 +381,59 @@ def test_checkpointed_history_is_bit_identical(maker, B, N, ck):
     # other interrogation methods silently keep the full history
     ks = wl.make_kode(w, z_state=z, interrogate="schobert", checkpoint=ck)
     assert ks.checkpoint == 1
+
+
+@pytest.mark.parametrize("maker,B,mtol,vtol,xtol,dense_too", [
+    (wl.fitz_batch, 3000, 1e-10, 1e-9, 1e-9, True),
+    (lambda B: wl.lorenz_batch(B, N=500, tmax=2.0), 130, 1e-9, 1e-7, 1e-8, False),
+    (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7, False)])
+def test_shared_covariance_mode(maker, B, mtol, vtol, xtol, dense_too):
+    """shared_cov=True: covariance path computed once per prior, batch kernels run the mean
+    recursions only.  Against the oracle (which computes every system's covariance) and against
+    this backend's own general mode; var comes back as a broadcast view of one array."""
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(6).standard_normal((n, w["N"])))
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    for force_dense in ([False, True] if dense_too else [False]):
+        k = wl.make_kode(w, z_state=z, force_dense=force_dense, shared_cov=True)
+        assert k.shared_cov
+        n0 = k.launch_count
+        x, mu, var = k.solve(x0d, theta=thd)
+        assert k.launch_count == n0 + 3          # tables (once) + mean filter + mean smoother
+        assert var.shape == (B, w["N"] + 1, n, n) and var.stride(0) == 0
+        assert int(k.status.abs().sum()) == 0
+        assert traj_err(mu.cpu().numpy(), ref["mu"]).max() < mtol
+        assert traj_err(x.cpu().numpy(), ref["x"]).max() < xtol
+        assert var_err(var[0].cpu().numpy()[1:], ref["var"][0, 1:]).max() < vtol
+        assert not bool(var[0, 0].any())
+        mu2, var2 = k.solve_mv(x0d, theta=thd)
+        assert k.launch_count == n0 + 5          # tables are cached
+        assert bool((mu2 == mu).all())
+        assert bool((k.solve_sim(x0d, theta=thd) == x).all())
+        # general mode of the same backend
+        kg = wl.make_kode(w, z_state=z, force_dense=force_dense)
+        xg, mug, varg = kg.solve(x0d, theta=thd)
+        scale = float(mug.abs().amax())
+        assert float((mug - mu).abs().max()) < 1e-9 * scale and float((xg - x).abs().max()) < 1e-7 * scale
+        # host path: one (N+1, n, n) variance crosses PCIe, returned as a broadcast view
+        xh, muh, varh = k.solve(x0, theta=theta)
+        np.testing.assert_array_equal(muh, mu.cpu().numpy())
+        np.testing.assert_array_equal(xh, x.cpu().numpy())
+        assert varh.shape == (B, w["N"] + 1, n, n) and varh.strides[0] == 0
+        np.testing.assert_array_equal(varh[0], var[0].cpu().numpy())
+        # changing the prior invalidates the tables
+        k.var_state = np.asfortranarray(4.0 * np.asarray(w["R"]))
+        _, var4 = k.solve_mv(x0d, theta=thd)
+        assert float(var4[0, -1, 0, 0]) > 1.5 * float(var[0, -1, 0, 0])
+    if n == 6:
+        g = load_golden("fitz_n400")
+        ks = wl.make_kode(w, z_state=z, shared_cov=True)
+        ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
+        for draw, key in ((False, "mu"), (True, "x")):
+            ll = ks.loglik(x0d, thd, Y, ind, [0, 3], gam, use_draw=draw).cpu().numpy()
+            want = [oracle.loglik(ref[key][i], ind, [0, 3], Y, gam) for i in range(0, B, 97)]
+            np.testing.assert_allclose(ll[::97], want, rtol=1e-8)
+    with pytest.raises(NotImplementedError):
+        wl.make_kode(w, z_state=z, interrogate="chkrebtii", shared_cov=True)

@@ -108,3 +108,34 @@ def test_checkpointed_history_gives_identical_results(name, N, blockdiag, ck):
         b = hostsim.solve(*args, kind="ll_draw", blockdiag=blockdiag, ck=ck, thin_index=ind, state_index=[0, 3], Y=Y,
                           gamma=0.3)
         np.testing.assert_array_equal(a["loglik"], b["loglik"])
+
+
+@pytest.mark.parametrize("blockdiag", [False, True], ids=["dense", "blockdiag"])
+@pytest.mark.parametrize("name,mtol,vtol,xtol", CASES)
+def test_shared_covariance_bodies_match_oracle(name, mtol, vtol, xtol, blockdiag):
+    """Shared-covariance mode (tables once + mean-only recursions) against the oracle, which
+    computes every system's covariance itself."""
+    if name.startswith("lorenz") or name.startswith("mseir"):
+        if not blockdiag:
+            pytest.skip("dense register family exists for n_state <= 6 only")
+    g, ode, p, x0, theta = _setup(name)
+    ref = oracle.solve_batch(p, x0, theta, g["z"], oracle.MODE_BOTH)
+    args = (ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, g["z"])
+    both = hostsim.solve(*args, kind="both", blockdiag=blockdiag, shared_cov=True)
+    assert not both["status"].any()
+    assert traj_err(both["mu"], ref["mu"]).max() < mtol
+    assert traj_err(both["x"], ref["x"]).max() < xtol
+    assert both["var"].shape[0] == 1
+    assert var_err(both["var"][:, 1:], ref["var"][:1, 1:]).max() < vtol
+    assert not both["var"][:, 0].any()
+    mv = hostsim.solve(*args, kind="mv", blockdiag=blockdiag, shared_cov=True)
+    sim = hostsim.solve(*args, kind="sim", blockdiag=blockdiag, shared_cov=True)
+    np.testing.assert_array_equal(mv["mu"], both["mu"])
+    np.testing.assert_array_equal(sim["x"], both["x"])
+    if name.startswith("fitz"):
+        ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
+        for kind, key in (("ll_mean", "mu"), ("ll_draw", "x")):
+            r = hostsim.solve(*args, kind=kind, blockdiag=blockdiag, shared_cov=True, thin_index=ind,
+                              state_index=[0, 3], Y=Y, gamma=gam)
+            want = [oracle.loglik(ref[key][b], ind, [0, 3], Y, gam) for b in range(len(x0))]
+            np.testing.assert_allclose(r["loglik"], want, rtol=1e-8)
