@@ -195,6 +195,8 @@ int rodeo_cuda_reset_launch_count(rodeo_problem *p);
 /* Device time (ms) of the forward and backward kernels of the most recent
  * rodeo_cuda_solve call, measured with CUDA events on its stream; synchronises. */
 int rodeo_cuda_last_kernel_ms(rodeo_problem *p, float *forward_ms, float *backward_ms);
+/* test hook: copy the first `bytes` of the handle's history workspace to a device buffer */
+int rodeo_cuda_debug_copy_history(rodeo_problem *p, void *dst_device, size_t bytes, void *cuda_stream);
 /* enable (1) / disable (0) the event recording used by rodeo_cuda_last_kernel_ms */
 int rodeo_cuda_set_timing(rodeo_problem *p, int enabled);
 

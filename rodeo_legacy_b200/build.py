@@ -20,7 +20,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=true", "-prec-div=true", "-prec-sqrt=true",      # IEEE div / sqrt, never fast-math
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
-]
+] + (["-DRODEO_DEBUG_RING"] if os.environ.get("RODEO_DEBUG_RING") else []) \
+  + (["-DRODEO_DEBUG_POISON"] if os.environ.get("RODEO_DEBUG_POISON") else [])
 
 
 def nvcc():

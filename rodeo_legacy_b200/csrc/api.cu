@@ -520,6 +520,14 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
   return RODEO_OK;
 }
 
+// Debug / test hook: copy the first `bytes` of the history workspace to a device buffer.
+int rodeo_cuda_debug_copy_history(rodeo_problem *p, void *dst_device, size_t bytes, void *cuda_stream) {
+  if (!p || !dst_device) return fail(RODEO_E_INVALID, "null argument");
+  if (bytes > p->ws_bytes) return fail(RODEO_E_INVALID, "more bytes than the workspace holds");
+  CK(cudaMemcpyAsync(dst_device, p->ws, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  return RODEO_OK;
+}
+
 int64_t rodeo_cuda_launch_count(const rodeo_problem *p) { return p ? p->launches : 0; }
 int rodeo_cuda_reset_launch_count(rodeo_problem *p) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");

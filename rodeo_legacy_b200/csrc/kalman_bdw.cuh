@@ -179,7 +179,8 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
       const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
       const int f = bdw_dispatch<Fam, DO_MEAN, DO_VAR, DO_SIM>(blk, P, t == N, rec, zt, mus, Ss, x);
       if (f && !fail) fail = blk * p + f;
-      __syncthreads();  // every warp is done with ring slot k (and with last step's tiles)
+      fence_proxy_async();  // this thread's reads of slot k are complete before the TMA may overwrite it
+      __syncthreads();      // every warp is done with ring slot k (and with last step's tiles)
       if (tid == 0 && N - t + 2 < N) {  // refill the slot with record r + 2 (time index t - 2)
         mbar_arrive_expect_tx(&bar[k], kRecBytes);
         bulk_g2s(ring + k * REC, hist_tile + (size_t)(N - t + 2) * REC, kRecBytes, &bar[k]);

@@ -33,6 +33,14 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory (LDS of a ring slot) before
+// later async-proxy accesses (the TMA refill of that slot).  Without it an LDS that is still
+// queued in the memory pipe when the refill lands returns the NEW record: observed on B200 as
+// one 32-system tile per ~10^4 picking up record r+2's tail elements (found by the
+// "covariance is bit-identical across the batch" property test).
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -108,33 +116,108 @@ __device__ __forceinline__ void flush_runs(const double *stage, double *out, lon
   }
 }
 
-// Emit time index t of the whole tile: every lane writes its row, the warp stores the tile.
+// Per-lane constants of the tile -> global store of one output array (run of W doubles per
+// system at stage[s*ROW + OFF ..], destination out + ((b0+s)*T1 + t)*W).  The run is cut into
+// 16-byte pieces, C = W/2 per system; SPI = 32/C systems are stored per instruction, so a lane
+// always handles the same piece c of the same relative system s: every address is
+// lane-constant + t*W + j*const, computed with one multiply-add per emit instead of a
+// divide / multiply chain per piece (the integer work of the generic flush_runs was half of all
+// instructions of the kernel; profiles/r01_backward_staged_fitz_blockdiag_ck2_ncu_summary.txt).
+template <int W, int OFF, int ROW>
+struct FlushPlan {
+  static constexpr bool kFast = (W % 2 == 0) && (OFF % 2 == 0) && (ROW % 2 == 0) && (W / 2 <= 32);
+  static constexpr int C = kFast ? W / 2 : 1;
+  static constexpr int SPI = kFast ? 32 / C : 1;          // systems per store instruction
+  static constexpr int NI = (kTile + SPI - 1) / SPI;      // store instructions per emit
+  const double *src;   // stage + s_l*ROW + OFF + 2*c_l
+  double *dst0;        // out + ((b0+s_l)*T1)*W + 2*c_l   (time index 0)
+  long jstride;        // SPI*T1*W doubles between consecutive instructions
+  int s_l;
+  bool active, full;
+  __device__ __forceinline__ void init(const double *stage, double *out, long b0, long B, long T1, int lane) {
+    if constexpr (kFast) {
+      s_l = lane / C;
+      const int c_l = lane - s_l * C;
+      active = lane < SPI * C;
+      full = b0 + kTile <= B;
+      src = stage + s_l * ROW + OFF + 2 * c_l;
+      dst0 = out ? out + ((b0 + s_l) * T1) * W + 2 * c_l : nullptr;
+      jstride = (long)SPI * T1 * W;
+      rem = (int)((B - b0 < kTile ? B - b0 : kTile));
+    }
+  }
+  int rem;             // valid systems in this tile
+  __device__ __forceinline__ void run(const double *stage, double *out, long b0, long B, long T1, int t,
+                                      int lane) const {
+    if constexpr (kFast) {
+      double *d = dst0 + (long)t * W;
+      if (active) {
+        if (full && (kTile % SPI == 0)) {
+#pragma unroll
+          for (int j = 0; j < NI; j++)
+            *reinterpret_cast<double2 *>(d + j * jstride) = *reinterpret_cast<const double2 *>(src + j * SPI * ROW);
+        } else {
+#pragma unroll
+          for (int j = 0; j < NI; j++)
+            if (j * SPI + s_l < rem)
+              *reinterpret_cast<double2 *>(d + j * jstride) = *reinterpret_cast<const double2 *>(src + j * SPI * ROW);
+        }
+      }
+    } else {
+      flush_runs<W, OFF, ROW>(stage, out, b0, B, T1, t, lane);
+    }
+  }
+};
+
 template <class Fam, class L, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
-__device__ __forceinline__ void emit_staged(double *stage, const SolveArgs &a, long b0, long T1, int t, int lane,
-                                            const double *mus, const double *Ss, const double *x) {
-  constexpr int n = Fam::n, ROW = L::ROW;
-  constexpr int OFF_VAR = DO_MEAN ? n : 0, OFF_X = OFF_VAR + (DO_VAR ? n * n : 0);
-  double *row = stage + lane * ROW;
-  if (DO_MEAN) {
-#pragma unroll
-    for (int i = 0; i < n; i++) row[i] = mus[i];
+struct StagedEmitter {
+  static constexpr int n = Fam::n, ROW = L::ROW;
+  static constexpr int OFF_VAR = DO_MEAN ? n : 0, OFF_X = OFF_VAR + (DO_VAR ? n * n : 0);
+  FlushPlan<n, 0, ROW> pm;
+  FlushPlan<n * n, OFF_VAR, ROW> pv;
+  FlushPlan<n, OFF_X, ROW> px;
+  double *stage;
+  long b0, T1;
+  int lane;
+  __device__ __forceinline__ void init(double *stage_, const SolveArgs &a, long b0_, long T1_, int lane_) {
+    stage = stage_;
+    b0 = b0_;
+    T1 = T1_;
+    lane = lane_;
+    if (DO_MEAN) pm.init(stage, a.mu_out, b0, a.B, T1, lane);
+    if (DO_VAR) pv.init(stage, a.var_out, b0, a.B, T1, lane);
+    if (DO_SIM) px.init(stage, a.x_out, b0, a.B, T1, lane);
   }
-  if (DO_VAR) {
+  // Emit time index t of the whole tile: every lane writes its row (16-byte shared stores where
+  // the row is even), the warp stores the tile.
+  __device__ __forceinline__ void emit(const SolveArgs &a, int t, const double *mus, const double *Ss,
+                                       const double *x) const {
+    double v[L::ROW];
+    if (DO_MEAN) {
 #pragma unroll
-    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n; i++) v[i] = mus[i];
+    }
+    if (DO_VAR) {
 #pragma unroll
-      for (int i = 0; i < n; i++) row[OFF_VAR + j * n + i] = Fam::var_at(Ss, i, j);
+      for (int j = 0; j < n; j++)
+#pragma unroll
+        for (int i = 0; i < n; i++) v[OFF_VAR + j * n + i] = Fam::var_at(Ss, i, j);
+    }
+    if (DO_SIM) {
+#pragma unroll
+      for (int i = 0; i < n; i++) v[OFF_X + i] = x[i];
+    }
+    if (L::OUTW < L::ROW) v[L::ROW - 1] = 0.0;
+    double2 *row = reinterpret_cast<double2 *>(stage + lane * ROW);
+#pragma unroll
+    for (int i = 0; i < ROW / 2; i++) row[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    __syncwarp();
+    if (DO_MEAN) pm.run(stage, a.mu_out, b0, a.B, T1, t, lane);
+    if (DO_VAR) pv.run(stage, a.var_out, b0, a.B, T1, t, lane);
+    if (DO_SIM) px.run(stage, a.x_out, b0, a.B, T1, t, lane);
+    __syncwarp();
   }
-  if (DO_SIM) {
-#pragma unroll
-    for (int i = 0; i < n; i++) row[OFF_X + i] = x[i];
-  }
-  __syncwarp();
-  if (DO_MEAN) flush_runs<n, 0, ROW>(stage, a.mu_out, b0, a.B, T1, t, lane);
-  if (DO_VAR) flush_runs<n * n, OFF_VAR, ROW>(stage, a.var_out, b0, a.B, T1, t, lane);
-  if (DO_SIM) flush_runs<n, OFF_X, ROW>(stage, a.x_out, b0, a.B, T1, t, lane);
-  __syncwarp();
-}
+};
 
 template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 __global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::MINB)
@@ -159,6 +242,10 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
   const double *hist_tile = a.hist + (size_t)tile * R * REC;
   constexpr uint32_t kRecBytes = REC * sizeof(double);
 
+#ifdef RODEO_DEBUG_POISON
+  for (int i = lane; i < 2 * REC; i += 32) ring[i] = __longlong_as_double(0x7ff8000000000000LL);
+  __syncwarp();
+#endif
   if (lane == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
@@ -180,17 +267,27 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
 #pragma unroll
     for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[bs * Ode::n_theta + i] : 0.0;
   }
+  StagedEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM> em;
+  em.init(stage, a, b0, T1, lane);
   uint32_t phase = 0;
   // wait for record r (ring slot r & 1); returns this lane's column of it
   auto acquire = [&](int r) -> const double * {
     const int k = r & 1;
     mbar_wait(&bar[k], (phase >> k) & 1u);
     phase ^= 1u << k;
+#ifdef RODEO_DEBUG_RING
+    if (r == 0) {  // does the ring slot hold exactly what HBM holds for record r? (last element only)
+      const double sm = *(const volatile double *)(ring + k * REC + lane + (NE - 1) * kTile);
+      const double g = *(const volatile double *)(hist_tile + (size_t)r * REC + lane + (NE - 1) * kTile);
+      if (g != sm && valid && a.status) atomicMax(a.status + b, 100000 + r * 100 + (NE - 1));
+    }
+#endif
     return ring + k * REC + lane;
   };
   // every lane is done with record r: refill its slot with record r + 2
   auto release = [&](int r) {
-    __syncwarp();
+    fence_proxy_async();   // all of this lane's reads of the slot are complete ...
+    __syncwarp();          // ... for every lane, before lane 0 lets the TMA overwrite it
     if (lane == 0 && r + 2 < R) {
       const int k = r & 1;
       mbar_arrive_expect_tx(&bar[k], kRecBytes);
@@ -202,7 +299,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
     fail = Fam::template bw_terminal<kTile, DO_MEAN, DO_VAR, DO_SIM>(P, rec, DO_SIM ? zb + (long)(N - 1) * n : nullptr,
                                                                      mus, Ss, x);
     release(0);
-    emit_staged<Fam, L, DO_MEAN, DO_VAR, DO_SIM>(stage, a, b0, T1, N, lane, mus, Ss, x);
+    em.emit(a, N, mus, Ss, x);
   }
   int r = 1;
   for (int t_hi = N; t_hi > 1;) {  // this group smooths time indices t_hi-1 .. max(t_hi-CK, 1)
@@ -213,7 +310,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
           P, rec, DO_SIM ? zb + (long)(base - 1) * n : nullptr, mus, Ss, x);
       if (f && !fail) fail = f;
       release(r);
-      emit_staged<Fam, L, DO_MEAN, DO_VAR, DO_SIM>(stage, a, b0, T1, base, lane, mus, Ss, x);
+      em.emit(a, base, mus, Ss, x);
     } else {
       const int t0 = base >= 1 ? base : 0;
       const int nfwd = t_hi - 1 - t0;  // re-run time indices t0+1 .. t_hi-1 into the scratch records
@@ -251,7 +348,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
           const int f = Fam::template bw_step<kTile, DO_MEAN, DO_VAR, DO_SIM>(
               P, scratch + j * REC + lane, DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
           if (f && !fail) fail = f;
-          emit_staged<Fam, L, DO_MEAN, DO_VAR, DO_SIM>(stage, a, b0, T1, t, lane, mus, Ss, x);
+          em.emit(a, t, mus, Ss, x);
         }
       }
       if (base >= 1) {
@@ -259,7 +356,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
             P, rec, DO_SIM ? zb + (long)(base - 1) * n : nullptr, mus, Ss, x);
         if (f && !fail) fail = f;
         release(r);
-        emit_staged<Fam, L, DO_MEAN, DO_VAR, DO_SIM>(stage, a, b0, T1, base, lane, mus, Ss, x);
+        em.emit(a, base, mus, Ss, x);
       }
     }
     t_hi = base >= 1 ? base : 1;
@@ -274,7 +371,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) Ss[i] = 0.0;
-    emit_staged<Fam, L, DO_MEAN, DO_VAR, DO_SIM>(stage, a, b0, T1, 0, lane, mus, Ss, x);
+    em.emit(a, 0, mus, Ss, x);
   }
   if (valid && a.status && fail && a.status[b] == 0) a.status[b] = fail;
 }
