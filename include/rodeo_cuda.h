@@ -171,6 +171,18 @@ int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0
                      double *x_out, double *mu_out, double *var_out, int32_t *status,
                      void *cuda_stream);
 
+/* Per-system priors (e.g. a sweep over the prior scale sigma).  As rodeo_cuda_solve,
+ * but every system may bring its own wgt_meas (m x n), mu_state (n), wgt_state (n x n),
+ * var_state (n x n): device arrays, batch-major, each system column-major like the constructor's
+ * arrays.  A NULL array means "the handle's shared value for every system".  Runs on the dense
+ * kernel family with the full history (each thread keeps its prior in registers / local memory
+ * instead of the constant bank); probde interrogation only. */
+int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, const double *x0,
+                                   const double *theta, const double *z, int64_t z_batch_stride,
+                                   const double *wgt_meas_b, const double *mu_state_b,
+                                   const double *wgt_state_b, const double *var_state_b, double *x_out,
+                                   double *mu_out, double *var_out, int32_t *status, void *cuda_stream);
+
 /* Host-pointer entry point (the call a NumPy user of the reference makes): copies the
  * inputs to the device, solves in chunks with copy/compute overlap, copies the results
  * back and synchronises.  Host buffers may be pageable or pinned (pinned is faster). */

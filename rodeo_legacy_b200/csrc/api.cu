@@ -249,8 +249,11 @@ static long chunk_capacity(const rodeo_problem *p, long batch) {
   return std::min(cap, round_up(batch, 32));
 }
 
+static int ensure_workspace_bytes(rodeo_problem *p, size_t need);
 static int ensure_workspace(rodeo_problem *p, long stride) {
-  size_t need = rodeo_cuda_history_bytes_per_system(p) * (size_t)stride;
+  return ensure_workspace_bytes(p, rodeo_cuda_history_bytes_per_system(p) * (size_t)stride);
+}
+static int ensure_workspace_bytes(rodeo_problem *p, size_t need) {
   if (need <= p->ws_bytes) return RODEO_OK;
   if (p->ws) {
     cudaFree(p->ws);
@@ -320,18 +323,25 @@ static int ensure_tables(rodeo_problem *p, const HostPrior &hp, cudaStream_t str
 static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const double *x0,
                       const double *theta, const double *z, long z_stride, double *x_out,
                       double *mu_out, double *var_out, int *status, const LoglikSpec *ll,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const BatchedPrior *bp = nullptr) {
   const int n = p->n, nth = kOdeTheta[p->ode];
   const long T1 = (long)p->N + 1;
-  const long cap = chunk_capacity(p, batch);
-  const int ck = effective_ck(p), slot = ck_slot(ck);
-  int rc = ensure_workspace(p, cap);
+  // per-system priors run on the dense family with the full history, never in shared-covariance mode
+  const KernelSet *ks = bp ? find_kernel_set(p->ode, p->n, false) : p->ks;
+  const bool shared = p->shared && !bp;
+  const int ck = bp ? 1 : effective_ck(p), slot = ck_slot(ck);
+  const size_t per_system = bp ? (size_t)p->N * ks->hist_elems * sizeof(double)
+                               : rodeo_cuda_history_bytes_per_system(p);
+  long cap = (long)(p->ws_limit / per_system) / 1024 * 1024;
+  if (cap < 1024) cap = 1024;
+  cap = std::min(cap, round_up(batch, 32));
+  int rc = ensure_workspace_bytes(p, per_system * (size_t)cap);
   if (rc) return rc;
   HostPrior hp{p->n, p->m, p->N, p->tmin, p->tmax, p->W.data(), p->Q.data(), p->c.data(), p->R.data()};
-  if (p->shared) {
+  if (shared) {
     if ((rc = ensure_tables(p, hp, stream))) return rc;
     if (var_out)   // ONE (N+1, n, n) array serves the whole batch in this mode
-      CK(cudaMemcpyAsync(var_out, p->tab + p->ks->sc_table_var_offset(p->N), (size_t)T1 * n * n * sizeof(double),
+      CK(cudaMemcpyAsync(var_out, p->tab + ks->sc_table_var_offset(p->N), (size_t)T1 * n * n * sizeof(double),
                          cudaMemcpyDeviceToDevice, stream));
   }
   const long n_chunks = (batch + cap - 1) / cap;
@@ -357,9 +367,9 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     a.n_steps = p->N + 1;
     a.x_out = x_out ? x_out + off * T1 * n : nullptr;
     a.mu_out = mu_out ? mu_out + off * T1 * n : nullptr;
-    a.var_out = (var_out && !p->shared) ? var_out + off * T1 * n * n : nullptr;
-    a.tab = p->shared ? p->tab : nullptr;
-    a.tab_fail = p->shared ? p->tab_fail : 0;
+    a.var_out = (var_out && !shared) ? var_out + off * T1 * n * n : nullptr;
+    a.tab = shared ? p->tab : nullptr;
+    a.tab_fail = shared ? p->tab_fail : 0;
     a.status = status ? status + off : nullptr;
     if (ll) {
       a.thin_index = ll->thin_index;
@@ -371,9 +381,17 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
       a.loglik = ll->out + off;
     }
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 0], stream));
-    CK(p->shared ? p->ks->sc_forward(hp, a, stream) : p->ks->forward[p->ig](hp, a, stream));
-    if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
-    CK(p->shared ? p->ks->sc_backward[bk](hp, a, stream) : p->ks->backward[slot][bk](hp, a, stream));
+    if (bp) {
+      BatchedPrior c{bp->W ? bp->W + off * p->m * n : nullptr, bp->Q ? bp->Q + off * n * n : nullptr,
+                     bp->c ? bp->c + off * n : nullptr, bp->R ? bp->R + off * n * n : nullptr};
+      CK(ks->pp_forward(hp, c, a, stream));
+      if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
+      CK(ks->pp_backward[bk](hp, c, a, stream));
+    } else {
+      CK(shared ? ks->sc_forward(hp, a, stream) : ks->forward[p->ig](hp, a, stream));
+      if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
+      CK(shared ? ks->sc_backward[bk](hp, a, stream) : ks->backward[slot][bk](hp, a, stream));
+    }
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
     p->launches += 2;
   }
@@ -415,6 +433,24 @@ int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0
   BackwardKind bk = mode == RODEO_MODE_MV ? BK_MV : mode == RODEO_MODE_SIM ? BK_SIM : BK_BOTH;
   return run_chunks(p, bk, (long)batch, x0, theta, z, (long)z_batch_stride, x_out, mu_out, var_out,
                     status, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, const double *x0,
+                                   const double *theta, const double *z, int64_t z_batch_stride,
+                                   const double *wgt_meas_b, const double *mu_state_b,
+                                   const double *wgt_state_b, const double *var_state_b, double *x_out,
+                                   double *mu_out, double *var_out, int32_t *status, void *cuda_stream) {
+  int rc = check_solve_args(p, mode, batch, x0, theta, z, x_out, mu_out, var_out);
+  if (rc) return rc;
+  if (batch == 0) return RODEO_OK;
+  const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
+  if (!dense || !dense->pp_forward || p->ig != RODEO_INTERROGATE_PROBDE)
+    return fail(RODEO_E_UNSUPPORTED, "per-system priors need a dense kernel set and the probde interrogation");
+  CK(cudaSetDevice(p->device));
+  BatchedPrior bp{wgt_meas_b, wgt_state_b, mu_state_b, var_state_b};
+  BackwardKind bk = mode == RODEO_MODE_MV ? BK_MV : mode == RODEO_MODE_SIM ? BK_SIM : BK_BOTH;
+  return run_chunks(p, bk, (long)batch, x0, theta, z, (long)z_batch_stride, x_out, mu_out, var_out, status,
+                    nullptr, (cudaStream_t)cuda_stream, &bp);
 }
 
 int rodeo_cuda_loglik(rodeo_problem *p, int use_draw, int64_t batch, const double *x0, const double *theta,

@@ -67,6 +67,54 @@ kalman_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_con
   if (b < a.B) Bodies<UNROLL>::template backward<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, b);
 }
 
+// ---- per-system priors: every system brings its own Q, c, R, W ------------------
+// BatchedPrior (registry.cuh) holds the device arrays.  The thread builds its private copy of the
+// prior (registers / local memory instead of the constant bank) and runs the same bodies.
+
+template <int n, int m>
+__device__ __forceinline__ void load_batched_prior(Prior<n, m> &P, const BatchedPrior &bp, long b) {
+  if (bp.Q) {
+    const double *q = bp.Q + b * n * n;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) P.Q[i * n + j] = q[i + j * n];
+  }
+  if (bp.R) {
+    const double *r = bp.R + b * n * n;
+    for (int i = 0; i < n; i++)
+      for (int j = i; j < n; j++) P.R[sidx<n>(i, j)] = r[i + j * n];
+  }
+  if (bp.c) {
+    for (int i = 0; i < n; i++) P.c[i] = bp.c[b * n + i];
+  }
+  if (bp.W) {
+    const double *w = bp.W + b * m * n;
+    for (int a = 0; a < m; a++)
+      for (int j = 0; j < n; j++) P.W[a * n + j] = w[a + j * m];
+  }
+}
+
+template <class Fam, bool UNROLL, int IG>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+kalman_forward_pp(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
+                  const __grid_constant__ SolveArgs a) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  typename Fam::PriorT Pl = P;
+  load_batched_prior(Pl, bp, b);
+  Bodies<UNROLL>::template forward<Fam, IG>(Pl, a, b);
+}
+
+template <class Fam, bool UNROLL, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+kalman_backward_pp(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
+                   const __grid_constant__ SolveArgs a) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  typename Fam::PriorT Pl = P;
+  load_batched_prior(Pl, bp, b);
+  Bodies<UNROLL>::template backward<Fam, 1, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(Pl, a, b);
+}
+
 inline dim3 grid_for(long B) { return dim3((unsigned)((B + kThreadsPerBlock - 1) / kThreadsPerBlock)); }
 
 template <class Fam, bool UNROLL, int IG>
@@ -79,6 +127,18 @@ template <class Fam, bool UNROLL, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM
 cudaError_t launch_backward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
   kalman_backward<Fam, UNROLL, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>
       <<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
+  return cudaGetLastError();
+}
+
+template <class Fam, bool UNROLL, int IG>
+cudaError_t launch_forward_pp(const HostPrior &h, const BatchedPrior &bp, const SolveArgs &a, cudaStream_t s) {
+  kalman_forward_pp<Fam, UNROLL, IG><<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), bp, a);
+  return cudaGetLastError();
+}
+template <class Fam, bool UNROLL, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+cudaError_t launch_backward_pp(const HostPrior &h, const BatchedPrior &bp, const SolveArgs &a, cudaStream_t s) {
+  kalman_backward_pp<Fam, UNROLL, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>
+      <<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), bp, a);
   return cudaGetLastError();
 }
 
@@ -136,6 +196,16 @@ KernelSet make_kernel_set(const char *name) {
   k.sc_table_var_offset = nullptr;
   k.sc_forward = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.sc_backward[b] = nullptr;
+  k.pp_forward = nullptr;
+  for (int b = 0; b < BK_COUNT; b++) k.pp_backward[b] = nullptr;
+  if constexpr (!BD) {  // per-system priors: dense family only (a batched prior need not be structured)
+    k.pp_forward = launch_forward_pp<Fam, UNROLL, IG_PROBDE>;
+    k.pp_backward[BK_MV] = launch_backward_pp<Fam, UNROLL, true, true, false, false>;
+    k.pp_backward[BK_SIM] = launch_backward_pp<Fam, UNROLL, false, false, true, false>;
+    k.pp_backward[BK_BOTH] = launch_backward_pp<Fam, UNROLL, true, true, true, false>;
+    k.pp_backward[BK_LL_MEAN] = launch_backward_pp<Fam, UNROLL, true, false, false, true>;
+    k.pp_backward[BK_LL_DRAW] = launch_backward_pp<Fam, UNROLL, false, false, true, true>;
+  }
   if constexpr (UNROLL) {  // shared-covariance mode for the register families
     k.sc_tables = launch_sc_tables<Fam>;
     k.sc_table_doubles = sc_table_doubles<Fam>;

@@ -19,6 +19,12 @@ constexpr int kNumCk = 3;                       // checkpoint intervals 1, 2, 4
 inline int ck_slot(int ck) { return ck == 1 ? 0 : ck == 2 ? 1 : ck == 4 ? 2 : -1; }
 
 typedef cudaError_t (*launch_fn)(const HostPrior &, const SolveArgs &, cudaStream_t);
+// Per-system priors: device arrays, batch-major, each system laid out like the constructor's
+// arrays (column-major); nullptr = use the handle's shared value.
+struct BatchedPrior {
+  const double *W, *Q, *c, *R;
+};
+typedef cudaError_t (*launch_pp_fn)(const HostPrior &, const BatchedPrior &, const SolveArgs &, cudaStream_t);
 
 struct KernelSet {
   int ode, n, m;
@@ -34,6 +40,9 @@ struct KernelSet {
   long (*sc_table_var_offset)(int N);
   launch_fn sc_forward;
   launch_fn sc_backward[BK_COUNT];
+  // per-system priors (dense family, probde interrogation); nullptr when not compiled
+  launch_pp_fn pp_forward;
+  launch_pp_fn pp_backward[BK_COUNT];
 };
 
 const KernelSet *find_kernel_set(int ode, int n, bool blockdiag);

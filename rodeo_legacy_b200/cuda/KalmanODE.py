@@ -308,9 +308,31 @@ class KalmanODE:
                 z = zc
         return on_dev, single, B, x0b, th, z, z_stride
 
-    def _run(self, mode, x0, W, theta, out=None):
+    def _batched_prior(self, priors, B, dev):
+        """Device arrays of per-system priors: each (B, ...) array becomes batch-major with every
+        system column-major (what the C ABI expects); missing keys stay None (= shared value)."""
+        shapes = {"wgt_meas": (self.n_meas, self.n_state), "mu_state": (self.n_state,),
+                  "wgt_state": (self.n_state, self.n_state), "var_state": (self.n_state, self.n_state)}
+        out = {}
+        for key, shp in shapes.items():
+            v = priors.get(key)
+            if v is None:
+                out[key] = None
+                continue
+            t = torch.as_tensor(v, dtype=torch.float64, device=dev)
+            if tuple(t.shape) != (B,) + shp:
+                raise TypeError('{} has incorrect shape.'.format(key))
+            out[key] = (t.transpose(1, 2) if len(shp) == 2 else t).contiguous()
+        unknown = set(priors) - set(shapes)
+        if unknown:
+            raise TypeError(f"unknown prior fields {sorted(unknown)}")
+        return out
+
+    def _run(self, mode, x0, W, theta, out=None, priors=None):
         need_z = bool(mode & MODE_SIM) or self._ig == 2
         on_dev, single, B, x0b, th, z, z_stride = self._prep(x0, W, theta, need_z)
+        if priors is not None:
+            return self._run_batched_prior(mode, priors, on_dev, single, B, x0b, th, z, z_stride)
         n, T = self.n_state, self.n_steps
         mv, sim = bool(mode & MODE_MV), bool(mode & MODE_SIM)
         shared = self.shared_cov
@@ -346,18 +368,48 @@ class KalmanODE:
             x, mu, var = (None if a is None else a[0] for a in (x, mu, var))
         return x, mu, var
 
+    def _run_batched_prior(self, mode, priors, on_dev, single, B, x0b, th, z, z_stride):
+        dev = x0b.device if on_dev else self.device
+        to_dev = lambda a: None if a is None else (a if isinstance(a, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(a.ravel(order="K") if (a.ndim == 3 and z_stride) else
+                                 (a.ravel(order="F") if a.ndim == 2 and a is z else a))).to(dev))
+        x0d, thd, zd = to_dev(x0b), to_dev(th), to_dev(z)
+        bp = self._batched_prior(priors, B, dev)
+        n, T = self.n_state, self.n_steps
+        mv, sim = bool(mode & MODE_MV), bool(mode & MODE_SIM)
+        mk = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+        x = mk(B, T, n) if sim else None
+        mu = mk(B, T, n) if mv else None
+        var = mk(B, T, n, n) if mv else None
+        status = torch.zeros(B, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(self._lib.rodeo_cuda_solve_batched_prior(
+                self._h, mode, B, _ptr(x0d), _ptr(thd), _ptr(zd), z_stride, _ptr(bp["wgt_meas"]),
+                _ptr(bp["mu_state"]), _ptr(bp["wgt_state"]), _ptr(bp["var_state"]), _ptr(x), _ptr(mu),
+                _ptr(var), _ptr(status), stream))
+        self.status = status if on_dev else status.cpu().numpy()
+        if not on_dev:
+            x, mu, var = (None if a is None else a.cpu().numpy() for a in (x, mu, var))
+        if single:
+            x, mu, var = (None if a is None else a[0] for a in (x, mu, var))
+        return x, mu, var
+
     # ---- the reference's three methods -----------------------------------------------------
-    def solve(self, x0, W=None, theta=None):
+    # `priors` (batched extension): dict with any of wgt_meas (B, m, n), mu_state (B, n),
+    # wgt_state (B, n, n), var_state (B, n, n) -- one prior PER SYSTEM (e.g. a sweep over sigma);
+    # missing fields use the object's shared value.
+    def solve(self, x0, W=None, theta=None, priors=None):
         """(kalman_sim, kalman_mu, kalman_var) -- KalmanODE.pyx:335-394."""
-        return self._run(MODE_BOTH, x0, W, theta)
+        return self._run(MODE_BOTH, x0, W, theta, priors=priors)
 
-    def solve_sim(self, x0, W=None, theta=None):
+    def solve_sim(self, x0, W=None, theta=None, priors=None):
         """A draw from the solution posterior -- KalmanODE.pyx:396-427."""
-        return self._run(MODE_SIM, x0, W, theta)[0]
+        return self._run(MODE_SIM, x0, W, theta, priors=priors)[0]
 
-    def solve_mv(self, x0, W=None, theta=None):
+    def solve_mv(self, x0, W=None, theta=None, priors=None):
         """(posterior mean, posterior variance) -- KalmanODE.pyx:429-463."""
-        return self._run(MODE_MV, x0, W, theta)[1:]
+        return self._run(MODE_MV, x0, W, theta, priors=priors)[1:]
 
     def solve_mv_into(self, x0, theta, mu_out, var_out):
         """Host path writing into caller-provided (e.g. pinned) NumPy buffers."""

@@ -441,3 +441,53 @@ def test_shared_covariance_mode(maker, B, mtol, vtol, xtol, dense_too):
             np.testing.assert_allclose(ll[::97], want, rtol=1e-8)
     with pytest.raises(NotImplementedError):
         wl.make_kode(w, z_state=z, interrogate="chkrebtii", shared_cov=True)
+
+
+def test_per_system_priors():
+    """every system brings its own prior (here: a sweep over the IBM scale sigma
+    and a perturbed W / c per system).  Against the oracle solving each system with its own prior."""
+    from rodeo_legacy_b200 import ibm_init, indep_init
+    w, x0, theta = wl.fitz_batch(40, seed=5)
+    B, n, N = 40, 6, w["N"]
+    rng = np.random.default_rng(2)
+    sig = 0.05 + 0.2 * rng.random((B, 2))
+    Q = np.empty((B, n, n)); R = np.empty((B, n, n)); W = np.empty((B, 2, n)); c = np.empty((B, n))
+    for b in range(B):
+        kin = indep_init(ibm_init(40.0 / N, [3, 3], list(sig[b])), [3, 3])
+        Q[b], R[b] = kin["wgt_state"], kin["var_state"]
+        W[b] = w["W"] + (1e-3 * rng.standard_normal((2, n)) if b % 2 else 0.0)
+        c[b] = 1e-4 * rng.standard_normal(n) if b % 3 == 0 else 0.0
+    z = np.asfortranarray(rng.standard_normal((n, N)))
+    k = wl.make_kode(w, z_state=z)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    pri = dict(wgt_state=Q, var_state=R, wgt_meas=W, mu_state=c)
+    x, mu, var = k.solve(x0d, theta=thd, priors=pri)
+    assert int(k.status.abs().sum()) == 0
+    for b in range(B):
+        po = oracle.Problem("fitz", W[b], w["tmin"], w["tmax"], N, Q[b], c[b], R[b])
+        ref = oracle.solve(po, x0[b], theta[b], z, oracle.MODE_BOTH)
+        assert traj_err(mu[b].cpu().numpy(), ref["mu"]).max() < 1e-9
+        assert traj_err(x[b].cpu().numpy(), ref["x"]).max() < 1e-7
+        # the perturbed W couples the two blocks by ~1e-14-sized entries: compare on the matrix scale
+        vb = var[b].cpu().numpy()
+        assert np.abs(vb - ref["var"]).max() < 1e-9 * np.abs(ref["var"]).max()
+        assert var_err(np.diagonal(vb, axis1=-2, axis2=-1)[1:, None, :], np.diagonal(ref["var"], axis1=-2, axis2=-1)[1:, None, :]).max() < 1e-8
+    # only some fields batched; NumPy in -> NumPy out; equals the shared-prior solve when the
+    # batched prior repeats the shared one
+    mu_s, var_s = k.solve_mv(x0, theta=theta)
+    mu_p, var_p = k.solve_mv(x0, theta=theta, priors=dict(var_state=np.tile(np.asarray(w["R"]), (B, 1, 1))))
+    assert isinstance(mu_p, np.ndarray)
+    assert np.abs(mu_p - mu_s).max() < 1e-10 * np.abs(mu_s).max()
+    assert np.abs(var_p - var_s).max() < 1e-10 * np.abs(var_s).max()
+    with pytest.raises(TypeError, match="incorrect shape"):
+        k.solve_mv(x0, theta=theta, priors=dict(var_state=np.zeros((B, 5, 5))))
+    # wide state: dense rolled family
+    w9, x09, th9 = wl.lorenz_batch(24, N=200, tmax=0.8)
+    k9 = wl.make_kode(w9)
+    R9 = np.stack([np.asarray(w9["R"]) * (1 + 0.5 * i / 24) for i in range(24)])
+    mu9, var9 = k9.solve_mv(torch.from_numpy(x09).cuda(), theta=torch.from_numpy(th9).cuda(), priors=dict(var_state=R9))
+    for b in (0, 11, 23):
+        po = oracle.Problem("lorenz63", w9["W"], w9["tmin"], w9["tmax"], 200, w9["Q"], w9["c"], R9[b])
+        ref = oracle.solve(po, x09[b], th9[b], None, oracle.MODE_MV)
+        assert traj_err(mu9[b].cpu().numpy(), ref["mu"]).max() < 1e-9
+        assert var_err(var9[b].cpu().numpy()[1:], ref["var"][1:]).max() < 1e-7
