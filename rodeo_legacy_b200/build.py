@@ -21,7 +21,8 @@ NVCC_FLAGS = [
     "--fmad=true", "-prec-div=true", "-prec-sqrt=true",      # IEEE div / sqrt, never fast-math
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ] + (["-DRODEO_DEBUG_RING"] if os.environ.get("RODEO_DEBUG_RING") else []) \
-  + (["-DRODEO_DEBUG_POISON"] if os.environ.get("RODEO_DEBUG_POISON") else [])
+  + (["-DRODEO_DEBUG_POISON"] if os.environ.get("RODEO_DEBUG_POISON") else []) \
+  + ([f"-DRODEO_STAGED_WARPS={os.environ['RODEO_STAGED_WARPS']}"] if os.environ.get("RODEO_STAGED_WARPS") else [])
 
 
 def nvcc():

@@ -47,37 +47,6 @@ struct BdwLayout {
   static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
 
-// Store columns [C0, C0+LEN) of every system's run of W doubles from the staging tile
-// (system s at tile[s*TW + OFF ..]) to out + ((b0+s)*T1 + t)*W + C0, cooperatively.
-template <int W, int C0, int LEN, int OFF, int TW, int NTHREADS>
-__device__ __forceinline__ void flush_part(const double *tile, double *out, long b0, long B, long T1, int t,
-                                           int tid) {
-  constexpr bool V2 = (W % 2 == 0) && (C0 % 2 == 0) && (LEN % 2 == 0) && (OFF % 2 == 0);
-  if (V2) {
-    constexpr int C = LEN / 2;
-#pragma unroll
-    for (int q0 = 0; q0 < kTile * C; q0 += NTHREADS) {
-      const int q = q0 + tid;
-      if (q < kTile * C) {
-        const int s = q / C, c = q - s * C;
-        if (b0 + s < B) {
-          const double2 v = *reinterpret_cast<const double2 *>(tile + s * TW + OFF + 2 * c);
-          *reinterpret_cast<double2 *>(out + ((b0 + s) * T1 + t) * W + C0 + 2 * c) = v;
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int q0 = 0; q0 < kTile * LEN; q0 += NTHREADS) {
-      const int q = q0 + tid;
-      if (q < kTile * LEN) {
-        const int s = q / LEN, c = q - s * LEN;
-        if (b0 + s < B) out[((b0 + s) * T1 + t) * W + C0 + c] = tile[s * TW + OFF + c];
-      }
-    }
-  }
-}
-
 // Per-warp work with the block index as a compile-time constant (so the block's Q, c, R are
 // immediate constant-bank operands): Blk<A>::run is selected by a warp-uniform switch.
 template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, int A>

@@ -66,7 +66,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
-constexpr int kStagedWarps = 2;  // warps per CTA
+#ifndef RODEO_STAGED_WARPS
+#define RODEO_STAGED_WARPS 2
+#endif
+constexpr int kStagedWarps = RODEO_STAGED_WARPS;  // warps per CTA
 constexpr int kStagedThreads = kStagedWarps * 32;
 
 template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
@@ -74,14 +77,26 @@ struct StagedLayout {
   static constexpr int n = Fam::n, NE = Fam::NE;
   static constexpr int REC = NE * kTile;                                         // doubles per record
   static constexpr int OUTW = (DO_MEAN ? n : 0) + (DO_VAR ? n * n : 0) + (DO_SIM ? n : 0);
-  static constexpr int ROW = (OUTW + 1) / 2 * 2;                                 // row stride (even)
+  // The staging tile can be emitted in one pass or in two (pass 0 = mean, draw and the first H
+  // variance entries, pass 1 = the rest), which halves the tile (FN solve_mv: 10.5 -> 6.5 KB per
+  // warp) and lets 5-7 CTAs fit per SM instead of 4.  MEASURED on B200 (FN solve_mv, checkpoint 2):
+  // one pass 2.32 ms; two passes split mid-sector 3.07-3.34 ms; two passes split on a 32-byte sector
+  // boundary with the register cap that realises the extra occupancy 2.50 ms.  The second
+  // write/sync/read round costs more than the occupancy buys: one pass it is.
+  static constexpr bool TWO_PASS = false;
+  // variance entries in pass 0: about half, rounded up to whole 32-byte sectors of the run so that
+  // no sector is written by both passes
+  static constexpr int H = TWO_PASS ? ((n * n / 2 + 3) / 4 * 4) : n * n;
+  static constexpr int VEC_W = (DO_MEAN ? n : 0) + (DO_SIM ? n : 0);
+  static constexpr int W0 = VEC_W + (DO_VAR ? H : 0), W1 = TWO_PASS ? n * n - H : 0;
+  static constexpr int ROW = ((W0 > W1 ? W0 : W1) + 1) / 2 * 2;                  // row stride (even)
   // per warp: 2 ring slots (checkpoint records, TMA), CK-1 scratch records (re-run filter),
   // the output staging tile, 2 mbarriers
   static constexpr int WARP_DOUBLES = (2 + (CK - 1)) * REC + kTile * ROW + 2;
   static constexpr size_t smem_bytes = (size_t)kStagedWarps * WARP_DOUBLES * sizeof(double);
-  // No min-blocks launch bound: capping registers (tried: 168 / 128 per thread for the
-  // block-diagonal family) makes ptxas spill inside the unrolled step and DOUBLED the kernel
-  // time on B200 (2.52 -> 5.12 ms, FN solve_mv); 254 registers and 8 warps / SM is faster.
+  // No min-blocks launch bound: with a one-pass tile shared memory limits the kernel to 4 CTAs per
+  // SM anyway, and a register cap below what ptxas wants only adds spills (tried 168 / 128:
+  // 2.5 -> 5.1 ms).
   static constexpr int MINB = 1;
 };
 
@@ -116,23 +131,55 @@ __device__ __forceinline__ void flush_runs(const double *stage, double *out, lon
   }
 }
 
-// Per-lane constants of the tile -> global store of one output array (run of W doubles per
-// system at stage[s*ROW + OFF ..], destination out + ((b0+s)*T1 + t)*W).  The run is cut into
-// 16-byte pieces, C = W/2 per system; SPI = 32/C systems are stored per instruction, so a lane
-// always handles the same piece c of the same relative system s: every address is
-// lane-constant + t*W + j*const, computed with one multiply-add per emit instead of a
-// divide / multiply chain per piece (the integer work of the generic flush_runs was half of all
-// instructions of the kernel; profiles/r01_backward_staged_fitz_blockdiag_ck2_ncu_summary.txt).
-template <int W, int OFF, int ROW>
+// Generic (any parity) store of columns [C0, C0+LEN) of every system's run of W doubles from a
+// staging tile (system s at tile[s*TW + OFF ..]) to out + ((b0+s)*T1 + t)*W + C0, by NTHREADS threads.
+template <int W, int C0, int LEN, int OFF, int TW, int NTHREADS>
+__device__ __forceinline__ void flush_part(const double *tile, double *out, long b0, long B, long T1, int t,
+                                           int tid) {
+  constexpr bool V2 = (W % 2 == 0) && (C0 % 2 == 0) && (LEN % 2 == 0) && (OFF % 2 == 0) && (TW % 2 == 0);
+  if (V2) {
+    constexpr int C = LEN / 2;
+#pragma unroll
+    for (int q0 = 0; q0 < kTile * C; q0 += NTHREADS) {
+      const int q = q0 + tid;
+      if (q < kTile * C) {
+        const int s = q / C, c = q - s * C;
+        if (b0 + s < B) {
+          const double2 v = *reinterpret_cast<const double2 *>(tile + s * TW + OFF + 2 * c);
+          *reinterpret_cast<double2 *>(out + ((b0 + s) * T1 + t) * W + C0 + 2 * c) = v;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q0 = 0; q0 < kTile * LEN; q0 += NTHREADS) {
+      const int q = q0 + tid;
+      if (q < kTile * LEN) {
+        const int s = q / LEN, c = q - s * LEN;
+        if (b0 + s < B) out[((b0 + s) * T1 + t) * W + C0 + c] = tile[s * TW + OFF + c];
+      }
+    }
+  }
+}
+
+// Per-lane constants of the tile -> global store of columns [C0, C0+LEN) of one output array
+// (run of W doubles per system, staged at stage[s*ROW + OFF ..], destination
+// out + ((b0+s)*T1 + t)*W + C0).  The piece is cut into 16-byte chunks, C = LEN/2 per system;
+// SPI = 32/C systems are stored per instruction, so a lane always handles the same chunk c of the
+// same relative system s: every address is lane-constant + t*W + j*const, computed with one
+// multiply-add per emit instead of a divide / multiply chain per chunk (the integer work of the
+// generic flush was half of all instructions of the kernel).
+template <int W, int C0, int LEN, int OFF, int ROW>
 struct FlushPlan {
-  static constexpr bool kFast = (W % 2 == 0) && (OFF % 2 == 0) && (ROW % 2 == 0) && (W / 2 <= 32);
-  static constexpr int C = kFast ? W / 2 : 1;
+  static constexpr bool kFast = (W % 2 == 0) && (C0 % 2 == 0) && (LEN % 2 == 0) && (OFF % 2 == 0) &&
+                                (ROW % 2 == 0) && (LEN / 2 <= 32) && (LEN > 0);
+  static constexpr int C = kFast ? LEN / 2 : 1;
   static constexpr int SPI = kFast ? 32 / C : 1;          // systems per store instruction
   static constexpr int NI = (kTile + SPI - 1) / SPI;      // store instructions per emit
   const double *src;   // stage + s_l*ROW + OFF + 2*c_l
-  double *dst0;        // out + ((b0+s_l)*T1)*W + 2*c_l   (time index 0)
+  double *dst0;        // out + ((b0+s_l)*T1)*W + C0 + 2*c_l   (time index 0)
   long jstride;        // SPI*T1*W doubles between consecutive instructions
-  int s_l;
+  int s_l, rem;        // relative system of this lane; valid systems in this tile
   bool active, full;
   __device__ __forceinline__ void init(const double *stage, double *out, long b0, long B, long T1, int lane) {
     if constexpr (kFast) {
@@ -141,15 +188,16 @@ struct FlushPlan {
       active = lane < SPI * C;
       full = b0 + kTile <= B;
       src = stage + s_l * ROW + OFF + 2 * c_l;
-      dst0 = out ? out + ((b0 + s_l) * T1) * W + 2 * c_l : nullptr;
+      dst0 = out ? out + ((b0 + s_l) * T1) * W + C0 + 2 * c_l : nullptr;
       jstride = (long)SPI * T1 * W;
       rem = (int)((B - b0 < kTile ? B - b0 : kTile));
     }
   }
-  int rem;             // valid systems in this tile
   __device__ __forceinline__ void run(const double *stage, double *out, long b0, long B, long T1, int t,
                                       int lane) const {
-    if constexpr (kFast) {
+    if constexpr (LEN == 0) {
+      return;
+    } else if constexpr (kFast) {
       double *d = dst0 + (long)t * W;
       if (active) {
         if (full && (kTile % SPI == 0)) {
@@ -164,18 +212,19 @@ struct FlushPlan {
         }
       }
     } else {
-      flush_runs<W, OFF, ROW>(stage, out, b0, B, T1, t, lane);
+      flush_part<W, C0, LEN, OFF, ROW, 32>(stage, out, b0, B, T1, t, lane);
     }
   }
 };
 
 template <class Fam, class L, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 struct StagedEmitter {
-  static constexpr int n = Fam::n, ROW = L::ROW;
-  static constexpr int OFF_VAR = DO_MEAN ? n : 0, OFF_X = OFF_VAR + (DO_VAR ? n * n : 0);
-  FlushPlan<n, 0, ROW> pm;
-  FlushPlan<n * n, OFF_VAR, ROW> pv;
-  FlushPlan<n, OFF_X, ROW> px;
+  static constexpr int n = Fam::n, ROW = L::ROW, H = L::H;
+  static constexpr int OFF_X = DO_MEAN ? n : 0, OFF_VAR = L::VEC_W;
+  FlushPlan<n, 0, (DO_MEAN ? n : 0), 0, ROW> pm;
+  FlushPlan<n, 0, (DO_SIM ? n : 0), OFF_X, ROW> px;
+  FlushPlan<n * n, 0, (DO_VAR ? H : 0), OFF_VAR, ROW> pv0;
+  FlushPlan<n * n, H, L::W1, 0, ROW> pv1;
   double *stage;
   long b0, T1;
   int lane;
@@ -185,37 +234,53 @@ struct StagedEmitter {
     T1 = T1_;
     lane = lane_;
     if (DO_MEAN) pm.init(stage, a.mu_out, b0, a.B, T1, lane);
-    if (DO_VAR) pv.init(stage, a.var_out, b0, a.B, T1, lane);
     if (DO_SIM) px.init(stage, a.x_out, b0, a.B, T1, lane);
+    if (DO_VAR) pv0.init(stage, a.var_out, b0, a.B, T1, lane);
+    if (L::TWO_PASS) pv1.init(stage, a.var_out, b0, a.B, T1, lane);
   }
-  // Emit time index t of the whole tile: every lane writes its row (16-byte shared stores where
-  // the row is even), the warp stores the tile.
-  __device__ __forceinline__ void emit(const SolveArgs &a, int t, const double *mus, const double *Ss,
-                                       const double *x) const {
-    double v[L::ROW];
-    if (DO_MEAN) {
-#pragma unroll
-      for (int i = 0; i < n; i++) v[i] = mus[i];
-    }
-    if (DO_VAR) {
-#pragma unroll
-      for (int j = 0; j < n; j++)
-#pragma unroll
-        for (int i = 0; i < n; i++) v[OFF_VAR + j * n + i] = Fam::var_at(Ss, i, j);
-    }
-    if (DO_SIM) {
-#pragma unroll
-      for (int i = 0; i < n; i++) v[OFF_X + i] = x[i];
-    }
-    if (L::OUTW < L::ROW) v[L::ROW - 1] = 0.0;
+  __device__ __forceinline__ void put_row(const double *v) const {
     double2 *row = reinterpret_cast<double2 *>(stage + lane * ROW);
 #pragma unroll
     for (int i = 0; i < ROW / 2; i++) row[i] = make_double2(v[2 * i], v[2 * i + 1]);
+  }
+  // Emit time index t of the whole tile: every lane writes its row (16-byte shared stores), the
+  // warp stores the tile; long rows go out in two passes through the same tile.
+  __device__ __forceinline__ void emit(const SolveArgs &a, int t, const double *mus, const double *Ss,
+                                       const double *x) const {
+    {
+      double v[ROW];
+#pragma unroll
+      for (int i = 0; i < ROW; i++) v[i] = 0.0;
+      if (DO_MEAN) {
+#pragma unroll
+        for (int i = 0; i < n; i++) v[i] = mus[i];
+      }
+      if (DO_SIM) {
+#pragma unroll
+        for (int i = 0; i < n; i++) v[OFF_X + i] = x[i];
+      }
+      if (DO_VAR) {
+#pragma unroll
+        for (int e = 0; e < H; e++) v[OFF_VAR + e] = Fam::var_at(Ss, e % n, e / n);
+      }
+      put_row(v);
+    }
     __syncwarp();
     if (DO_MEAN) pm.run(stage, a.mu_out, b0, a.B, T1, t, lane);
-    if (DO_VAR) pv.run(stage, a.var_out, b0, a.B, T1, t, lane);
     if (DO_SIM) px.run(stage, a.x_out, b0, a.B, T1, t, lane);
+    if (DO_VAR) pv0.run(stage, a.var_out, b0, a.B, T1, t, lane);
     __syncwarp();
+    if (L::TWO_PASS) {
+      double v[ROW];
+#pragma unroll
+      for (int i = 0; i < ROW; i++) v[i] = 0.0;
+#pragma unroll
+      for (int e = H; e < n * n; e++) v[e - H] = Fam::var_at(Ss, e % n, e / n);
+      put_row(v);
+      __syncwarp();
+      pv1.run(stage, a.var_out, b0, a.B, T1, t, lane);
+      __syncwarp();
+    }
   }
 };
 
