@@ -491,3 +491,32 @@ def test_per_system_priors():
         ref = oracle.solve(po, x09[b], th9[b], None, oracle.MODE_MV)
         assert traj_err(mu9[b].cpu().numpy(), ref["mu"]).max() < 1e-9
         assert var_err(var9[b].cpu().numpy()[1:], ref["var"][1:]).max() < 1e-7
+
+
+def test_config5_sweep():
+    """BASELINE config 5 on one GPU at reduced size: a theta sweep through the fused
+    log-likelihood (chunked workspace, as the 1,048,576-theta run of tools/sweep_c5.py), the
+    sharding helpers on a single rank, and an oracle check of a strided sample."""
+    from rodeo_legacy_b200.dist import gather_batch, shard_range
+    total = 40000
+    w = wl.fitz()
+    rng = np.random.default_rng(0)
+    theta = np.exp(np.log(w["theta0"]) + 0.1 * rng.standard_normal((total, 3)))
+    x0 = np.tile(w["x0"], (total, 1))
+    ind = np.arange(10, 401, 10)
+    k = wl.make_kode(w)
+    k.set_workspace_limit(8192 * k.history_bytes_per_system)        # 5 chunks
+    mu_true, _ = k.solve_mv(w["x0"], theta=w["theta0"])
+    Y = mu_true[ind][:, [0, 3]] + 0.2 * np.random.default_rng(5).standard_normal((40, 2))
+    lo, hi = shard_range(total, 0, 1)
+    assert (lo, hi) == (0, total)
+    n0 = k.launch_count
+    ll = gather_batch(k.loglik(torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda(), Y, ind, [0, 3], 0.2), total)
+    assert k.launch_count - n0 == 10 and ll.shape == (total,)
+    pick = np.linspace(0, total - 1, 24).astype(int)
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], None, oracle.MODE_MV)
+    want = [oracle.loglik(m, ind, [0, 3], Y, 0.2) for m in ref["mu"]]
+    np.testing.assert_allclose(ll[pick].cpu().numpy(), want, rtol=1e-8)
+    # the sweep finds the neighbourhood of the true parameters
+    best = theta[int(ll.argmax())]
+    assert np.all(np.abs(np.log(best / w["theta0"])) < 0.25)

@@ -4,9 +4,11 @@ over the GPUs of one box (one rank per GPU under torchrun), no data-path collect
 all_gather of 8 bytes per system at the end.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        tools/sweep_c5.py [--total 1048576] [--check 16]
+        tools/sweep_c5.py [--total 1048576]
 
-Prints one JSON line from rank 0 (device time = max over ranks, gather included)."""
+Prints one JSON line from rank 0 (device time = max over ranks, gather included).  The values are
+checked against the CPU oracle in tests/test_gpu_parity.py::test_config5_sweep (this tool never
+touches the oracle)."""
 import argparse
 import json
 import os
@@ -26,7 +28,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--total", type=int, default=1 << 20)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--check", type=int, default=16, help="systems checked against the CPU oracle on rank 0")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -64,21 +65,10 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         best = min(best, float(t.item()))
-    ok = None
-    if rank == 0 and a.check:
-        import oracle
-        pick = np.linspace(0, a.total - 1, a.check).astype(int)
-        full_theta = np.exp(np.log(w["theta0"]) + 0.1 * np.random.default_rng(0).standard_normal((a.total, 3))[pick])
-        ref = oracle.solve_batch(wl.make_oracle_problem(w), np.tile(w["x0"], (len(pick), 1)), full_theta,
-                                 None, oracle.MODE_MV, nthreads=len(os.sched_getaffinity(0)))
-        want = np.array([oracle.loglik(m, ind, [0, 3], Y, 0.2) for m in ref["mu"]])
-        got = ll[pick].cpu().numpy()
-        ok = bool(np.allclose(got, want, rtol=1e-8))
-        assert ok, (got, want)
     if rank == 0:
         print(json.dumps({"config": "C5 fitz loglik sweep", "total": a.total, "n_gpus": world, "ms": best,
                           "solves_per_s": a.total / best * 1e3, "gathered": int(ll.numel()),
-                          "oracle_check": ok, "argmax_theta_index": int(ll.argmax())}), flush=True)
+                          "argmax_theta_index": int(ll.argmax()), "loglik_checksum": float(ll.sum())}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
