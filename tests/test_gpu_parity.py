@@ -105,6 +105,21 @@ def test_per_system_draws_and_ragged_chunks(force_dense):
     np.testing.assert_array_equal(xh, x)
 
 
+def test_per_system_draws_wide_state():
+    """z per system through the warp-per-block smoother (Lorenz63, 3 blocks), partial last tile."""
+    w, x0, theta = wl.lorenz_batch(75, N=300, tmax=1.2)
+    z = np.random.default_rng(3).standard_normal((75, 9, 300))
+    k = wl.make_kode(w, z_state=z)
+    assert k.kernel_family == ("blockdiag", "registers")
+    x, mu, var = k.solve(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda())
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+    assert traj_err(x.cpu().numpy(), ref["x"]).max() < 1e-8
+    assert traj_err(mu.cpu().numpy(), ref["mu"]).max() < 1e-9
+    assert var_err(var.cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-7
+    xh = k.solve_sim(x0, theta=theta)
+    np.testing.assert_array_equal(xh, x.cpu().numpy())
+
+
 @pytest.mark.parametrize("force_dense", [False, True], ids=["auto", "dense"])
 def test_fitz_full_size_properties(force_dense):
     """BASELINE config 2 (65,536 theta draws, n_eval 400, solve_mv) through properties that

@@ -139,3 +139,36 @@ def test_shared_covariance_bodies_match_oracle(name, mtol, vtol, xtol, blockdiag
                               state_index=[0, 3], Y=Y, gamma=gam)
             want = [oracle.loglik(ref[key][b], ind, [0, 3], Y, gam) for b in range(len(x0))]
             np.testing.assert_allclose(r["loglik"], want, rtol=1e-8)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_dense_problems(seed):
+    """Random dense priors (nothing block diagonal, nothing triangular, W dense, c nonzero): the
+    dense kernel bodies against the oracle, including checkpointed history."""
+    rng = np.random.default_rng(seed)
+    n, m, N = 6, 2, 60
+    A = rng.standard_normal((n, n))
+    R = 1e-3 * (A @ A.T + n * np.eye(n))
+    Q = np.eye(n) + 0.05 * rng.standard_normal((n, n))
+    W = rng.standard_normal((m, n))
+    c = 0.01 * rng.standard_normal(n)
+    B = 3
+    x0 = rng.standard_normal((B, n))
+    theta = np.exp(np.log([0.2, 0.2, 3.0]) + 0.1 * rng.standard_normal((B, 3)))
+    z = rng.standard_normal((n, N))
+    p = oracle.Problem("fitz", W, 0.0, 3.0, N, Q, c, R)
+    ref = oracle.solve_batch(p, x0, theta, z, oracle.MODE_BOTH)
+    assert not ref["status"].any()
+    for ck in (1, 2, 4):
+        r = hostsim.solve("fitz", W, 0.0, 3.0, N, Q, c, R, x0, theta, z, kind="both", ck=ck)
+        assert not r["status"].any()
+        assert traj_err(r["mu"], ref["mu"]).max() < 1e-10
+        assert traj_err(r["x"], ref["x"]).max() < 1e-9
+        assert np.abs(r["var"] - ref["var"]).max() < 1e-11 * np.abs(ref["var"]).max()
+    sc = hostsim.solve("fitz", W, 0.0, 3.0, N, Q, c, R, x0, theta, z, kind="both", shared_cov=True)
+    assert traj_err(sc["mu"], ref["mu"]).max() < 1e-10
+    assert traj_err(sc["x"], ref["x"]).max() < 1e-9
+    assert np.abs(sc["var"][0] - ref["var"][0]).max() < 1e-11 * np.abs(ref["var"]).max()
+    # a prior that is not positive definite is reported, not hidden
+    bad = hostsim.solve("fitz", W, 0.0, 3.0, N, Q, c, -R, x0, theta, z, kind="mv")
+    assert bad["status"].all()
