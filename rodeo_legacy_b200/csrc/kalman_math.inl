@@ -34,7 +34,7 @@ RD_UNROLL
 RD_UNROLL
     for (int k = j + 1; k < n; k++) {
       double lkj = A[sidx<n>(k, j)];
-RD_UNROLL
+RD_UNROLL_IN
       for (int i = k; i < n; i++) A[sidx<n>(i, k)] -= A[sidx<n>(i, j)] * lkj;
     }
   }
@@ -47,14 +47,14 @@ RD_HD void chol_solve_vec(const double *L, const double *invd, double *x, int st
 RD_UNROLL
   for (int i = 0; i < n; i++) {
     double s = x[i * stride];
-RD_UNROLL
+RD_UNROLL_IN
     for (int k = 0; k < i; k++) s -= L[sidx<n>(i, k)] * x[k * stride];
     x[i * stride] = s * invd[i];
   }
 RD_UNROLL
   for (int i = n - 1; i >= 0; i--) {
     double s = x[i * stride];
-RD_UNROLL
+RD_UNROLL_IN
     for (int k = i + 1; k < n; k++) s -= L[sidx<n>(k, i)] * x[k * stride];
     x[i * stride] = s * invd[i];
   }
@@ -66,7 +66,7 @@ RD_HD void predict_mean(const double *Q, const double *c, const double *mu, doub
 RD_UNROLL
   for (int i = 0; i < n; i++) {
     double s = c[i];
-RD_UNROLL
+RD_UNROLL_IN
     for (int k = 0; k < n; k++) s += Q[i * n + k] * mu[k];
     mup[i] = s;
   }
@@ -83,7 +83,7 @@ RD_UNROLL
 RD_UNROLL
     for (int k = 0; k < n; k++) {
       double s = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
       for (int l = 0; l < n; l++) s += Q[i * n + l] * S[sidx<n>(l, k)];
       Ti[k] = s;
       if (KEEP_T) T[i * n + k] = s;
@@ -91,7 +91,7 @@ RD_UNROLL
 RD_UNROLL
     for (int j = i; j < n; j++) {
       double s = R[sidx<n>(i, j)];
-RD_UNROLL
+RD_UNROLL_IN
       for (int k = 0; k < n; k++) s += Ti[k] * Q[j * n + k];
       Sp[sidx<n>(i, j)] = s;
     }
@@ -111,7 +111,7 @@ RD_UNROLL
 RD_UNROLL
     for (int j = 0; j < n; j++) {
       double s = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
       for (int k = 0; k < n; k++) s += W[a * n + k] * S[sidx<n>(k, j)];
       A[a * n + j] = s;
     }
@@ -121,7 +121,7 @@ RD_UNROLL
 RD_UNROLL
     for (int b = a; b < m; b++) {
       double s = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
       for (int j = 0; j < n; j++) s += A[a * n + j] * W[b * n + j];
       Sm[sidx<m>(a, b)] = zero_H ? s : s + s;
     }
@@ -130,7 +130,7 @@ RD_UNROLL
 RD_UNROLL
   for (int a = 0; a < m; a++) {
     double s = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
     for (int k = 0; k < n; k++) s += W[a * n + k] * mu[k];
     e[a] = y[a] - s;
   }
@@ -146,14 +146,14 @@ RD_UNROLL
       for (int a = 0; a < m; a++) dumpK[a * n + j] = kj[a];
     }
     double s = mu[j];
-RD_UNROLL
+RD_UNROLL_IN
     for (int a = 0; a < m; a++) s += kj[a] * e[a];
     mu[j] = s;
     // Sf(i, j), i <= j: Sp(i, j) - sum_a K(a, i) A(a, j) = Sp(i, j) - sum_a A(a, i) K(a, j)
 RD_UNROLL
     for (int i = 0; i <= j; i++) {
       double v = S[sidx<n>(i, j)];
-RD_UNROLL
+RD_UNROLL_IN
       for (int a = 0; a < m; a++) v -= A[a * n + i] * kj[a];
       S[sidx<n>(i, j)] = v;
     }
@@ -172,7 +172,7 @@ RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool z
 RD_UNROLL
   for (int j = 0; j < p; j++) {
     double v = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
     for (int k = 0; k < p; k++) v += w[k] * S[sidx<p>(k, j)];
     A[j] = v;
   }
@@ -189,7 +189,7 @@ RD_UNROLL
     const double kj = A[j] * inv;
     if (dumpK) dumpK[j] = kj;
     mu[j] += kj * e;
-RD_UNROLL
+RD_UNROLL_IN
     for (int i = 0; i <= j; i++) S[sidx<p>(i, j)] -= A[i] * kj;
   }
   return fail;
@@ -203,7 +203,7 @@ RD_HD int state_sim(double *x, const double *mu, double *V, const double *z) {
 RD_UNROLL
   for (int i = 0; i < n; i++) {
     double s = mu[i];
-RD_UNROLL
+RD_UNROLL_IN
     for (int k = 0; k <= i; k++) s += V[sidx<n>(i, k)] * z[k];
     x[i] = s;
   }
@@ -284,7 +284,7 @@ RD_UNROLL
 RD_UNROLL
     for (int i = 0; i < n; i++) {
       double s = muf[i];
-RD_UNROLL
+RD_UNROLL_IN
       for (int k = 0; k < n; k++) s += T[k * n + i] * dmu[k];
       mus[i] = s;
     }
@@ -296,7 +296,7 @@ RD_UNROLL
 RD_UNROLL
     for (int i = 0; i < n; i++) {
       double s = muf[i];
-RD_UNROLL
+RD_UNROLL_IN
       for (int k = 0; k < n; k++) s += T[k * n + i] * dx[k];
       mt[i] = s;
     }
@@ -312,13 +312,13 @@ RD_UNROLL
 RD_UNROLL
       for (int j = 0; j < n; j++) {
         double s = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
         for (int l = 0; l < n; l++) s += Q[k * n + l] * Sf[sidx<n>(l, j)];
         Tk[j] = s;
       }
 RD_UNROLL
       for (int i = 0; i < n; i++)
-RD_UNROLL
+RD_UNROLL_IN
         for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * Tk[j];
     }
 RD_UNROLL
@@ -338,14 +338,14 @@ RD_UNROLL
 RD_UNROLL
       for (int l = 0; l < n; l++) {
         double s = 0.0;
-RD_UNROLL
+RD_UNROLL_IN
         for (int k = 0; k < n; k++) s += T[k * n + i] * Ss[sidx<n>(k, l)];
         G[l] = s;
       }
 RD_UNROLL
       for (int j = i; j < n; j++) {
         double s = rec_S2[sidx<n>(i, j) * STRIDE];
-RD_UNROLL
+RD_UNROLL_IN
         for (int l = 0; l < n; l++) s += G[l] * T[l * n + j];
         Sn[sidx<n>(i, j)] = s;
       }

@@ -52,7 +52,11 @@ enum { IG_PROBDE = 0, IG_SCHOBERT = 1, IG_CHKREBTII = 2 };
 
 }  // namespace rodeo
 
+// RD_UNROLL: every loop; RD_UNROLL_IN: innermost accumulation loops of the math routines, which
+// are unrolled in BOTH policies (in the rolled family that gives the local-memory loads of one
+// dot product instruction-level parallelism instead of one dependent load per iteration).
 #define RD_UNROLL _Pragma("unroll")
+#define RD_UNROLL_IN _Pragma("unroll")
 namespace rodeo {
 namespace reg {
 #include "kalman_math.inl"
@@ -69,6 +73,7 @@ namespace loc {
 }  // namespace loc
 }  // namespace rodeo
 #undef RD_UNROLL
+#undef RD_UNROLL_IN
 
 namespace rodeo {
 
