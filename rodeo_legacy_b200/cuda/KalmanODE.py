@@ -281,7 +281,7 @@ class KalmanODE:
                 th = (th.expand(B, self.n_theta) if th.shape[0] == 1 else th).contiguous()
             else:
                 th = np.asarray(theta, dtype=np.float64).reshape(-1, self.n_theta)
-                th = np.ascontiguousarray(np.broadcast_to(th, (B, self.n_theta)) if th.shape[0] == 1 else th)
+                th = np.array(np.broadcast_to(th, (B, self.n_theta))) if th.shape[0] == 1 else np.ascontiguousarray(th)
             if th.shape[0] != B:
                 raise TypeError('{} has incorrect shape.'.format('theta'))
         z, z_stride = None, 0

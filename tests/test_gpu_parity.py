@@ -535,3 +535,37 @@ def test_config5_sweep():
     # the sweep finds the neighbourhood of the true parameters
     best = theta[int(ll.argmax())]
     assert np.all(np.abs(np.log(best / w["theta0"])) < 0.25)
+
+
+def test_batched_inference_front_end():
+    """The caller side: inference.kalman_nlpost batched over phi (examples/inference.py:85-94) and
+    phi_fit (Nelder-Mead + a Hessian stencil evaluated in one batched call)."""
+    import scipy.stats
+    from rodeo_legacy_b200.inference import inference, thin_index
+    g = load_golden("fitz_n400")
+    w = wl.fitz()
+    z = np.asfortranarray(g["z"])
+    k = wl.make_kode(w, z_state=z)
+    inf = inference([0, 3], 0, 40, None, W=w["W"], kode=k)
+    Y, gam = g["Y"], float(g["gamma"])
+    phi_mean, phi_sd = np.log(w["theta0"]), np.ones(3)
+    rng = np.random.default_rng(8)
+    phi = phi_mean + 0.1 * rng.standard_normal((37, 3))
+    nl = inf.kalman_nlpost(phi, Y, w["x0"], 0.1, phi_mean, phi_sd, gam)          # draws, as the reference
+    nl_mean = inf.kalman_nlpost(phi, Y, w["x0"], 0.1, phi_mean, phi_sd, gam, use_draw=False)
+    assert nl.shape == (37,)
+    po = wl.make_oracle_problem(w)
+    ref = oracle.solve_batch(po, np.tile(w["x0"], (37, 1)), np.exp(phi), z, oracle.MODE_BOTH)
+    ind = thin_index(np.linspace(1, 40, 40), np.linspace(0, 40, 401))
+    for key, got in (("x", nl), ("mu", nl_mean)):
+        want = [-(inf.loglike(Y, ref[key][b][ind][:, [0, 3]], gam) + inf.loglike(phi[b], phi_mean, phi_sd))
+                for b in range(37)]
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+    # a single phi returns a float, equal to the batched value
+    assert np.isclose(inf.kalman_nlpost(phi[3], Y, w["x0"], 0.1, phi_mean, phi_sd, gam), nl[3], rtol=1e-12)
+    # the golden observations were generated around theta_true: the fit must land near it
+    phi_hat, phi_var = inf.phi_fit(Y, w["x0"], 0.1, w["theta0"], phi_sd, gam, use_draw=False)
+    assert np.all(np.abs(phi_hat - phi_mean) < 0.5)
+    assert np.all(np.linalg.eigvalsh(phi_var) > 0) and np.all(np.sqrt(np.diag(phi_var)) < 1.0)
+    th = inf.theta_sample(phi_hat, phi_var, 1000, rng)
+    assert th.shape == (1000, 3) and np.all(th > 0)

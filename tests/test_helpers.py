@@ -78,3 +78,19 @@ def test_small_linear_helpers():
     np.testing.assert_allclose(Ac, V[2:, :2] @ np.linalg.inv(V[:2, :2]), rtol=1e-10)
     np.testing.assert_allclose(Vc, V[2:, 2:] - Ac @ V[:2, 2:], rtol=1e-12)
     np.testing.assert_allclose(b, mu[2:] - Ac @ mu[:2], rtol=1e-12)
+
+
+def test_thin_index_matches_reference_thinning():
+    """rodeo_legacy_b200.inference.thin_index against the indices the reference's own
+    inference.thinning picked (tests/golden/make_golden.py)."""
+    from rodeo_legacy_b200.inference import thin_index, inference
+    g = load_golden("fitz_n400")
+    np.testing.assert_array_equal(thin_index(g["data_t"], np.linspace(0, 40, 401)), g["thin_ind"])
+    t = load_golden("thinning_n130")
+    np.testing.assert_array_equal(thin_index(t["data_t"], t["ode_t"]), t["ind"])
+    inf = inference([0, 3], 0, 40, None)
+    X = np.arange(401.0)[:, None] * np.ones((1, 6))
+    np.testing.assert_array_equal(inf.thinning(g["data_t"], np.linspace(0, 40, 401), X)[:, 0], g["thin_ind"])
+    # loglike = the reference's: scale passed as `var`
+    np.testing.assert_allclose(inf.loglike(np.array([0.3]), np.array([0.1]), 0.2),
+                               -0.5 * np.log(2 * np.pi) - np.log(0.2) - 0.5)
