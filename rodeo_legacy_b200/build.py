@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ] + (["-DRODEO_DEBUG_RING"] if os.environ.get("RODEO_DEBUG_RING") else []) \
   + (["-DRODEO_DEBUG_POISON"] if os.environ.get("RODEO_DEBUG_POISON") else []) \
+  + ([f"-DRODEO_BDW_MIN_BLOCKS={os.environ['RODEO_BDW_MIN_BLOCKS']}"] if os.environ.get("RODEO_BDW_MIN_BLOCKS") else []) \
   + ([f"-DRODEO_STAGED_WARPS={os.environ['RODEO_STAGED_WARPS']}"] if os.environ.get("RODEO_STAGED_WARPS") else [])
 
 

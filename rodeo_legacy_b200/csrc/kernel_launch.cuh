@@ -145,7 +145,10 @@ cudaError_t launch_backward_pp(const HostPrior &h, const BatchedPrior &bp, const
 // backward launchers of one family for checkpoint interval CK (slot CKI of the table)
 template <class Fam, class Ode, bool BD, bool UNROLL, int CK, int CKI>
 void fill_backward(KernelSet &k) {
-  if constexpr (UNROLL && BD && Ode::n_meas >= 3) {
+#ifndef RODEO_BDW_MIN_BLOCKS
+#define RODEO_BDW_MIN_BLOCKS 3
+#endif
+  if constexpr (UNROLL && BD && Ode::n_meas >= RODEO_BDW_MIN_BLOCKS) {
     // block-diagonal with >= 3 blocks: one warp per diagonal block, CTA per tile (measured:
     // 2.1x on MSEIR, 1.9x on Lorenz63 over thread-per-system; 8 % slower at 2 blocks).
     // Full history only (checkpoint interval 1): see kalman_bdw.cuh.
