@@ -127,7 +127,9 @@ int rodeo_cuda_problem_destroy(rodeo_problem *p);
 /* Overwrite one of the prior / measurement arrays (host pointer, column-major). */
 int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *host_values);
 
-/* Which kernel family the handle currently uses (it is re-selected whenever a field is set). */
+/* Which kernel family the handle currently uses (it is re-selected whenever a field is set).
+ * *registers: 1 = thread-per-system register kernels, 2 = dense wide-state kernels (half a warp per
+ * system, n_state 7..16), 0 = rolled local-memory fallback. */
 int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t *registers,
                             int32_t *hist_doubles_per_step);
 

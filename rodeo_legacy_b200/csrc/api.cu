@@ -183,11 +183,17 @@ int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *v) {
   return rc;
 }
 
+// dense wide-state kernels (kalman_dw.cuh) serve the plain solves of the sets that carry them
+static bool wide_path(const rodeo_problem *p) {
+  return p->ks->wide_hist_elems > 0 && !p->shared && p->ig != RODEO_INTERROGATE_CHKREBTII &&
+         p->ks->wide_forward[p->ig] != nullptr;
+}
+
 int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t *registers,
                             int32_t *hist_doubles_per_step) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
   if (blockdiag) *blockdiag = p->ks->blockdiag;
-  if (registers) *registers = p->ks->registers;
+  if (registers) *registers = p->ks->registers ? 1 : (wide_path(p) ? 2 : 0);
   if (hist_doubles_per_step) *hist_doubles_per_step = p->ks->hist_elems;
   return RODEO_OK;
 }
@@ -206,7 +212,11 @@ static int effective_ck(const rodeo_problem *p) {
 size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
   if (!p) return 0;
   if (p->shared) return (size_t)p->N * p->n * sizeof(double);   // filtered means only
-  return (size_t)n_records(p->N, effective_ck(p)) * p->ks->hist_elems * sizeof(double);
+  const size_t thread = (size_t)n_records(p->N, effective_ck(p)) * p->ks->hist_elems * sizeof(double);
+  // the wide kernels keep (n + 1) rows of 16 lanes per step; the log-likelihood entry point of the same
+  // handle still runs the thread-per-system kernels, so size for the larger of the two
+  const size_t wide = wide_path(p) ? (size_t)p->N * p->ks->wide_hist_elems * sizeof(double) : 0;
+  return wide > thread ? wide : thread;
 }
 
 int rodeo_cuda_set_shared_cov(rodeo_problem *p, int enabled) {
@@ -329,6 +339,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   // per-system priors run on the dense family with the full history, never in shared-covariance mode
   const KernelSet *ks = bp ? find_kernel_set(p->ode, p->n, false) : p->ks;
   const bool shared = p->shared && !bp;
+  const bool wide = !bp && !ll && bk <= BK_BOTH && wide_path(p);
   const int ck = bp ? 1 : effective_ck(p), slot = ck_slot(ck);
   const size_t per_system = bp ? (size_t)p->N * ks->hist_elems * sizeof(double)
                                : rodeo_cuda_history_bytes_per_system(p);
@@ -388,9 +399,11 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
       if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
       CK(ks->pp_backward[bk](hp, c, a, stream));
     } else {
-      CK(shared ? ks->sc_forward(hp, a, stream) : ks->forward[p->ig](hp, a, stream));
+      CK(shared ? ks->sc_forward(hp, a, stream)
+                : wide ? ks->wide_forward[p->ig](hp, a, stream) : ks->forward[p->ig](hp, a, stream));
       if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
-      CK(shared ? ks->sc_backward[bk](hp, a, stream) : ks->backward[slot][bk](hp, a, stream));
+      CK(shared ? ks->sc_backward[bk](hp, a, stream)
+                : wide ? ks->wide_backward[bk](hp, a, stream) : ks->backward[slot][bk](hp, a, stream));
     }
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
     p->launches += 2;

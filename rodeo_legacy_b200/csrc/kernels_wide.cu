@@ -1,0 +1,29 @@
+// kernels_wide.cu -- dense wide-state kernels (half a warp per system, kalman_dw.cuh) attached to
+// the dense kernel sets whose state does not fit one thread's registers.
+#include "kernel_launch.cuh"
+#include "kalman_dw.cuh"
+namespace rodeo {
+
+template <class Ode, int n>
+static void attach(KernelSet *sets, int count) {
+  using Fam = DwFam<Ode, n>;
+  for (int i = 0; i < count; i++) {
+    KernelSet &k = sets[i];
+    if (k.ode != Ode::id || k.n != n || k.blockdiag) continue;
+    k.wide_forward[IG_PROBDE] = launch_dw_forward<Fam, IG_PROBDE>;
+    k.wide_forward[IG_SCHOBERT] = launch_dw_forward<Fam, IG_SCHOBERT>;
+    k.wide_backward[BK_MV] = launch_dw_backward<Fam, true, true, false>;
+    k.wide_backward[BK_SIM] = launch_dw_backward<Fam, false, false, true>;
+    k.wide_backward[BK_BOTH] = launch_dw_backward<Fam, true, true, true>;
+    k.wide_hist_elems = Fam::NE;
+  }
+}
+
+void attach_wide(KernelSet *sets, int count) {
+  attach<OdeFitz, 8>(sets, count);
+  attach<OdeLorenz63, 9>(sets, count);
+  attach<OdeMseir, 10>(sets, count);
+  attach<OdeMseir, 15>(sets, count);
+}
+
+}  // namespace rodeo

@@ -8,6 +8,8 @@ RODEO_REG(chkrebtii_dense) RODEO_REG(chkrebtii_bd) RODEO_REG(fitz_dense) RODEO_R
 RODEO_REG(lorenz_dense) RODEO_REG(lorenz_bd) RODEO_REG(mseir_dense) RODEO_REG(mseir_bd)
 #undef RODEO_REG
 
+void attach_wide(KernelSet *, int);   // kernels_wide.cu
+
 static KernelSet g_sets[64];
 static int g_count = -1;
 
@@ -22,6 +24,7 @@ static void init_sets() {
   register_lorenz_bd(g_sets, &c);
   register_mseir_dense(g_sets, &c);
   register_mseir_bd(g_sets, &c);
+  attach_wide(g_sets, c);
   g_count = c;
 }
 

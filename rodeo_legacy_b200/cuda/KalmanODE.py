@@ -207,7 +207,7 @@ class KalmanODE:
         ibm_init / car_init + indep_init + zero_pad produce); ``force_dense=True`` disables it."""
         bd, rg, _ = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _lib.check(self._lib.rodeo_cuda_problem_info(self._h, ctypes.byref(bd), ctypes.byref(rg), ctypes.byref(_)))
-        return ("blockdiag" if bd.value else "dense", "registers" if rg.value else "rolled")
+        return ("blockdiag" if bd.value else "dense", ("rolled", "registers", "wide")[rg.value])
 
     @property
     def shared_cov(self):

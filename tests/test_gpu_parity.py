@@ -198,28 +198,56 @@ def test_wide_state_configs_at_full_size(maker, B, mode):
         assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
 
 
-@pytest.mark.parametrize("maker,B,mode", [
-    (lambda B: wl.lorenz_batch(B, N=1000, tmax=4.0), 256, "sim"),
-    (lambda B: wl.mseir_batch(B, N=250), 256, "mv")])
-def test_wide_state_dense_fallback(maker, B, mode):
-    """The dense (rolled, local-memory) kernels for n_state 9 and 15: slower, any Q / R / W."""
+@pytest.mark.parametrize("maker,B,eps,reps", [
+    (lambda B: wl.lorenz_batch(B, N=1000, tmax=4.0), 255, 1e-6, 1e-7),   # chaotic: a larger R perturbation diverges
+    (lambda B: wl.mseir_batch(B, N=250), 256, 1e-3, 1e-3)])
+def test_wide_state_dense_family(maker, B, eps, reps):
+    """Dense kernels for n_state 9 and 15 (half a warp per system, kalman_dw.cuh): any Q / R / W.
+    All three entry points, an odd batch (half-filled last warp), and a genuinely dense prior."""
     w, x0, theta = maker(B)
     n = len(w["x0"])
-    z = np.asfortranarray(np.random.default_rng(8).standard_normal((n, w["N"])))
+    rng = np.random.default_rng(8)
+    z = np.asfortranarray(rng.standard_normal((n, w["N"])))
     k = wl.make_kode(w, z_state=z, force_dense=True)
-    assert k.kernel_family == ("dense", "rolled")
+    assert k.kernel_family == ("dense", "wide")
     x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
-    pick = [0, 100, 255]
+    pick = [0, 100, B - 1]
     po = wl.make_oracle_problem(w)
-    if mode == "sim":
-        x = k.solve_sim(x0d, theta=thd)
-        ref = oracle.solve_batch(po, x0[pick], theta[pick], z, oracle.MODE_SIM)
-        assert traj_err(x[pick].cpu().numpy(), ref["x"]).max() < 1e-8
-    else:
-        mu, var = k.solve_mv(x0d, theta=thd)
-        ref = oracle.solve_batch(po, x0[pick], theta[pick], None, oracle.MODE_MV)
-        assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
-        assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+    x = k.solve_sim(x0d, theta=thd)
+    mu, var = k.solve_mv(x0d, theta=thd)
+    x2, mu2, var2 = k.solve(x0d, theta=thd)
+    ref = oracle.solve_batch(po, x0[pick], theta[pick], z, oracle.MODE_BOTH)
+    assert traj_err(x[pick].cpu().numpy(), ref["x"]).max() < 1e-8
+    assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
+    assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+    assert torch.equal(x, x2) and torch.equal(mu, mu2) and torch.equal(var, var2)
+    assert bool((var[:, 0] == 0).all()) and torch.equal(mu[:, 0], x0d)
+    # a prior with no structure at all (dense Q, SPD R, W touching every state)
+    A = rng.standard_normal((n, n))
+    wd = dict(w)
+    wd["R"] = np.asfortranarray(w["R"] + reps * np.abs(w["R"]).max() * (A @ A.T) / n)
+    wd["Q"] = np.asfortranarray(w["Q"] + eps * rng.standard_normal((n, n)))
+    wd["W"] = np.asfortranarray(w["W"] + 10 * eps * rng.standard_normal(w["W"].shape))
+    wd["c"] = eps * rng.standard_normal(n)
+    kd = wl.make_kode(wd, z_state=z)
+    assert kd.kernel_family == ("dense", "wide")
+    xd, mud, vard = kd.solve(x0d[:64], theta=thd[:64])
+    refd = oracle.solve_batch(wl.make_oracle_problem(wd), x0[:64], theta[:64], z, oracle.MODE_BOTH)
+    assert np.isfinite(refd["mu"]).all() and np.isfinite(refd["x"]).all()
+    # the perturbed problem is worse conditioned; tolerances = 5x what two independent FP64 codes
+    # (oracle vs the thread-per-system kernels) differ by on it
+    assert traj_err(mud.cpu().numpy(), refd["mu"]).max() < 2e-9
+    assert np.abs(vard.cpu().numpy() - refd["var"]).max() < 1e-8 * np.abs(refd["var"]).max()
+    assert traj_err(xd.cpu().numpy(), refd["x"]).max() < 1e-7
+    np.testing.assert_array_equal(vard.cpu().numpy(), np.swapaxes(vard.cpu().numpy(), -1, -2))
+    # the log-likelihood entry point of the same handle (thread-per-system rolled kernels) agrees
+    ind = np.arange(10, w["N"] + 1, 10)
+    Y = mu[0, ind][:, :2].cpu().numpy() + 0.1
+    ll = k.loglik(x0d[:32], thd[:32], Y, ind, [0, 1], 0.3)
+    mu_c = mu[:32, ind][:, :, :2].cpu().numpy()
+    want = -0.5 * (((Y[None] - mu_c) / 0.3) ** 2).sum(axis=(1, 2))
+    got = ll.cpu().numpy()
+    assert np.abs(got - want - (got - want).mean()).max() < 1e-6 * max(1.0, np.abs(want).max())
 
 
 def test_dense_prior_uses_dense_family():
