@@ -38,7 +38,7 @@ struct DwFam {
   static constexpr int NE = ROWS * kDwLanes;          // history doubles per system per record
   static constexpr int LD = (n_ % 2) ? n_ : n_ + 1;   // odd leading dimension of the scratch matrices
   static constexpr int SCR = 3 * n_ * LD + n_ * n_;   // per system: XA, XB, XC (n x LD) + OUT (n*n)
-  static constexpr int CONST = n_ * n_ + Ode_::n_meas * n_;   // per CTA: R and W
+  static constexpr int CONST = 2 * n_ * n_ + Ode_::n_meas * n_ + n_;   // per CTA: R, W, Q, c
   using PriorT = Prior<n_, Ode_::n_meas>;
 };
 
@@ -49,16 +49,16 @@ __device__ __forceinline__ double dw_sum(double v) {
   return v;
 }
 
-// y[i] = c[i] + sum_k Q[i][k] x[k]   (replicated vectors, constant matrix)
+// Element j of c + Q x for a replicated vector x: row j of Q and c[j] are lane-indexed, so they come
+// from the shared copies (Qs row-major n x n, cs).  Computing the n elements on n lanes and
+// all-gathering them costs n FMA + 2n shuffles per lane instead of n*n replicated FMA.
 template <int n>
-__device__ __forceinline__ void dw_affine(const double *Q, const double *c, const double *x, double *y) {
+__device__ __forceinline__ double dw_affine_row(const double *Qs, const double *cs, const double *x, int j) {
+  if (j >= n) return 0.0;
+  double s = cs[j];
 #pragma unroll
-  for (int i = 0; i < n; i++) {
-    double s = c[i];
-#pragma unroll
-    for (int k = 0; k < n; k++) s += Q[i * n + k] * x[k];
-    y[i] = s;
-  }
+  for (int k = 0; k < n; k++) s += Qs[j * n + k] * x[k];
+  return s;
 }
 
 // out[:, j] = Q in[:, j]   (column owned by this lane)
@@ -157,6 +157,20 @@ __device__ __forceinline__ void dw_put(double *X, const double *col, int j, bool
   }
 }
 
+// CTA-shared copies of the lane-indexed prior constants: R (full, row-major), W, Q, c.
+template <class Fam>
+__device__ __forceinline__ void dw_load_consts(const typename Fam::PriorT &P, double *smem) {
+  constexpr int n = Fam::n, m = Fam::m;
+  double *Rs = smem, *Ws = Rs + n * n, *Qs = Ws + m * n, *cs = Qs + n * n;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    Rs[e] = P.R[sidx<n>(e / n, e % n)];
+    Qs[e] = P.Q[e];
+  }
+  for (int e = threadIdx.x; e < m * n; e += blockDim.x) Ws[e] = P.W[e];
+  for (int e = threadIdx.x; e < n; e += blockDim.x) cs[e] = P.c[e];
+  __syncthreads();
+}
+
 template <class Fam>
 __device__ __forceinline__ long dw_hist_offset(long b, int r, int R) {
   // [pair][record][row][32]: pair = b / 2, lane slot = (b % 2) * 16 + j
@@ -170,14 +184,12 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
   constexpr int n = Fam::n, m = Fam::m, LD = Fam::LD;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
   extern __shared__ __align__(16) double smem[];
-  double *Rs = smem, *Ws = smem + n * n;              // R (n*n) and W (m*n), shared by the CTA
+  const double *Rs = smem, *Ws = Rs + n * n, *Qs = Ws + m * n, *cs = Qs + n * n;
   const int tid = threadIdx.x, lane = tid % 32, j = lane % kDwLanes;
   const int sys_in_cta = tid / kDwLanes;
   double *X = smem + Fam::CONST + (size_t)sys_in_cta * Fam::SCR;   // this system's scratch
   double *XA = X, *XB = X + n * LD;                   // XB reused as the (m x n) image of A
-  for (int e = tid; e < n * n; e += blockDim.x) Rs[e] = P.R[sidx<n>(e / n, e % n)];
-  for (int e = tid; e < m * n; e += blockDim.x) Ws[e] = P.W[e];
-  __syncthreads();
+  dw_load_consts<Fam>(P, smem);
   const long b = (long)blockIdx.x * (kDwWarps * 2) + sys_in_cta;
   const bool valid = b < a.B, act = valid && j < n;
   const long bs = valid ? b : 0;
@@ -193,7 +205,9 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
   int fail = 0;
   for (int t = 0; t < N; t++) {
     double mup[n], T[n], Pc[n], y[m];
-    dw_affine<n>(P.Q, P.c, mu, mup);
+    const double mupj = dw_affine_row<n>(Qs, cs, mu, j);
+#pragma unroll
+    for (int i = 0; i < n; i++) mup[i] = dw_bcast(mupj, i);
     dw_qcol<n>(P.Q, Sf, T);
     dw_predict_cov<n, LD>(P.Q, Rs, T, XA, j, act, Pc);
     const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
@@ -229,9 +243,7 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
       Kc[q] = Ac[q];
     }
     reg::chol_solve_vec<m>(Sm, invd, Kc, 1);            // K~[:, j]
-    double mufj = 0.0;
-#pragma unroll
-    for (int i = 0; i < n; i++) mufj = (i == j) ? mup[i] : mufj;
+    double mufj = mupj;
 #pragma unroll
     for (int q = 0; q < m; q++) mufj += Kc[q] * e[q];
     // Sigma_f[:, j] = P[:, j] - A^T K~[:, j]: needs every column of A -> scratch (m x n image)
@@ -268,13 +280,13 @@ __global__ void __launch_bounds__(kDwWarps * 32)
 kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   constexpr int n = Fam::n, LD = Fam::LD;
   extern __shared__ __align__(16) double smem[];
-  double *Rs = smem;
+  constexpr int m = Fam::m;
+  const double *Rs = smem, *Qs = Rs + n * n + m * n, *cs = Qs + n * n;
   const int tid = threadIdx.x, lane = tid % 32, j = lane % kDwLanes;
   const int sys_in_cta = tid / kDwLanes;
   double *X = smem + Fam::CONST + (size_t)sys_in_cta * Fam::SCR;
   double *XA = X, *XB = X + n * LD, *XC = X + 2 * n * LD, *XO = X + 3 * n * LD;
-  for (int e = tid; e < n * n; e += blockDim.x) Rs[e] = P.R[sidx<n>(e / n, e % n)];
-  __syncthreads();
+  dw_load_consts<Fam>(P, smem);
   const long b = (long)blockIdx.x * (kDwWarps * 2) + sys_in_cta;
   const bool valid = b < a.B, act = valid && j < n;
   const long bs = valid ? b : 0;
@@ -284,7 +296,7 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
   double *mu_o = DO_MEAN ? a.mu_out + bs * T1 * n : nullptr;
   double *var_o = DO_VAR ? a.var_out + bs * T1 * n * n : nullptr;
   double *x_o = DO_SIM ? a.x_out + bs * T1 * n : nullptr;
-  double mus[n], xs[n], Ss[n];     // replicated smoothed mean / draw; column j of Sigma_s
+  double musj = 0.0, xsj = 0.0, Ss[n];   // element j of the smoothed mean / draw; column j of Sigma_s
   int fail = 0;
 
   // Writes time index t.  The covariance column is symmetrised on the way out (and in place, so the
@@ -319,7 +331,6 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
 #pragma unroll
     for (int i = 0; i < n; i++) Sf[i] = act ? h[i * 32] : ((i == j) ? 1.0 : 0.0);
     const double mufj = act ? h[n * 32] : 0.0;
-    double xj = 0.0;
     if (DO_SIM) {
       double V[n], invd[n];
 #pragma unroll
@@ -328,43 +339,41 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
       if (f && !fail) fail = f;
       // x = mu + L z: lane k contributes L[:, k] z[k]; row sums over the lanes
       const double zk = act ? zb[(long)(N - 1) * n + j] : 0.0;
+      double xj = 0.0;
 #pragma unroll
       for (int i = 0; i < n; i++) {
-        const double part = (act && i >= j) ? V[i] * zk : 0.0;
-        const double s = dw_sum(part);
-        xs[i] = s;
+        const double s = dw_sum((act && i >= j) ? V[i] * zk : 0.0);
+        xj = (i == j) ? s : xj;
       }
-#pragma unroll
-      for (int i = 0; i < n; i++) xs[i] += dw_bcast(mufj, i);
-#pragma unroll
-      for (int i = 0; i < n; i++) xj = (i == j) ? xs[i] : xj;
+      xsj = xj + mufj;
     }
+    musj = mufj;
 #pragma unroll
-    for (int i = 0; i < n; i++) {
-      mus[i] = dw_bcast(mufj, i);
-      Ss[i] = Sf[i];
-    }
-    emit(N, mufj, xj, Ss);
+    for (int i = 0; i < n; i++) Ss[i] = Sf[i];
+    emit(N, musj, xsj, Ss);
   }
   for (int t = N - 1; t >= 1; t--) {
     const double *h = a.hist + dw_hist_offset<Fam>(bs, N - t, N) + j;
-    double Sf[n], muf[n], mup[n], T[n], Pc[n], invd[n];
+    double Sf[n], T[n], Pc[n], invd[n];
 #pragma unroll
     for (int i = 0; i < n; i++) Sf[i] = act ? h[i * 32] : 0.0;
     const double mufj = act ? h[n * 32] : 0.0;
+    double mupj;
+    {
+      double muf[n];
 #pragma unroll
-    for (int i = 0; i < n; i++) muf[i] = dw_bcast(mufj, i);
-    dw_affine<n>(P.Q, P.c, muf, mup);
+      for (int i = 0; i < n; i++) muf[i] = dw_bcast(mufj, i);
+      mupj = dw_affine_row<n>(Qs, cs, muf, j);
+    }
     dw_qcol<n>(P.Q, Sf, T);                                   // T[:, j] = Q Sigma_f[:, j]
     dw_predict_cov<n, LD>(P.Q, Rs, T, XA, j, act, Pc);        // Sigma_p[:, j]
     if (!act) {                                               // identity column keeps the Cholesky finite
 #pragma unroll
       for (int i = 0; i < n; i++) Pc[i] = (i == j) ? 1.0 : 0.0;
     }
-    double D[n];
-    if (DO_VAR) {
+    if (DO_VAR && act) {   // D = Sigma_s+ - Sigma_p (symmetric) straight into its scratch matrix
 #pragma unroll
-      for (int i = 0; i < n; i++) D[i] = act ? Ss[i] - Pc[i] : 0.0;
+      for (int i = 0; i < n; i++) XC[i * LD + j] = Ss[i] - Pc[i];
     }
     int f = dw_chol<n>(Pc, invd, j);                           // Pc now holds L[:, j]
     if (f && !fail) fail = f;
@@ -380,23 +389,24 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
     for (int i = 0; i < n; i++) Tt[i] = T[i];
     dw_solve<n, LD>(XA, invd, Tt);                             // T~[:, j]
     __syncwarp();
-    double musj = 0.0, xj = 0.0;
+    // mu_s[j] = mu_f[j] + T~[:, j] . (mu_s+ - mu_p): the difference is formed per element and all-gathered
     if (DO_MEAN) {
+      const double dj = musj - mupj;
       double s = mufj;
 #pragma unroll
-      for (int k = 0; k < n; k++) s += Tt[k] * (mus[k] - mup[k]);
+      for (int k = 0; k < n; k++) s += Tt[k] * dw_bcast(dj, k);
       musj = s;
     }
     double mtj = 0.0;
     if (DO_SIM) {
+      const double dj = xsj - mupj;
       double s = mufj;
 #pragma unroll
-      for (int k = 0; k < n; k++) s += Tt[k] * (xs[k] - mup[k]);
+      for (int k = 0; k < n; k++) s += Tt[k] * dw_bcast(dj, k);
       mtj = s;
     }
     // T~ into XB (XB[k][i] = T~[k][i]) for the products with T~^T
     dw_put<n, LD>(XB, Tt, j, act);
-    if (DO_VAR) dw_put<n, LD>(XC, D, j, act);                  // D (symmetric) into XC
     __syncwarp();
     if (DO_SIM) {
       // V~[:, j] = Sigma_f[:, j] - T~^T T[:, j];  (T~^T T)[i][j] = sum_k T~[k][i] T[k][j]
@@ -411,16 +421,13 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
       int f2 = dw_chol<n>(V, vinv, j);
       if (f2 && !fail) fail = f2;
       const double zk = act ? zb[(long)(t - 1) * n + j] : 0.0;
-      double xnew[n];
+      double xj = 0.0;
 #pragma unroll
       for (int i = 0; i < n; i++) {
-        const double part = (act && i >= j) ? V[i] * zk : 0.0;
-        xnew[i] = dw_sum(part);
+        const double s = dw_sum((act && i >= j) ? V[i] * zk : 0.0);
+        xj = (i == j) ? s : xj;
       }
-#pragma unroll
-      for (int i = 0; i < n; i++) xs[i] = xnew[i] + dw_bcast(mtj, i);
-#pragma unroll
-      for (int i = 0; i < n; i++) xj = (i == j) ? xs[i] : xj;
+      xsj = xj + mtj;
     }
     if (DO_VAR) {
       // G[:, j] = D T~[:, j];  Sigma_s[:, j] = Sigma_f[:, j] + T~^T G[:, j]
@@ -432,20 +439,18 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
         for (int k = 0; k < n; k++) s += XC[i * LD + k] * Tt[k];
         G[i] = s;
       }
+      // Sigma_f is read again here (an L1 / L2 hit) rather than held in registers through the step
+      const volatile double *hv = h;
 #pragma unroll
       for (int i = 0; i < n; i++) {
-        double s = Sf[i];
+        double s = (DO_SIM || !act) ? Sf[i] : hv[i * 32];
 #pragma unroll
         for (int k = 0; k < n; k++) s += XB[k * LD + i] * G[k];
         Ss[i] = act ? s : 0.0;
       }
     }
     __syncwarp();
-    if (DO_MEAN) {
-#pragma unroll
-      for (int i = 0; i < n; i++) mus[i] = dw_bcast(musj, i);
-    }
-    emit(t, musj, xj, Ss);
+    emit(t, musj, xsj, Ss);
   }
   {  // time index 0: the initial state is known, Sigma_0 = 0
     double z0[n];

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--only", default="")
     ap.add_argument("--checkpoint", type=int, default=0)
+    ap.add_argument("--dense", action="store_true", help="force the general dense kernel families")
     a = ap.parse_args()
     rows = []
 
@@ -48,7 +49,7 @@ def main():
         if mode != "mv":
             np.random.seed(2)
             z = np.asfortranarray(np.random.randn(n, w["N"]))
-        k = wl.make_kode(w, z_state=z, checkpoint=a.checkpoint)
+        k = wl.make_kode(w, z_state=z, checkpoint=a.checkpoint, force_dense=a.dense)
         x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
         k.set_timing(True)
         if mode == "mv":
@@ -61,7 +62,7 @@ def main():
             fn = lambda: k.loglik(x0d, thd, Y, ind, [0, 3], 0.2)
         ms = timed(fn, a.reps)
         f, b = k.last_kernel_ms()
-        rows.append(dict(config=name, checkpoint=k.checkpoint, batch=B, n_state=n, n_eval=w["N"], mode=mode, ms=ms,
+        rows.append(dict(config=name, family="/".join(k.kernel_family), checkpoint=k.checkpoint, batch=B, n_state=n, n_eval=w["N"], mode=mode, ms=ms,
                          solves_per_s=B / ms * 1e3, forward_ms=f, backward_ms=b,
                          alg_GBps=n_alg_bytes_step * w["N"] * B / ms / 1e6,
                          launches=k.launch_count))
