@@ -213,8 +213,7 @@ size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
   if (!p) return 0;
   if (p->shared) return (size_t)p->N * p->n * sizeof(double);   // filtered means only
   const size_t thread = (size_t)n_records(p->N, effective_ck(p)) * p->ks->hist_elems * sizeof(double);
-  // the wide kernels keep (n + 1) rows of 16 lanes per step; the log-likelihood entry point of the same
-  // handle still runs the thread-per-system kernels, so size for the larger of the two
+  // the wide kernels keep (n + 1) rows of 16 lanes per step (padding lanes included)
   const size_t wide = wide_path(p) ? (size_t)p->N * p->ks->wide_hist_elems * sizeof(double) : 0;
   return wide > thread ? wide : thread;
 }
@@ -339,9 +338,10 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   // per-system priors run on the dense family with the full history, never in shared-covariance mode
   const KernelSet *ks = bp ? find_kernel_set(p->ode, p->n, false) : p->ks;
   const bool shared = p->shared && !bp;
-  const bool wide = !bp && !ll && bk <= BK_BOTH && wide_path(p);
+  const bool wide = !bp && wide_path(p) && p->ks->wide_backward[bk] != nullptr;
   const int ck = bp ? 1 : effective_ck(p), slot = ck_slot(ck);
-  const size_t per_system = bp ? (size_t)p->N * ks->hist_elems * sizeof(double)
+  const bool wide_pp = bp && ks->wide_pp_forward != nullptr;   // dense wide-state kernels, per-system priors
+  const size_t per_system = bp ? (size_t)p->N * (wide_pp ? ks->wide_hist_elems : ks->hist_elems) * sizeof(double)
                                : rodeo_cuda_history_bytes_per_system(p);
   long cap = (long)(p->ws_limit / per_system) / 1024 * 1024;
   if (cap < 1024) cap = 1024;
@@ -395,9 +395,9 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     if (bp) {
       BatchedPrior c{bp->W ? bp->W + off * p->m * n : nullptr, bp->Q ? bp->Q + off * n * n : nullptr,
                      bp->c ? bp->c + off * n : nullptr, bp->R ? bp->R + off * n * n : nullptr};
-      CK(ks->pp_forward(hp, c, a, stream));
+      CK(wide_pp ? ks->wide_pp_forward(hp, c, a, stream) : ks->pp_forward(hp, c, a, stream));
       if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
-      CK(ks->pp_backward[bk](hp, c, a, stream));
+      CK(wide_pp ? ks->wide_pp_backward[bk](hp, c, a, stream) : ks->pp_backward[bk](hp, c, a, stream));
     } else {
       CK(shared ? ks->sc_forward(hp, a, stream)
                 : wide ? ks->wide_forward[p->ig](hp, a, stream) : ks->forward[p->ig](hp, a, stream));

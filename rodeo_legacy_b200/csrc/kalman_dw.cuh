@@ -38,7 +38,7 @@ struct DwFam {
   static constexpr int NE = ROWS * kDwLanes;          // history doubles per system per record
   static constexpr int LD = (n_ % 2) ? n_ : n_ + 1;   // odd leading dimension of the scratch matrices
   static constexpr int SCR = 3 * n_ * LD + n_ * n_;   // per system: XA, XB, XC (n x LD) + OUT (n*n)
-  static constexpr int CONST = 2 * n_ * n_ + Ode_::n_meas * n_ + n_;   // per CTA: R, W, Q, c
+  static constexpr int CONST = 2 * n_ * n_ + Ode_::n_meas * n_ + n_;   // R, W, Q, c (per CTA, or per system)
   using PriorT = Prior<n_, Ode_::n_meas>;
 };
 
@@ -157,17 +157,26 @@ __device__ __forceinline__ void dw_put(double *X, const double *col, int j, bool
   }
 }
 
-// CTA-shared copies of the lane-indexed prior constants: R (full, row-major), W, Q, c.
-template <class Fam>
-__device__ __forceinline__ void dw_load_consts(const typename Fam::PriorT &P, double *smem) {
+// Shared copies of the lane-indexed prior constants: R (full, row-major), W, Q, c.  One copy per
+// CTA, or -- per-system priors (PP) -- one per system, filled by that system's 16 lanes from the
+// batched device arrays (column-major per system, nullptr = the handle's shared value).
+template <class Fam, bool PP>
+__device__ __forceinline__ void dw_load_consts(const typename Fam::PriorT &P, const BatchedPrior &bp, long b,
+                                               double *dst) {
   constexpr int n = Fam::n, m = Fam::m;
-  double *Rs = smem, *Ws = Rs + n * n, *Qs = Ws + m * n, *cs = Qs + n * n;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-    Rs[e] = P.R[sidx<n>(e / n, e % n)];
-    Qs[e] = P.Q[e];
+  double *Rs = dst, *Ws = Rs + n * n, *Qs = Ws + m * n, *cs = Qs + n * n;
+  const int first = PP ? (int)(threadIdx.x % kDwLanes) : (int)threadIdx.x;
+  const int step = PP ? kDwLanes : (int)blockDim.x;
+  for (int e = first; e < n * n; e += step) {
+    const int i = e / n, k = e % n;
+    Rs[e] = (PP && bp.R) ? bp.R[b * n * n + i + k * n] : P.R[sidx<n>(i, k)];
+    Qs[e] = (PP && bp.Q) ? bp.Q[b * n * n + i + k * n] : P.Q[e];
   }
-  for (int e = threadIdx.x; e < m * n; e += blockDim.x) Ws[e] = P.W[e];
-  for (int e = threadIdx.x; e < n; e += blockDim.x) cs[e] = P.c[e];
+  for (int e = first; e < m * n; e += step) {
+    const int q = e / n, k = e % n;
+    Ws[e] = (PP && bp.W) ? bp.W[b * m * n + q + k * m] : P.W[e];
+  }
+  for (int e = first; e < n; e += step) cs[e] = (PP && bp.c) ? bp.c[b * n + e] : P.c[e];
   __syncthreads();
 }
 
@@ -177,22 +186,25 @@ __device__ __forceinline__ long dw_hist_offset(long b, int r, int R) {
   return (((b >> 1) * R + r) * (long)Fam::ROWS) * 32 + (b & 1) * kDwLanes;
 }
 
-template <class Fam, int IG>
+template <class Fam, int IG, bool PP>
 __global__ void __launch_bounds__(kDwWarps * 32)
-kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
+                  const __grid_constant__ SolveArgs a) {
   using Ode = typename Fam::Ode;
   constexpr int n = Fam::n, m = Fam::m, LD = Fam::LD;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
   extern __shared__ __align__(16) double smem[];
-  const double *Rs = smem, *Ws = Rs + n * n, *Qs = Ws + m * n, *cs = Qs + n * n;
   const int tid = threadIdx.x, lane = tid % 32, j = lane % kDwLanes;
   const int sys_in_cta = tid / kDwLanes;
-  double *X = smem + Fam::CONST + (size_t)sys_in_cta * Fam::SCR;   // this system's scratch
-  double *XA = X, *XB = X + n * LD;                   // XB reused as the (m x n) image of A
-  dw_load_consts<Fam>(P, smem);
   const long b = (long)blockIdx.x * (kDwWarps * 2) + sys_in_cta;
   const bool valid = b < a.B, act = valid && j < n;
   const long bs = valid ? b : 0;
+  double *cst = PP ? smem + (size_t)sys_in_cta * (Fam::SCR + Fam::CONST) : smem;
+  double *X = PP ? cst + Fam::CONST : smem + Fam::CONST + (size_t)sys_in_cta * Fam::SCR;   // this system's scratch
+  double *XA = X, *XB = X + n * LD;                   // XB reused as the (m x n) image of A
+  dw_load_consts<Fam, PP>(P, bp, bs, cst);
+  const double *Rs = cst, *Ws = Rs + n * n, *Qs = Ws + m * n, *cs = Qs + n * n;
+  const double *Qu = PP ? Qs : P.Q, *Wu = PP ? Ws : P.W;   // operands every lane reads at the same index
   double mu[n], Sf[n], th[NT];
 #pragma unroll
   for (int i = 0; i < n; i++) {
@@ -208,8 +220,8 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
     const double mupj = dw_affine_row<n>(Qs, cs, mu, j);
 #pragma unroll
     for (int i = 0; i < n; i++) mup[i] = dw_bcast(mupj, i);
-    dw_qcol<n>(P.Q, Sf, T);
-    dw_predict_cov<n, LD>(P.Q, Rs, T, XA, j, act, Pc);
+    dw_qcol<n>(Qu, Sf, T);
+    dw_predict_cov<n, LD>(Qu, Rs, T, XA, j, act, Pc);
     const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
     Ode::template eval<n>(mup, tt, th, y);
     // A[:, j] = W P[:, j]
@@ -218,7 +230,7 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
     for (int q = 0; q < m; q++) {
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < n; k++) s += P.W[q * n + k] * Pc[k];
+      for (int k = 0; k < n; k++) s += Wu[q * n + k] * Pc[k];
       Ac[q] = act ? s : 0.0;
     }
     // S = A W^T (+ H = A W^T under probde), reduced over the lanes
@@ -238,7 +250,7 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
     for (int q = 0; q < m; q++) {
       double s = 0.0;
 #pragma unroll
-      for (int k = 0; k < n; k++) s += P.W[q * n + k] * mup[k];
+      for (int k = 0; k < n; k++) s += Wu[q * n + k] * mup[k];
       e[q] = y[q] - s;
       Kc[q] = Ac[q];
     }
@@ -274,28 +286,35 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
   if (valid && j == 0 && a.status) a.status[b] = fail;
 }
 
-// Backward pass (smooth_mv / smooth_sim / both).
-template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+// Backward pass (smooth_mv / smooth_sim / both); with LOGLIK no per-step output is written: the thinned
+// Gaussian log-likelihood of the mean (DO_MEAN) or the draw (DO_SIM) is accumulated instead, each lane
+// handling the observed components it owns (examples/inference.py:54-56, 66-83).
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK, bool PP>
 __global__ void __launch_bounds__(kDwWarps * 32)
-kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
+                   const __grid_constant__ SolveArgs a) {
   constexpr int n = Fam::n, LD = Fam::LD;
   extern __shared__ __align__(16) double smem[];
   constexpr int m = Fam::m;
-  const double *Rs = smem, *Qs = Rs + n * n + m * n, *cs = Qs + n * n;
   const int tid = threadIdx.x, lane = tid % 32, j = lane % kDwLanes;
   const int sys_in_cta = tid / kDwLanes;
-  double *X = smem + Fam::CONST + (size_t)sys_in_cta * Fam::SCR;
-  double *XA = X, *XB = X + n * LD, *XC = X + 2 * n * LD, *XO = X + 3 * n * LD;
-  dw_load_consts<Fam>(P, smem);
   const long b = (long)blockIdx.x * (kDwWarps * 2) + sys_in_cta;
   const bool valid = b < a.B, act = valid && j < n;
   const long bs = valid ? b : 0;
+  double *cst = PP ? smem + (size_t)sys_in_cta * (Fam::SCR + Fam::CONST) : smem;
+  double *X = PP ? cst + Fam::CONST : smem + Fam::CONST + (size_t)sys_in_cta * Fam::SCR;
+  double *XA = X, *XB = X + n * LD, *XC = X + 2 * n * LD, *XO = X + 3 * n * LD;
+  dw_load_consts<Fam, PP>(P, bp, bs, cst);
+  const double *Rs = cst, *Qs = Rs + n * n + m * n, *cs = Qs + n * n;
+  const double *Qu = PP ? Qs : P.Q;
   const int N = P.n_eval;
   const long T1 = (long)N + 1;
   const double *zb = DO_SIM ? a.z + bs * a.z_stride : nullptr;
-  double *mu_o = DO_MEAN ? a.mu_out + bs * T1 * n : nullptr;
-  double *var_o = DO_VAR ? a.var_out + bs * T1 * n * n : nullptr;
-  double *x_o = DO_SIM ? a.x_out + bs * T1 * n : nullptr;
+  double *mu_o = (DO_MEAN && !LOGLIK) ? a.mu_out + bs * T1 * n : nullptr;
+  double *var_o = (DO_VAR && !LOGLIK) ? a.var_out + bs * T1 * n * n : nullptr;
+  double *x_o = (DO_SIM && !LOGLIK) ? a.x_out + bs * T1 * n : nullptr;
+  double lpj = 0.0;                      // this lane's share of the log-likelihood
+  int d = LOGLIK ? a.n_obs_times - 1 : -1;
   double musj = 0.0, xsj = 0.0, Ss[n];   // element j of the smoothed mean / draw; column j of Sigma_s
   int fail = 0;
 
@@ -303,6 +322,18 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
   // recursion carries the same bits it reported): column-wise arithmetic leaves Sigma(i, j) and
   // Sigma(j, i) a rounding apart, and every other kernel family returns exactly symmetric matrices.
   auto emit = [&](int t, double musj, double xsj, double *Scol) {
+    if (LOGLIK) {
+      while (d >= 0 && a.thin_index[d] == t) {
+        for (int k = 0; k < a.n_obs_comp; k++) {
+          if (a.state_index[k] == j) {
+            const double r = (a.Y[d * a.n_obs_comp + k] - (DO_SIM ? xsj : musj)) / a.gamma;
+            lpj -= 0.5 * r * r;
+          }
+        }
+        d--;
+      }
+      return;
+    }
     if (DO_MEAN && act) mu_o[(long)t * n + j] = musj;
     if (DO_SIM && act) x_o[(long)t * n + j] = xsj;
     if (DO_VAR) {
@@ -365,8 +396,8 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
       for (int i = 0; i < n; i++) muf[i] = dw_bcast(mufj, i);
       mupj = dw_affine_row<n>(Qs, cs, muf, j);
     }
-    dw_qcol<n>(P.Q, Sf, T);                                   // T[:, j] = Q Sigma_f[:, j]
-    dw_predict_cov<n, LD>(P.Q, Rs, T, XA, j, act, Pc);        // Sigma_p[:, j]
+    dw_qcol<n>(Qu, Sf, T);                                   // T[:, j] = Q Sigma_f[:, j]
+    dw_predict_cov<n, LD>(Qu, Rs, T, XA, j, act, Pc);        // Sigma_p[:, j]
     if (!act) {                                               // identity column keeps the Cholesky finite
 #pragma unroll
       for (int i = 0; i < n; i++) Pc[i] = (i == j) ? 1.0 : 0.0;
@@ -459,38 +490,50 @@ kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
     const double v = act ? a.x0[bs * n + j] : 0.0;
     emit(0, v, v, z0);
   }
+  if (LOGLIK) {
+    const double lp = dw_sum(act ? lpj : 0.0);
+    const double cst = -0.91893853320467274178 - log(a.gamma);
+    if (valid && j == 0) a.loglik[b] = lp + cst * (double)(a.n_obs_times * a.n_obs_comp);
+  }
   if (valid && j == 0 && a.status && fail && a.status[b] == 0) a.status[b] = fail;
 }
 
-template <class Fam>
+template <class Fam, bool PP>
 inline size_t dw_smem_bytes() {
-  return ((size_t)Fam::CONST + (size_t)kDwWarps * 2 * Fam::SCR) * sizeof(double);
+  const size_t consts = PP ? (size_t)kDwWarps * 2 * Fam::CONST : (size_t)Fam::CONST;
+  return (consts + (size_t)kDwWarps * 2 * Fam::SCR) * sizeof(double);
+}
+
+template <class Fam, class Kern>
+inline cudaError_t dw_launch(Kern kern, size_t smem, const HostPrior &h, const BatchedPrior &bp, const SolveArgs &a,
+                             cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  typename Fam::PriorT P;
+  fill_prior(P, h);
+  const unsigned grid = (unsigned)((a.B + kDwWarps * 2 - 1) / (kDwWarps * 2));
+  kern<<<grid, kDwWarps * 32, smem, s>>>(P, bp, a);
+  return cudaGetLastError();
 }
 
 template <class Fam, int IG>
 cudaError_t launch_dw_forward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  auto kern = kalman_dw_forward<Fam, IG>;
-  const size_t smem = dw_smem_bytes<Fam>();
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  typename Fam::PriorT P;
-  fill_prior(P, h);
-  const unsigned grid = (unsigned)((a.B + kDwWarps * 2 - 1) / (kDwWarps * 2));
-  kern<<<grid, kDwWarps * 32, smem, s>>>(P, a);
-  return cudaGetLastError();
+  return dw_launch<Fam>(kalman_dw_forward<Fam, IG, false>, dw_smem_bytes<Fam, false>(), h, BatchedPrior{}, a, s);
 }
-
-template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
 cudaError_t launch_dw_backward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  auto kern = kalman_dw_backward<Fam, DO_MEAN, DO_VAR, DO_SIM>;
-  const size_t smem = dw_smem_bytes<Fam>();
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  typename Fam::PriorT P;
-  fill_prior(P, h);
-  const unsigned grid = (unsigned)((a.B + kDwWarps * 2 - 1) / (kDwWarps * 2));
-  kern<<<grid, kDwWarps * 32, smem, s>>>(P, a);
-  return cudaGetLastError();
+  return dw_launch<Fam>(kalman_dw_backward<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK, false>, dw_smem_bytes<Fam, false>(), h,
+                        BatchedPrior{}, a, s);
+}
+// per-system priors (probde interrogation)
+template <class Fam>
+cudaError_t launch_dw_forward_pp(const HostPrior &h, const BatchedPrior &bp, const SolveArgs &a, cudaStream_t s) {
+  return dw_launch<Fam>(kalman_dw_forward<Fam, IG_PROBDE, true>, dw_smem_bytes<Fam, true>(), h, bp, a, s);
+}
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+cudaError_t launch_dw_backward_pp(const HostPrior &h, const BatchedPrior &bp, const SolveArgs &a, cudaStream_t s) {
+  return dw_launch<Fam>(kalman_dw_backward<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK, true>, dw_smem_bytes<Fam, true>(), h, bp,
+                        a, s);
 }
 
 }  // namespace rodeo

@@ -202,7 +202,9 @@ KernelSet make_kernel_set(const char *name) {
   k.pp_forward = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.pp_backward[b] = nullptr;
   k.wide_forward[0] = k.wide_forward[1] = nullptr;
-  k.wide_backward[0] = k.wide_backward[1] = k.wide_backward[2] = nullptr;
+  for (int b = 0; b < BK_COUNT; b++) k.wide_backward[b] = nullptr;
+  k.wide_pp_forward = nullptr;
+  for (int b = 0; b < BK_COUNT; b++) k.wide_pp_backward[b] = nullptr;
   k.wide_hist_elems = 0;
   if constexpr (!BD) {  // per-system priors: dense family only (a batched prior need not be structured)
     k.pp_forward = launch_forward_pp<Fam, UNROLL, IG_PROBDE>;

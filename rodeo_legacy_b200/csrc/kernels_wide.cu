@@ -12,9 +12,17 @@ static void attach(KernelSet *sets, int count) {
     if (k.ode != Ode::id || k.n != n || k.blockdiag) continue;
     k.wide_forward[IG_PROBDE] = launch_dw_forward<Fam, IG_PROBDE>;
     k.wide_forward[IG_SCHOBERT] = launch_dw_forward<Fam, IG_SCHOBERT>;
-    k.wide_backward[BK_MV] = launch_dw_backward<Fam, true, true, false>;
-    k.wide_backward[BK_SIM] = launch_dw_backward<Fam, false, false, true>;
-    k.wide_backward[BK_BOTH] = launch_dw_backward<Fam, true, true, true>;
+    k.wide_backward[BK_MV] = launch_dw_backward<Fam, true, true, false, false>;
+    k.wide_backward[BK_SIM] = launch_dw_backward<Fam, false, false, true, false>;
+    k.wide_backward[BK_BOTH] = launch_dw_backward<Fam, true, true, true, false>;
+    k.wide_backward[BK_LL_MEAN] = launch_dw_backward<Fam, true, false, false, true>;
+    k.wide_backward[BK_LL_DRAW] = launch_dw_backward<Fam, false, false, true, true>;
+    k.wide_pp_forward = launch_dw_forward_pp<Fam>;
+    k.wide_pp_backward[BK_MV] = launch_dw_backward_pp<Fam, true, true, false, false>;
+    k.wide_pp_backward[BK_SIM] = launch_dw_backward_pp<Fam, false, false, true, false>;
+    k.wide_pp_backward[BK_BOTH] = launch_dw_backward_pp<Fam, true, true, true, false>;
+    k.wide_pp_backward[BK_LL_MEAN] = launch_dw_backward_pp<Fam, true, false, false, true>;
+    k.wide_pp_backward[BK_LL_DRAW] = launch_dw_backward_pp<Fam, false, false, true, true>;
     k.wide_hist_elems = Fam::NE;
   }
 }

@@ -44,10 +44,12 @@ struct KernelSet {
   launch_pp_fn pp_forward;
   launch_pp_fn pp_backward[BK_COUNT];
   // dense wide-state kernels (kalman_dw.cuh: half a warp per system); nullptr / 0 when not compiled.
-  // Used for solve / solve_sim / solve_mv under the probde and schobert interrogations; they keep
+  // Used for every entry point under the probde and schobert interrogations; they keep
   // their own history layout (wide_hist_elems doubles per system per step, full history).
   launch_fn wide_forward[2];
-  launch_fn wide_backward[3];
+  launch_fn wide_backward[BK_COUNT];
+  launch_pp_fn wide_pp_forward;
+  launch_pp_fn wide_pp_backward[BK_COUNT];
   int wide_hist_elems;
 };
 

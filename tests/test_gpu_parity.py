@@ -240,14 +240,30 @@ def test_wide_state_dense_family(maker, B, eps, reps):
     assert np.abs(vard.cpu().numpy() - refd["var"]).max() < 1e-8 * np.abs(refd["var"]).max()
     assert traj_err(xd.cpu().numpy(), refd["x"]).max() < 1e-7
     np.testing.assert_array_equal(vard.cpu().numpy(), np.swapaxes(vard.cpu().numpy(), -1, -2))
-    # the log-likelihood entry point of the same handle (thread-per-system rolled kernels) agrees
+    # per-system priors on the same family: each of 20 systems its own (dense) Q, R, W, c
+    nb = 20
+    m_ = w["W"].shape[0]
+    Qb = np.stack([np.asarray(w["Q"]) + 0.1 * eps * rng.standard_normal((n, n)) for _ in range(nb)])
+    Rb = np.stack([np.asarray(w["R"]) * (1 + 0.02 * i) + 0.1 * reps * np.abs(w["R"]).max() * (A @ A.T) / n for i in range(nb)])
+    Wb = np.stack([np.asarray(w["W"]) + eps * rng.standard_normal((m_, n)) for _ in range(nb)])
+    cb = 0.1 * eps * rng.standard_normal((nb, n))
+    xp, mup_, varp = k.solve(x0d[:nb], theta=thd[:nb], priors=dict(wgt_state=Qb, var_state=Rb, wgt_meas=Wb, mu_state=cb))
+    for b in (0, 7, nb - 1):
+        po_b = oracle.Problem(w["ode"], Wb[b], w["tmin"], w["tmax"], w["N"], Qb[b], cb[b], Rb[b])
+        rb = oracle.solve(po_b, x0[b], theta[b], z, oracle.MODE_BOTH)
+        assert traj_err(mup_[b].cpu().numpy(), rb["mu"]).max() < 2e-9
+        assert np.abs(varp[b].cpu().numpy() - rb["var"]).max() < 1e-8 * np.abs(rb["var"]).max()
+        assert traj_err(xp[b].cpu().numpy(), rb["x"]).max() < 1e-7
+    # fused log-likelihood epilogue of the same family: equals the density of the returned mean / draw
     ind = np.arange(10, w["N"] + 1, 10)
-    Y = mu[0, ind][:, :2].cpu().numpy() + 0.1
-    ll = k.loglik(x0d[:32], thd[:32], Y, ind, [0, 1], 0.3)
-    mu_c = mu[:32, ind][:, :, :2].cpu().numpy()
-    want = -0.5 * (((Y[None] - mu_c) / 0.3) ** 2).sum(axis=(1, 2))
-    got = ll.cpu().numpy()
-    assert np.abs(got - want - (got - want).mean()).max() < 1e-6 * max(1.0, np.abs(want).max())
+    comp = [0, n - 1, 0]                     # a repeated component is legal
+    Y = mu[0, ind][:, comp].cpu().numpy() + 0.1
+    cst = -Y.size * (np.log(0.3) + 0.5 * np.log(2 * np.pi))
+    for draw, traj in ((False, mu), (True, x)):
+        got = k.loglik(x0d, thd, Y, ind, comp, 0.3, use_draw=draw).cpu().numpy()
+        tc = traj[:, ind][:, :, comp].cpu().numpy()
+        want = cst - 0.5 * (((Y[None] - tc) / 0.3) ** 2).sum(axis=(1, 2))
+        assert got.shape == (B,) and np.abs(got - want).max() < 1e-9 * np.abs(want).max()
 
 
 def test_dense_prior_uses_dense_family():
