@@ -74,5 +74,22 @@ def build(force=False, verbose=False, ptxas_info=False):
     return LIB
 
 
+def build_microbench():
+    """tools/microbench/write_pattern: no-compute kernel writing the smoother's output pattern (what the
+    memory system sustains for 288-byte runs of 65,536 interleaved streams); bench.py reports it next to the
+    kernel's own DRAM rate.  Returns the binary's path."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tools", "microbench", "write_pattern.cu")
+    out = src[:-3]
+    if _stale(out, [src]):
+        cmd = [nvcc(), "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-cudart", "static", "-o", out, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("write_pattern microbenchmark failed to build")
+    return out
+
+
 if __name__ == "__main__":
+    build_microbench()
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, ptxas_info="--ptxas" in sys.argv))

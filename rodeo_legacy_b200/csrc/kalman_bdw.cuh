@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::THREA
 kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   using L = BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
   constexpr int p = L::p, n = L::n, PS = L::PS, REC = L::REC, TW = L::TW, NT = L::THREADS;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double *ring = smem;
   double *tiles = ring + 2 * REC;
   uint64_t *bar = reinterpret_cast<uint64_t *>(tiles + 2 * kTile * TW);

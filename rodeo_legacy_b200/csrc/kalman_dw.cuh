@@ -193,7 +193,7 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
   using Ode = typename Fam::Ode;
   constexpr int n = Fam::n, m = Fam::m, LD = Fam::LD;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, lane = tid % 32, j = lane % kDwLanes;
   const int sys_in_cta = tid / kDwLanes;
   const long b = (long)blockIdx.x * (kDwWarps * 2) + sys_in_cta;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kDwWarps * 32)
 kalman_dw_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
                    const __grid_constant__ SolveArgs a) {
   constexpr int n = Fam::n, LD = Fam::LD;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   constexpr int m = Fam::m;
   const int tid = threadIdx.x, lane = tid % 32, j = lane % kDwLanes;
   const int sys_in_cta = tid / kDwLanes;

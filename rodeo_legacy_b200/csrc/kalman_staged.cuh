@@ -17,12 +17,72 @@
 //     which the smoother then consumes exactly like loaded records.
 // Warps never synchronise with each other (no __syncthreads after the prologue).
 #pragma once
+#include <cuda.h>   // CUtensorMap and its enums only: the encoder is fetched through the runtime, no libcuda link
 #include <cstdint>
+#include <cstring>
+#include <type_traits>
 
 #include "kalman_tps.cuh"
 #include "registry.cuh"
 
 namespace rodeo {
+
+// ---- TMA tensor stores for the outputs (n_state = 6) ---------------------------------------------
+// out[b][t][0..W) viewed as a 3-D tensor {W, T1, B}; one box {W, 1, 32} = the W-double runs of the 32
+// systems of a tile at one time index, i.e. exactly what a warp emits per step.  The staging tile in
+// shared memory is the box image ([32][W] doubles, dense), so ONE cp.async.bulk.tensor per array and
+// step replaces the tile -> register -> global flush (36 LDS.128 + 36 STG.128 per warp-step for FN
+// solve_mv) and the hardware clips the systems beyond B.  Needs 16-byte multiples everywhere:
+// W * 8 % 16 == 0, i.e. even n_state.
+struct StoreMaps {
+  alignas(64) CUtensorMap mu, var, x;
+};
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline encode_tiled_fn tensor_map_encoder() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+// Tensor map of one output array: W doubles per (system, time index).
+inline cudaError_t encode_out_map(CUtensorMap *m, double *base, int W, long T1, long B) {
+  if (!base) {
+    memset(m, 0, sizeof *m);
+    return cudaSuccess;
+  }
+  encode_tiled_fn enc = tensor_map_encoder();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)T1, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * 8 * (cuuint64_t)T1};
+  const cuuint32_t box[3] = {(cuuint32_t)W, 1, (cuuint32_t)kTile};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// shared -> global tensor store of one box (bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(static_cast<uint32_t>(__cvta_generic_to_shared(src_smem))), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed store has finished READING shared memory (the tile may be overwritten)
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// every committed store is complete
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -92,7 +152,12 @@ struct StagedLayout {
   static constexpr int ROW = ((W0 > W1 ? W0 : W1) + 1) / 2 * 2;                  // row stride (even)
   // per warp: 2 ring slots (checkpoint records, TMA), CK-1 scratch records (re-run filter),
   // the output staging tile, 2 mbarriers
-  static constexpr int WARP_DOUBLES = (2 + (CK - 1)) * REC + kTile * ROW + 2;
+  // outputs leave through TMA tensor stores (dense per-array tiles) when every run is a 16-byte multiple and
+  // the dense rows cost at most a 2-way bank conflict on the 16-byte row writes: n_state = 6
+  static constexpr bool kTma = (n == 6) && !TWO_PASS;
+  // per-warp region kept a multiple of 128 bytes (TMA source alignment)
+  static constexpr int STAGE = kTma ? kTile * (VEC_W + (DO_VAR ? n * n : 0)) : kTile * ROW;   // staging tile(s)
+  static constexpr int WARP_DOUBLES = ((2 + (CK - 1)) * REC + STAGE + 2 + 15) / 16 * 16;
   static constexpr size_t smem_bytes = (size_t)kStagedWarps * WARP_DOUBLES * sizeof(double);
   // No min-blocks launch bound: with a one-pass tile shared memory limits the kernel to 4 CTAs per
   // SM anyway, and a register cap below what ptxas wants only adds spills (tried 168 / 128:
@@ -284,14 +349,70 @@ struct StagedEmitter {
   }
 };
 
+// Emission through TMA tensor stores: per-array dense tiles [32][W] (mean, draw, variance, each starting
+// on a 128-byte boundary); every lane writes its rows with 16-byte shared stores, lane 0 issues one tensor
+// store per array.  The previous step's stores must have finished reading the tiles before they are
+// overwritten (wait_group.read).  Measured alternatives (FN solve_mv backward kernel, 2.35 ms with the LSU
+// flush): all arrays through the TMA 2.25 ms; variance through the TMA and the 48-byte mean runs through the
+// LSU flush 2.26 ms; mean runs paired into sector-aligned 96-byte pieces (registers hold the previous step)
+// 2.32 ms.  At 2.25 ms the kernel moves its 10.7 GB at 4.77 TB/s, which is what a no-compute kernel
+// writing the same 288-byte-run pattern reaches (tools/microbench/write_pattern.cu: 4.74 TB/s).
+template <class Fam, class L, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+struct TmaEmitter {
+  static constexpr int n = Fam::n;
+  static constexpr int OFF_MU = 0, OFF_X = OFF_MU + (DO_MEAN ? kTile * n : 0), OFF_VAR = OFF_X + (DO_SIM ? kTile * n : 0);
+  static_assert((kTile * n) % 16 == 0, "tiles must start on 128-byte boundaries");
+  double *stage;
+  const StoreMaps *maps;
+  int b0, lane;
+  __device__ __forceinline__ void init(double *stage_, const StoreMaps *maps_, long b0_, int lane_) {
+    stage = stage_;
+    maps = maps_;
+    b0 = (int)b0_;
+    lane = lane_;
+  }
+  template <int W>
+  __device__ __forceinline__ void put(double *tile, const double *v) const {
+    double2 *row = reinterpret_cast<double2 *>(tile + lane * W);
+#pragma unroll
+    for (int i = 0; i < W / 2; i++) row[i] = make_double2(v[2 * i], v[2 * i + 1]);
+  }
+  __device__ __forceinline__ void emit(const SolveArgs &, int t, const double *mus, const double *Ss,
+                                       const double *x) const {
+    if (lane == 0) tma_wait_read();
+    __syncwarp();
+    if (DO_MEAN) put<n>(stage + OFF_MU, mus);
+    if (DO_SIM) put<n>(stage + OFF_X, x);
+    if (DO_VAR) {
+      double2 *row = reinterpret_cast<double2 *>(stage + OFF_VAR + lane * n * n);
+#pragma unroll
+      for (int i = 0; i < n * n / 2; i++)
+        row[i] = make_double2(Fam::var_at(Ss, (2 * i) % n, (2 * i) / n), Fam::var_at(Ss, (2 * i + 1) % n, (2 * i + 1) / n));
+    }
+    fence_proxy_async();   // the rows (generic proxy) become visible to the TMA (async proxy) ...
+    __syncwarp();          // ... of every lane, before lane 0 issues the stores
+    if (lane == 0) {
+      if (DO_MEAN) tma_store_3d(&maps->mu, stage + OFF_MU, 0, t, b0);
+      if (DO_SIM) tma_store_3d(&maps->x, stage + OFF_X, 0, t, b0);
+      if (DO_VAR) tma_store_3d(&maps->var, stage + OFF_VAR, 0, t, b0);
+      tma_commit();
+    }
+  }
+  __device__ __forceinline__ void finish() const {
+    if (lane == 0) tma_wait_all();
+    __syncwarp();
+  }
+};
+
 template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 __global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::MINB)
-kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
+                       const __grid_constant__ StoreMaps maps) {
   using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
   using Ode = typename Fam::Ode;
   constexpr int n = Fam::n, NS = Fam::NS, NE = Fam::NE, REC = L::REC;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long tile = (long)blockIdx.x * kStagedWarps + warp;
   const long n_tiles = (a.B + kTile - 1) / kTile;
@@ -299,7 +420,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
   double *ring = smem + (size_t)warp * L::WARP_DOUBLES;
   double *scratch = ring + 2 * REC;
   double *stage = scratch + (CK - 1) * REC;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(stage + kTile * L::ROW);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(stage + L::STAGE);
   const int N = P.n_eval, R = n_records(N, CK);
   const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
   const bool valid = b < a.B;
@@ -332,8 +453,10 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
 #pragma unroll
     for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[bs * Ode::n_theta + i] : 0.0;
   }
-  StagedEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM> em;
-  em.init(stage, a, b0, T1, lane);
+  typename std::conditional<L::kTma, TmaEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM>,
+                            StagedEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM>>::type em;
+  if constexpr (L::kTma) em.init(stage, &maps, b0, lane);
+  else em.init(stage, a, b0, T1, lane);
   uint32_t phase = 0;
   // wait for record r (ring slot r & 1); returns this lane's column of it
   auto acquire = [&](int r) -> const double * {
@@ -438,6 +561,7 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
     for (int i = 0; i < NS; i++) Ss[i] = 0.0;
     em.emit(a, 0, mus, Ss, x);
   }
+  if constexpr (L::kTma) em.finish();
   if (valid && a.status && fail && a.status[b] == 0) a.status[b] = fail;
 }
 
@@ -449,7 +573,15 @@ cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaS
   if (e != cudaSuccess) return e;
   const long n_tiles = (a.B + kTile - 1) / kTile;
   const unsigned grid = (unsigned)((n_tiles + kStagedWarps - 1) / kStagedWarps);
-  kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(make_prior<Fam>(h), a);
+  StoreMaps maps;
+  memset(&maps, 0, sizeof maps);
+  if (L::kTma) {
+    constexpr int n = Fam::n;
+    if (DO_MEAN && (e = encode_out_map(&maps.mu, a.mu_out, n, a.n_steps, a.B)) != cudaSuccess) return e;
+    if (DO_SIM && (e = encode_out_map(&maps.x, a.x_out, n, a.n_steps, a.B)) != cudaSuccess) return e;
+    if (DO_VAR && (e = encode_out_map(&maps.var, a.var_out, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
+  }
+  kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(make_prior<Fam>(h), a, maps);
   return cudaGetLastError();
 }
 
