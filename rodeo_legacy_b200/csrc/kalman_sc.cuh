@@ -37,23 +37,28 @@ kalman_sc_loglik(const __grid_constant__ typename Fam::PriorT P, const __grid_co
 }
 
 constexpr int kScWarps = 4;
+constexpr int kScBlock = 4;   // time indices per stored piece (BlockedRuns)
 
 template <class Fam, bool DO_MEAN, bool DO_SIM>
 __global__ void __launch_bounds__(kScWarps * 32)
 kalman_sc_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   constexpr int n = Fam::n;
-  constexpr int OUTW = n * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0)), ROW = (OUTW + 1) / 2 * 2;
-  __shared__ __align__(16) double smem[kScWarps * kTile * ROW];
+  using Runs = BlockedRuns<n, kScBlock, 32>;
+  constexpr int NARR = (DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0);
+  extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long tile = (long)blockIdx.x * kScWarps + warp;
   if (tile * kTile >= a.B) return;
-  double *stage = smem + warp * kTile * ROW;
+  double *stage = smem + (size_t)warp * NARR * Runs::DOUBLES;
   const int N = P.n_eval;
   const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
   const bool valid = b < a.B;
   const long bs = valid ? b : b0;
   const double *zb = DO_SIM ? a.z + bs * a.z_stride : nullptr;
   const double *hist = a.hist + hist_offset(bs - (bs % kTile) + lane, 0, N, n);  // this lane's column, record 0
+  Runs rm, rx;
+  if (DO_MEAN) rm.init(stage, a.mu_out, b0, a.B, T1, lane);
+  if (DO_SIM) rx.init(stage + (DO_MEAN ? Runs::DOUBLES : 0), a.x_out, b0, a.B, T1, lane);
   double mus[n], x[n], nxt[n];
 #pragma unroll
   for (int i = 0; i < n; i++) nxt[i] = hist[i * kTile];
@@ -80,22 +85,19 @@ kalman_sc_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
         x[i] = v;
       }
     }
-    double *row = stage + lane * ROW;
-    if (DO_MEAN) {
-#pragma unroll
-      for (int i = 0; i < n; i++) row[i] = mus[i];
-    }
-    if (DO_SIM) {
-#pragma unroll
-      for (int i = 0; i < n; i++) row[(DO_MEAN ? n : 0) + i] = x[i];
-    }
+    if (DO_MEAN) rm.put(lane, t, mus);
+    if (DO_SIM) rx.put(lane, t, x);
     __syncwarp();
-    if (DO_MEAN) flush_runs<n, 0, ROW>(stage, a.mu_out, b0, a.B, T1, t, lane);
-    if (DO_SIM) flush_runs<n, (DO_MEAN ? n : 0), ROW>(stage, a.x_out, b0, a.B, T1, t, lane);
+    if (DO_MEAN) rm.store(t, lane);
+    if (DO_SIM) rx.store(t, lane);
     __syncwarp();
   }
 }
 
+template <class Fam, bool DO_MEAN, bool DO_SIM>
+inline size_t sc_backward_smem() {
+  return (size_t)kScWarps * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0)) * BlockedRuns<Fam::n, kScBlock, 32>::DOUBLES * sizeof(double);
+}
 
 // ---- launchers --------------------------------------------------------------------------------
 template <class Fam>
@@ -125,7 +127,11 @@ cudaError_t launch_sc_backward(const HostPrior &h, const SolveArgs &a, cudaStrea
   } else {
     const long n_tiles = (a.B + kTile - 1) / kTile;
     const unsigned grid = (unsigned)((n_tiles + kScWarps - 1) / kScWarps);
-    kalman_sc_backward<Fam, DO_MEAN, DO_SIM><<<grid, kScWarps * 32, 0, s>>>(make_prior<Fam>(h), a);
+    auto kern = kalman_sc_backward<Fam, DO_MEAN, DO_SIM>;
+    const size_t smem = sc_backward_smem<Fam, DO_MEAN, DO_SIM>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kScWarps * 32, smem, s>>>(make_prior<Fam>(h), a);
   }
   return cudaGetLastError();
 }

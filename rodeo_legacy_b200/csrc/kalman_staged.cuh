@@ -282,6 +282,90 @@ struct FlushPlan {
   }
 };
 
+// Short per-step runs (a mean or a draw: W = n doubles, 48-120 bytes) written one per visit straddle
+// 32-byte sectors and leave the memory system at less than half speed (tools/microbench/write_pattern.cu:
+// 48-byte runs 2.2 TB/s, the same bytes as sector-aligned multi-step pieces 4.7-4.9 TB/s).  BlockedRuns
+// collects K consecutive time indices of a system in a shared-memory row and stores them as ONE piece of
+// K*W doubles.  Blocks are cut on the GLOBAL run index g = b*T1 + t (block = K runs with g / K equal), so
+// every full block starts at a multiple of K*W*8 bytes whatever the parity of T1 and b: systems of one
+// tile complete their blocks at different steps, a few rows per step.  Trajectory ends give partial blocks.
+// Rows are written by their owner thread (put), stored cooperatively by NT threads after a barrier (store).
+template <int W, int K, int NT>
+struct BlockedRuns {
+  static_assert((K & (K - 1)) == 0 && (K * W) % 2 == 0 && kTile % K == 0, "K a power of two, K*W even");
+  static constexpr int RS = K * W, PR = RS / 2;     // doubles and 16-byte pieces per row
+  static constexpr int DOUBLES = kTile * RS;
+  // steady state with T1 odd: the K residue classes of the row index complete their blocks in turn, one class
+  // (kTile / K rows) per step; thread tid handles piece q = j*NT + tid of the class, q = i*PR + p
+  static constexpr int CLS_PIECES = (kTile / K) * PR, JN = (CLS_PIECES + NT - 1) / NT;
+  double *tile, *out;
+  long b0, B, T1;
+  int N, r0;                 // r0 = (b0*T1) mod K
+  int soff[JN], doff[JN], rowj[JN];
+  bool odd;
+  __device__ __forceinline__ void init(double *tile_, double *out_, long b0_, long B_, long T1_, int tid) {
+    tile = tile_;
+    out = out_;
+    b0 = b0_;
+    B = B_;
+    T1 = T1_;
+    N = (int)T1_ - 1;
+    r0 = (int)((b0_ * T1_) & (K - 1));
+    odd = (T1_ & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < JN; j++) {
+      const int q = j * NT + tid, i = q / PR, p = q - i * PR;
+      rowj[j] = q < CLS_PIECES ? i * K : -1;
+      soff[j] = i * K * RS + 2 * p;
+      doff[j] = i * K * (int)T1_ * W + 2 * p;
+    }
+  }
+  __device__ __forceinline__ void put(int s, int t, const double *v) const {
+    const int slot = (int)(((b0 + s) * T1 + t) & (K - 1));
+    double *d = tile + s * RS + slot * W;
+    if constexpr (W % 2 == 0) {
+#pragma unroll
+      for (int i = 0; i < W / 2; i++) reinterpret_cast<double2 *>(d)[i] = make_double2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < W; i++) d[i] = v[i];
+    }
+  }
+  // any T1, trajectory ends: every piece looks up its row's state
+  __device__ __noinline__ void store_general(int t, int tid) const {
+    for (int q = tid; q < kTile * PR; q += NT) {
+      const int s = q / PR, p = q - s * PR;
+      const long g = (b0 + s) * T1 + t;
+      const int slot = (int)(g & (K - 1));
+      if (b0 + s >= B || (slot != 0 && t != 0)) continue;     // this row's block is not complete yet
+      int hi = slot + (N - t);                                // last valid slot (the block may run past time N)
+      hi = hi < K - 1 ? hi : K - 1;
+      const int d0 = 2 * p, k0 = d0 / W, k1 = (d0 + 1) / W;
+      const bool v0 = k0 >= slot && k0 <= hi, v1 = k1 >= slot && k1 <= hi;
+      const double *src = tile + s * RS + d0;
+      double *dst = out + (g - slot) * W + d0;
+      if (v0 && v1) *reinterpret_cast<double2 *>(dst) = *reinterpret_cast<const double2 *>(src);
+      else if (v0) dst[0] = src[0];
+      else if (v1) dst[1] = src[1];
+    }
+  }
+  __device__ __forceinline__ void store(int t, int tid) const {
+    if (!odd || t == 0 || N - t < K - 1) {
+      store_general(t, tid);
+      return;
+    }
+    // the class c with ((b0 + c)*T1 + t) mod K == 0; T1 odd, so T1*T1 = 1 (mod 8): c = -(r0 + t)*T1 (mod K)
+    const int cls = (int)((-(long)(r0 + t) * T1) & (K - 1));
+    const double *src = tile + cls * RS;
+    double *dst = out + ((b0 + cls) * T1 + t) * W;
+    const int rows_left = (int)(B - b0 - cls);                // rows b0 + cls + rowj exist while rowj < rows_left
+#pragma unroll
+    for (int j = 0; j < JN; j++)
+      if (rowj[j] >= 0 && rowj[j] < rows_left)
+        *reinterpret_cast<double2 *>(dst + doff[j]) = *reinterpret_cast<const double2 *>(src + soff[j]);
+  }
+};
+
 template <class Fam, class L, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 struct StagedEmitter {
   static constexpr int n = Fam::n, ROW = L::ROW, H = L::H;
