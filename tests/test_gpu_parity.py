@@ -449,7 +449,10 @@ def test_checkpointed_history_is_bit_identical(maker, B, N, ck):
 @pytest.mark.parametrize("maker,B,mtol,vtol,xtol,dense_too", [
     (wl.fitz_batch, 3000, 1e-10, 1e-9, 1e-9, True),
     (lambda B: wl.lorenz_batch(B, N=500, tmax=2.0), 130, 1e-9, 1e-7, 1e-8, False),
-    (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7, False)])
+    (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7, False),
+    # n_eval + 1 even / a multiple of 4: the blocked output runs take their general path; ragged last tile
+    (lambda B: wl.lorenz_batch(B, N=501, tmax=2.0), 45, 1e-9, 1e-7, 1e-8, False),
+    (lambda B: wl.mseir_batch(B, N=203), 33, 1e-10, 1e-8, 1e-7, False)])
 def test_shared_covariance_mode(maker, B, mtol, vtol, xtol, dense_too):
     """shared_cov=True: covariance path computed once per prior, batch kernels run the mean
     recursions only.  Against the oracle (which computes every system's covariance) and against
