@@ -7,6 +7,54 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
+// store variants: 0 plain, 1 st.cs (streaming), 2 st.wt, 3 L2 evict_last hint, 4 L2 evict_first hint
+template <int MODE>
+__device__ __forceinline__ void store16(double *p, double2 v, unsigned long long pol) {
+  if (MODE == 1) __stcs(reinterpret_cast<double2 *>(p), v);
+  else if (MODE == 2) __stwt(reinterpret_cast<double2 *>(p), v);
+  else if (MODE >= 3)
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+  else *reinterpret_cast<double2 *>(p) = v;
+}
+
+template <int W, int MODE>
+__global__ void __launch_bounds__(64) k_write_hint(double *out, long B, int T1) {
+  const int lane = threadIdx.x % 32;
+  const long tile = (long)blockIdx.x * 2 + threadIdx.x / 32;
+  const long b0 = tile * 32;
+  if (b0 >= B) return;
+  unsigned long long pol = 0;
+  if (MODE == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  if (MODE == 4) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  constexpr int C = W / 2;
+  for (int t = T1 - 1; t >= 0; t--) {
+#pragma unroll 4
+    for (int q = lane; q < 32 * C; q += 32) {
+      const int s = q / C, c = q - s * C;
+      store16<MODE>(out + ((b0 + s) * T1 + t) * W + 2 * c, make_double2((double)t, (double)c), pol);
+    }
+  }
+}
+
+template <int W, int MODE>
+void run_hint(double *out, long B, int T1, const char *name) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const unsigned grid = (unsigned)((B / 32 + 1) / 2);
+  float best = 1e30f;
+  for (int it = 0; it < 4; it++) {
+    cudaEventRecord(e0);
+    k_write_hint<W, MODE><<<grid, 64>>>(out, B, T1);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it && ms < best) best = ms;
+  }
+  printf("{\"pattern\": \"%s\", \"W\": %d, \"ms\": %.3f, \"GBps\": %.0f}\n", name, W, best, (double)B * T1 * W * 8 / best / 1e6);
+}
+
 template <int W, int KT>
 __global__ void __launch_bounds__(64) k_write(double *out, long B, int T1) {
   const int lane = threadIdx.x % 32;
@@ -56,6 +104,10 @@ int main(int argc, char **argv) {
   run<36, 2>(out, B, T1, "var runs, two steps per visit");
   run<36, 4>(out, B, T1, "var runs, four steps per visit");
   run<36, 8>(out, B, T1, "var runs, eight steps per visit");
+  run_hint<36, 1>(out, B, T1, "var runs, st.global.cs");
+  run_hint<36, 2>(out, B, T1, "var runs, st.global.wt");
+  run_hint<36, 3>(out, B, T1, "var runs, L2 evict_last hint");
+  run_hint<36, 4>(out, B, T1, "var runs, L2 evict_first hint");
   run<6, 1>(out, B, T1, "mean runs, one step per visit");
   run<6, 2>(out, B, T1, "mean runs, two steps per visit");
   run<6, 4>(out, B, T1, "mean runs, four steps per visit");
