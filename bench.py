@@ -49,6 +49,9 @@ def workload_config(extra=None):
     return c
 
 
+REF_FLOPS_PER_SOLVE = 3621 * 400          # SURVEY 8(d), C2, general mode
+
+
 def measured_traffic(kernel_key):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture
     (profiles/traffic.json, written by tools/ncu_traffic.py from `ncu --set full`), or None."""
@@ -71,6 +74,21 @@ def write_pattern_peak():
         import subprocess
         out = subprocess.run([exe, "--quick"], capture_output=True, text=True, timeout=60).stdout
         return float(json.loads(out.strip().splitlines()[0])["GBps"])
+    except Exception:
+        return None
+
+
+def fp64_peak():
+    """Sustained FP64 FMA rate of this GPU in TFLOP/s (tools/microbench/fp64_peak.cu, measured live; the
+    best of its occupancy settings), or None."""
+    exe = os.path.join(ROOT, "tools", "microbench", "fp64_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        import subprocess
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        vals = [json.loads(l).get("fp64_TFLOPs") for l in out.strip().splitlines()]
+        return max(v for v in vals if v)
     except Exception:
         return None
 
@@ -409,6 +427,7 @@ def main():
         key = "backward_mv_fitz6_" + ("dense" if args.dense else "blockdiag")
         traffic = measured_traffic(key)
         wpat = write_pattern_peak()
+        f64 = fp64_peak()
         bwd_gbs = ALG_BYTES_BACKWARD * B / (bwd_ms * 1e-3) / 1e9
         fwd_gbs = ALG_BYTES_FORWARD * B / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None
         step_gbs = ALG_BYTES_SOLVE * B * args.steps / (ms * 1e-3) / 1e9
@@ -430,6 +449,13 @@ def main():
                                  "write_pattern_peak = GB/s of a no-compute kernel writing this workload's "
                                  "288-byte-run output pattern (tools/microbench/write_pattern.cu, measured in "
                                  "this run): 82 % of the kernel's traffic is that pattern",
+                         "fp64": {"peak_TFLOPs": f64, "source": "tools/microbench/fp64_peak.cu, measured in this run "
+                                                                "(nominal 37.2)",
+                                  "reference_flops_per_solve": REF_FLOPS_PER_SOLVE,
+                                  "reference_equivalent_TFLOPs": value / world * REF_FLOPS_PER_SOLVE / 1e12,
+                                  "note": "SURVEY 8(d): 3621 flop/step x 400 steps as the reference's dense "
+                                          "KalmanTV executes them; the block-diagonal kernels skip the structural "
+                                          "zeros, so this can exceed the peak -- the second bound, never the binding one"},
                          "algorithmic_bytes_per_launch": ALG_BYTES_BACKWARD * B,
                          "kernel_ms": bwd_ms, "forward_kernel_ms": fwd_ms,
                          "forward_achieved": fwd_gbs,

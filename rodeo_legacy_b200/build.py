@@ -75,19 +75,24 @@ def build(force=False, verbose=False, ptxas_info=False):
 
 
 def build_microbench():
-    """tools/microbench/write_pattern: no-compute kernel writing the smoother's output pattern (what the
-    memory system sustains for 288-byte runs of 65,536 interleaved streams); bench.py reports it next to the
-    kernel's own DRAM rate.  Returns the binary's path."""
+    """tools/microbench: write_pattern (no-compute kernel writing the smoother's output pattern: what the
+    memory system sustains for 288-byte runs of 65,536 interleaved streams), fp64_peak (sustained DFMA
+    rate; MEASURED_PEAKS.json has no FP64 figure) and the write_pattern2 sensitivity experiment.  bench.py
+    runs the first two next to the kernels.  Returns the binaries' paths."""
     root = os.path.dirname(HERE)
-    src = os.path.join(root, "tools", "microbench", "write_pattern.cu")
-    out = src[:-3]
-    if _stale(out, [src]):
-        cmd = [nvcc(), "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-cudart", "static", "-o", out, src]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("write_pattern microbenchmark failed to build")
-    return out
+    outs = []
+    for name in ("write_pattern", "fp64_peak", "write_pattern2"):
+        src = os.path.join(root, "tools", "microbench", name + ".cu")
+        out = src[:-3]
+        if _stale(out, [src]):
+            cmd = [nvcc(), "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-cudart", "static",
+                   "-o", out, src]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError(f"microbenchmark {name} failed to build")
+        outs.append(out)
+    return outs
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ import numpy as np
 from .utils import mvncond
 
 __all__ = ["root_gen", "car_mou", "car_cov", "car_var", "car_state",
-           "car_initial_draw", "car_init"]
+           "car_initial_draw", "car_initial_draw_batch", "car_init"]
 
 
 def root_gen(tau, p):
@@ -100,6 +100,31 @@ def car_initial_draw(roots, sigma, x0, p):
     out[:q + 1] = x0
     out[q + 1:] = np.random.multivariate_normal(A @ x0 + b, V)
     return out
+
+
+def car_initial_draw_batch(roots, sigma, X0, p, z=None):
+    """car_initial_draw for a batch: X0 is (B, q+1) -> (B, p), each row's unknown derivatives an
+    independent draw from the stationary CAR law conditioned on the known ones
+    (rodeo/car/car_init.py:22-49, vectorised).  NumPy in -> NumPy out (global NumPy
+    RNG unless standard normals `z` (B, p-q-1) are given); torch in -> torch out on the input's device
+    (torch RNG), so x0 for a batch of solves can be produced next to the solver without a host
+    round trip.  The conditional law does not depend on the system: one (A, b, chol V) serves the batch."""
+    is_torch = hasattr(X0, "device") and not isinstance(X0, np.ndarray)
+    q = X0.shape[1] - 1
+    if p == q + 1:
+        return X0
+    V_inf = car_cov([], roots, sigma, v_infinity=True)
+    A, b, V = mvncond(np.zeros(p), V_inf, np.arange(p) <= q)
+    L = np.linalg.cholesky(V)
+    if is_torch:
+        import torch
+        kw = dict(dtype=torch.float64, device=X0.device)
+        At, bt, Lt = torch.as_tensor(A, **kw), torch.as_tensor(b, **kw), torch.as_tensor(L, **kw)
+        zz = torch.randn(X0.shape[0], p - q - 1, **kw) if z is None else torch.as_tensor(z, **kw)
+        return torch.cat([X0.to(torch.float64), X0.to(torch.float64) @ At.T + bt + zz @ Lt.T], dim=1)
+    X0 = np.asarray(X0, dtype=float)
+    zz = np.random.standard_normal((X0.shape[0], p - q - 1)) if z is None else np.asarray(z, dtype=float)
+    return np.concatenate([X0, X0 @ A.T + b + zz @ L.T], axis=1)
 
 
 def car_init(dt, n_deriv_prior, tau, sigma, x0=None):

@@ -54,6 +54,34 @@ def test_car_init_matches_reference():
     np.testing.assert_allclose(x0, lg["x0"], rtol=1e-9, atol=1e-12)
 
 
+def test_car_initial_draw_batch():
+    """Batched initial draw: row b equals the single-system draw made with the same normals; the
+    conditional law (mean A x0 + b, variance V) is the reference's (rodeo/car/car_init.py:22-49)."""
+    import torch
+    from rodeo_legacy_b200.car import car_initial_draw_batch, car_cov, root_gen
+    from rodeo_legacy_b200.utils import mvncond
+    roots, sigma, p = root_gen(1.5, 4), 0.3, 4
+    rng = np.random.default_rng(3)
+    X0 = rng.standard_normal((50, 2))
+    z = rng.standard_normal((50, 2))
+    out = car_initial_draw_batch(roots, sigma, X0, p, z=z)
+    assert out.shape == (50, 4) and np.array_equal(out[:, :2], X0)
+    A, b, V = mvncond(np.zeros(p), car_cov([], roots, sigma, v_infinity=True), np.arange(p) <= 1)
+    L = np.linalg.cholesky(V)
+    np.testing.assert_allclose(out[:, 2:], X0 @ A.T + b + z @ L.T, rtol=1e-13)
+    # all derivatives known: nothing to draw
+    assert car_initial_draw_batch(roots, sigma, rng.standard_normal((3, 4)), p).shape == (3, 4)
+    # torch in -> torch out, same numbers
+    out_t = car_initial_draw_batch(roots, sigma, torch.from_numpy(X0), p, z=z)
+    assert isinstance(out_t, torch.Tensor)
+    np.testing.assert_allclose(out_t.numpy(), out, rtol=1e-13)
+    # sample moments of fresh draws match the conditional law
+    np.random.seed(0)
+    big = car_initial_draw_batch(roots, sigma, np.tile(X0[:1], (20000, 1)), p)[:, 2:]
+    assert np.abs(big.mean(0) - (A @ X0[0] + b)).max() < 4 * np.sqrt(np.diag(V).max() / 20000)
+    assert np.abs(np.cov(big.T) - V).max() < 0.05 * np.abs(V).max()
+
+
 def test_rand_mat_shape_and_quirk():
     np.random.seed(0)
     z = rand_mat(10, 4)
