@@ -132,7 +132,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 constexpr int kStagedWarps = RODEO_STAGED_WARPS;  // warps per CTA
 constexpr int kStagedThreads = kStagedWarps * 32;
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK = false>
 struct StagedLayout {
   static constexpr int n = Fam::n, NE = Fam::NE;
   static constexpr int REC = NE * kTile;                                         // doubles per record
@@ -154,9 +154,9 @@ struct StagedLayout {
   // the output staging tile, 2 mbarriers
   // outputs leave through TMA tensor stores (dense per-array tiles) when every run is a 16-byte multiple and
   // the dense rows cost at most a 2-way bank conflict on the 16-byte row writes: n_state = 6
-  static constexpr bool kTma = (n == 6) && !TWO_PASS;
+  static constexpr bool kTma = (n == 6) && !TWO_PASS && !LOGLIK;
   // per-warp region kept a multiple of 128 bytes (TMA source alignment)
-  static constexpr int STAGE = kTma ? kTile * (VEC_W + (DO_VAR ? n * n : 0)) : kTile * ROW;   // staging tile(s)
+  static constexpr int STAGE = LOGLIK ? 0 : kTma ? kTile * (VEC_W + (DO_VAR ? n * n : 0)) : kTile * ROW;   // staging tile(s)
   static constexpr int WARP_DOUBLES = ((2 + (CK - 1)) * REC + STAGE + 2 + 15) / 16 * 16;
   static constexpr size_t smem_bytes = (size_t)kStagedWarps * WARP_DOUBLES * sizeof(double);
   // No min-blocks launch bound: with a one-pass tile shared memory limits the kernel to 4 CTAs per
@@ -488,11 +488,34 @@ struct TmaEmitter {
   }
 };
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
-__global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::MINB)
+// No per-step output at all: the thinned Gaussian log-likelihood of the smoothed mean (or of the draw) is
+// accumulated per system (examples/inference.py:54-56, 66-94) and one double per system leaves the kernel.
+template <class Fam, bool DO_SIM>
+struct LoglikEmitter {
+  double lp;
+  int d;
+  __device__ __forceinline__ void init(const SolveArgs &a) {
+    lp = 0.0;
+    d = a.n_obs_times - 1;
+  }
+  __device__ __forceinline__ void emit(const SolveArgs &a, int t, const double *mus, const double *, const double *x) {
+    while (d >= 0 && a.thin_index[d] == t) {
+      lp += reg::loglik_terms<Fam::n>(a, d, DO_SIM ? x : mus);
+      d--;
+    }
+  }
+  __device__ __forceinline__ void finish(const SolveArgs &a, long b, bool valid) const {
+    // constant of the normal density: -(log sqrt(2 pi) + log gamma) per observation
+    const double cst = -0.91893853320467274178 - log(a.gamma);
+    if (valid) a.loglik[b] = lp + cst * (double)(a.n_obs_times * a.n_obs_comp);
+  }
+};
+
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK = false>
+__global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>::MINB)
 kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
                        const __grid_constant__ StoreMaps maps) {
-  using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
+  using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
   using Ode = typename Fam::Ode;
   constexpr int n = Fam::n, NS = Fam::NS, NE = Fam::NE, REC = L::REC;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
@@ -537,9 +560,12 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
 #pragma unroll
     for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[bs * Ode::n_theta + i] : 0.0;
   }
-  typename std::conditional<L::kTma, TmaEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM>,
-                            StagedEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM>>::type em;
-  if constexpr (L::kTma) em.init(stage, &maps, b0, lane);
+  typename std::conditional<
+      LOGLIK, LoglikEmitter<Fam, DO_SIM>,
+      typename std::conditional<L::kTma, TmaEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM>,
+                                StagedEmitter<Fam, L, DO_MEAN, DO_VAR, DO_SIM>>::type>::type em;
+  if constexpr (LOGLIK) em.init(a);
+  else if constexpr (L::kTma) em.init(stage, &maps, b0, lane);
   else em.init(stage, a, b0, T1, lane);
   uint32_t phase = 0;
   // wait for record r (ring slot r & 1); returns this lane's column of it
@@ -645,14 +671,15 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
     for (int i = 0; i < NS; i++) Ss[i] = 0.0;
     em.emit(a, 0, mus, Ss, x);
   }
-  if constexpr (L::kTma) em.finish();
+  if constexpr (LOGLIK) em.finish(a, b, valid);
+  else if constexpr (L::kTma) em.finish();
   if (valid && a.status && fail && a.status[b] == 0) a.status[b] = fail;
 }
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK = false>
 cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
-  auto kern = kalman_backward_staged<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
+  using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
+  auto kern = kalman_backward_staged<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
   if (e != cudaSuccess) return e;
   const long n_tiles = (a.B + kTile - 1) / kTile;

@@ -168,8 +168,13 @@ void fill_backward(KernelSet &k) {
     k.backward[CKI][BK_SIM] = launch_backward<Fam, UNROLL, CK, false, false, true, false>;
     k.backward[CKI][BK_BOTH] = launch_backward<Fam, UNROLL, CK, true, true, true, false>;
   }
-  k.backward[CKI][BK_LL_MEAN] = launch_backward<Fam, UNROLL, CK, true, false, false, true>;
-  k.backward[CKI][BK_LL_DRAW] = launch_backward<Fam, UNROLL, CK, false, false, true, true>;
+  if constexpr (UNROLL) {   // register families: history through the TMA ring, nothing staged out
+    k.backward[CKI][BK_LL_MEAN] = launch_backward_staged<Fam, CK, true, false, false, true>;
+    k.backward[CKI][BK_LL_DRAW] = launch_backward_staged<Fam, CK, false, false, true, true>;
+  } else {
+    k.backward[CKI][BK_LL_MEAN] = launch_backward<Fam, UNROLL, CK, true, false, false, true>;
+    k.backward[CKI][BK_LL_DRAW] = launch_backward<Fam, UNROLL, CK, false, false, true, true>;
+  }
 }
 
 // K = n_state for the dense family, block size p for the block-diagonal family.
