@@ -38,39 +38,64 @@ kalman_sc_loglik(const __grid_constant__ typename Fam::PriorT P, const __grid_co
 
 constexpr int kScWarps = 4;
 constexpr int kScBlock = 4;   // time indices per stored piece (BlockedRuns)
+constexpr int kScRing = 4;    // filtered-mean records in flight per warp (TMA ring)
 
+// Mean-only smoother / sampler.  The per-step arithmetic is tiny (two p x p mat-vecs per block), so the kernel
+// lives on memory-level parallelism: each warp keeps kScRing records (n*32 doubles, one cp.async.bulk each) in
+// flight in a shared-memory ring, and writes its outputs as 4-step blocks (BlockedRuns).
 template <class Fam, bool DO_MEAN, bool DO_SIM>
 __global__ void __launch_bounds__(kScWarps * 32)
 kalman_sc_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
-  constexpr int n = Fam::n;
+  constexpr int n = Fam::n, REC = n * kTile;
   using Runs = BlockedRuns<n, kScBlock, 32>;
   constexpr int NARR = (DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0);
+  constexpr int WARP_DOUBLES = (kScRing * REC + NARR * Runs::DOUBLES + kScRing + 15) / 16 * 16;
   extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long tile = (long)blockIdx.x * kScWarps + warp;
   if (tile * kTile >= a.B) return;
-  double *stage = smem + (size_t)warp * NARR * Runs::DOUBLES;
+  double *ring = smem + (size_t)warp * WARP_DOUBLES;
+  double *stage = ring + kScRing * REC;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(stage + NARR * Runs::DOUBLES);
   const int N = P.n_eval;
   const long T1 = (long)N + 1, b0 = tile * kTile, b = b0 + lane;
   const bool valid = b < a.B;
   const long bs = valid ? b : b0;
   const double *zb = DO_SIM ? a.z + bs * a.z_stride : nullptr;
-  const double *hist = a.hist + hist_offset(bs - (bs % kTile) + lane, 0, N, n);  // this lane's column, record 0
+  const double *hist_tile = a.hist + (size_t)tile * N * REC;     // record r = time index N - r
+  constexpr uint32_t kRecBytes = REC * sizeof(double);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kScRing; k++) mbar_init(&bar[k], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kScRing; k++)
+      if (k < N) {
+        mbar_arrive_expect_tx(&bar[k], kRecBytes);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)k * REC, kRecBytes, &bar[k]);
+      }
+  }
   Runs rm, rx;
   if (DO_MEAN) rm.init(stage, a.mu_out, b0, a.B, T1, lane);
   if (DO_SIM) rx.init(stage + (DO_MEAN ? Runs::DOUBLES : 0), a.x_out, b0, a.B, T1, lane);
-  double mus[n], x[n], nxt[n];
-#pragma unroll
-  for (int i = 0; i < n; i++) nxt[i] = hist[i * kTile];
+  double mus[n], x[n];
+  uint32_t phase = 0;
   for (int t = N; t >= 0; t--) {
     if (t >= 1) {
+      const int r = N - t, k = r % kScRing;
+      mbar_wait(&bar[k], (phase >> k) & 1u);
+      phase ^= 1u << k;
       double cur[n];
 #pragma unroll
-      for (int i = 0; i < n; i++) cur[i] = nxt[i];
-      if (t >= 2) {  // prefetch the record of time index t-1
-        const double *h = hist + (long)(N - t + 1) * n * kTile;
-#pragma unroll
-        for (int i = 0; i < n; i++) nxt[i] = h[i * kTile];
+      for (int i = 0; i < n; i++) cur[i] = ring[k * REC + i * kTile + lane];
+      fence_proxy_async();   // this lane's reads of the slot are complete ...
+      __syncwarp();          // ... for every lane, before lane 0 lets the TMA overwrite it
+      if (lane == 0 && r + kScRing < N) {
+        mbar_arrive_expect_tx(&bar[k], kRecBytes);
+        bulk_g2s(ring + k * REC, hist_tile + (size_t)(r + kScRing) * REC, kRecBytes, &bar[k]);
       }
       const double *zt = DO_SIM ? zb + (long)(t - 1) * n : nullptr;
       if (t == N)
@@ -96,7 +121,9 @@ kalman_sc_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_
 
 template <class Fam, bool DO_MEAN, bool DO_SIM>
 inline size_t sc_backward_smem() {
-  return (size_t)kScWarps * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0)) * BlockedRuns<Fam::n, kScBlock, 32>::DOUBLES * sizeof(double);
+  constexpr int NARR = (DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0);
+  constexpr int WARP_DOUBLES = (kScRing * Fam::n * kTile + NARR * BlockedRuns<Fam::n, kScBlock, 32>::DOUBLES + kScRing + 15) / 16 * 16;
+  return (size_t)kScWarps * WARP_DOUBLES * sizeof(double);
 }
 
 // ---- launchers --------------------------------------------------------------------------------
