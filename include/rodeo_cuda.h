@@ -166,8 +166,9 @@ int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch);
 /* Device-pointer entry point.  All pointers are device memory on the problem's device.
  * theta may be NULL when the RHS has no parameters; z may be NULL for RODEO_MODE_MV with
  * probde/schobert interrogation; outputs not produced by `mode` may be NULL; status may
- * be NULL.  Work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and
- * the call returns without synchronising. */
+ * be NULL.  Output pointers must be 16-byte aligned (they are written with vector / TMA
+ * stores; RODEO_E_INVALID otherwise).  Work is enqueued on `cuda_stream` (a cudaStream_t,
+ * NULL = default stream) and the call returns without synchronising. */
 int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0,
                      const double *theta, const double *z, int64_t z_batch_stride,
                      double *x_out, double *mu_out, double *var_out, int32_t *status,

@@ -427,6 +427,13 @@ static int check_solve_args(rodeo_problem *p, int mode, int64_t batch, const dou
   return RODEO_OK;
 }
 
+// Device outputs are written with 16-byte vector / TMA stores.
+static int check_device_alignment(const double *x_out, const double *mu_out, const double *var_out) {
+  if ((reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(mu_out) | reinterpret_cast<uintptr_t>(var_out)) & 15)
+    return fail(RODEO_E_INVALID, "device output arrays must be 16-byte aligned");
+  return RODEO_OK;
+}
+
 extern "C" {
 
 int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch) {
@@ -440,6 +447,7 @@ int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0
                      const double *z, int64_t z_batch_stride, double *x_out, double *mu_out,
                      double *var_out, int32_t *status, void *cuda_stream) {
   int rc = check_solve_args(p, mode, batch, x0, theta, z, x_out, mu_out, var_out);
+  if (!rc && batch > 0) rc = check_device_alignment(x_out, mu_out, var_out);
   if (rc) return rc;
   if (batch == 0) return RODEO_OK;
   CK(cudaSetDevice(p->device));

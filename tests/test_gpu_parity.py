@@ -368,6 +368,18 @@ def test_error_behaviour():
     mu_a, _ = k.solve_mv(w["x0"], theta=w["theta0"])
     mu_b, _ = k.solve_mv(w["x0"], W=w["W"], theta=w["theta0"])
     np.testing.assert_array_equal(mu_a, mu_b)
+    # C ABI: device outputs must be 16-byte aligned (vector / TMA stores) -- refused, not faulted
+    import ctypes
+    from rodeo_legacy_b200.cuda import _lib
+    lib = _lib.load()
+    buf = torch.zeros(2 * 401 * 42 + 8, dtype=torch.float64, device="cuda")
+    x0d = torch.from_numpy(np.tile(w["x0"], (2, 1))).cuda()
+    thd = torch.from_numpy(np.tile(w["theta0"], (2, 1))).cuda()
+    st = torch.zeros(2, dtype=torch.int32, device="cuda")
+    mu_p, var_p = buf.data_ptr() + 8, buf.data_ptr() + 8 + 2 * 401 * 6 * 8
+    rc = lib.rodeo_cuda_solve(k._h, 1, 2, ctypes.c_void_p(x0d.data_ptr()), ctypes.c_void_p(thd.data_ptr()), None, 0,
+                              None, ctypes.c_void_p(mu_p), ctypes.c_void_p(var_p), ctypes.c_void_p(st.data_ptr()), None)
+    assert rc == -1 and b"16-byte aligned" in lib.rodeo_cuda_last_error()
     # empty batch
     mu_e, var_e = k.solve_mv(np.zeros((0, 6)), theta=np.zeros((0, 3)))
     assert mu_e.shape == (0, 401, 6) and var_e.shape == (0, 401, 6, 6)
