@@ -34,15 +34,13 @@ struct BdwLayout {
   static constexpr int REC = NE * kTile;
   static constexpr int VW = n * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0));   // "vector" pass width
   static constexpr int COLW = p * n;                                       // one block's variance columns
-  static constexpr int PB = (48 / COLW) < 1 ? 1 : ((48 / COLW) > nb ? nb : (48 / COLW));
-  static constexpr int NPASS_VAR = DO_VAR ? (nb + PB - 1) / PB : 0;
-  static constexpr int TW0 = (DO_VAR && PB * COLW > VW) ? PB * COLW : VW;
-  static constexpr int TW = (TW0 + 1) / 2 * 2;                             // tile row stride (even)
+  static constexpr int TW = (VW + 1) / 2 * 2;                              // mean / draw tile row stride (even)
+  static constexpr int VT = DO_VAR ? kTile * nb * p * p : 0;               // CTA tile: the nb p x p blocks per system
   static constexpr int THREADS = nb * 32;
-  static constexpr int SMEM_DOUBLES = 2 * REC + 2 * kTile * TW + 2;
+  static constexpr int SMEM_DOUBLES = 2 * REC + kTile * TW + VT + 2;
   static constexpr size_t smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
   // resident CTAs per SM to aim for: as many as shared memory allows, registers capped at 128
-  static constexpr int BY_SMEM = (int)((227 * 1024) / smem_bytes);
+  static constexpr int BY_SMEM = (int)((227 * 1024) / (smem_bytes + 1024));
   static constexpr int BY_REGS = 65536 / (THREADS * 128);
   static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
@@ -71,35 +69,69 @@ __device__ __forceinline__ int bdw_dispatch(int blk, const typename Fam::PriorT 
   return BdwBlock<Fam, DO_MEAN, DO_VAR, DO_SIM, A>::step(P, terminal, rec, zt, mus, Ss, x);
 }
 
-// Variance pass G of a step: the warps of blocks [G*PB, G*PB + NBLK) write their columns of the
-// dense n x n output (own block's rows from Ss, zeros elsewhere) into tile (G+1)&1; after a CTA
-// barrier all threads store those columns of every system's run.  Recurses over G at compile
-// time so that every length and offset is a constant.
-template <class Fam, class L, int G>
-__device__ __forceinline__ void bdw_var_passes(double *tiles, const double *Ss, double *var_out, long b0, long B,
-                                               long T1, int t, int tid, int blk, int lane) {
-  constexpr int p = L::p, n = L::n, nb = L::nb, TW = L::TW;
-  if constexpr (G < L::NPASS_VAR) {
-    constexpr int FIRST = G * L::PB;
-    constexpr int NBLK = (nb - FIRST) < L::PB ? (nb - FIRST) : L::PB;
-    double *tl = tiles + ((G + 1) & 1) * kTile * TW;
-    if (blk >= FIRST && blk < FIRST + NBLK) {
-      double *row = tl + lane * TW + (blk - FIRST) * L::COLW;
+// Variance of one step.  Every warp parks its p x p block of each system in a CTA tile ([32][nb*p*p] doubles: only
+// the non-zero entries); after the CTA barrier the warps share out the 32 systems and each writes WHOLE
+// n*n-double runs (structural zeros synthesised, block entries read from the tile), lane k storing the
+// 16-byte pieces k, k+32, ... of a run.  Whole runs matter: the memory system sustains long contiguous
+// runs far better than a run assembled from nb pieces written at different times with ragged 8-byte
+// edges (tools/microbench/write_pattern.cu).  For odd n a run starts on an odd double index for every
+// other (system, step): pieces are cut on 16-byte boundaries of the OUTPUT ADDRESS, so the first / last
+// piece of a run may be half (one 8-byte store).
+template <class L>
+struct BdwRunPlan {
+  static constexpr int NN = L::n * L::n, NQ = (NN + 2) / 2, NIT = (NQ + 31) / 32;
+  // for address parity par and piece q = lane + 32*it: tile index of its two doubles
+  // (-1: a structural zero, -2: outside the run)
+  short idx[2][NIT][2];
+  __device__ __forceinline__ void init(int lane) {
+    constexpr int p = L::p, n = L::n;
 #pragma unroll
-      for (int jj = 0; jj < p; jj++) {
+    for (int par = 0; par < 2; par++)
 #pragma unroll
-        for (int i = 0; i < n; i++) row[jj * n + i] = 0.0;
-      }
-      double *own = row + blk * p;  // this block's rows inside each of its columns
+      for (int it = 0; it < NIT; it++)
 #pragma unroll
-      for (int jj = 0; jj < p; jj++) {
+        for (int h = 0; h < 2; h++) {
+          const int q = lane + 32 * it, r = 2 * q - par + h;      // double index inside the run: r = j*n + i
+          int v = -2;
+          if (q < NQ && r >= 0 && r < NN) {
+            const int j = r / n, i = r - j * n;
+            v = (j / p == i / p) ? (j / p) * p * p + (j % p) * p + (i % p) : -1;
+          }
+          idx[par][it][h] = (short)v;
+        }
+  }
+};
+
+template <class Fam, class L>
+__device__ __forceinline__ void bdw_park_var(double *vt, const double *Ss, int blk, int lane) {
+  constexpr int p = L::p;
+  double *row = vt + lane * (L::nb * p * p) + blk * p * p;
 #pragma unroll
-        for (int ii = 0; ii < p; ii++) own[jj * n + ii] = Ss[sidx<p>(ii, jj)];
-      }
+  for (int jj = 0; jj < p; jj++)
+#pragma unroll
+    for (int ii = 0; ii < p; ii++) row[jj * p + ii] = Ss[sidx<p>(ii, jj)];
+}
+
+template <class Fam, class L>
+__device__ __forceinline__ void bdw_emit_var(const double *vt, const BdwRunPlan<L> &plan, double *var_out, long b0,
+                                             long B, long T1, int t, int blk, int lane) {
+  constexpr int p = L::p, nb = L::nb;
+  using Plan = BdwRunPlan<L>;
+  const int rows = (int)(B - b0 < kTile ? B - b0 : kTile);
+  for (int s = blk; s < rows; s += nb) {
+    double *run = var_out + ((b0 + s) * T1 + t) * (long)Plan::NN;
+    const int par = (int)((reinterpret_cast<uintptr_t>(run) >> 3) & 1);
+    const double *src = vt + s * (nb * p * p);
+#pragma unroll
+    for (int it = 0; it < Plan::NIT; it++) {
+      const int i0 = par ? plan.idx[1][it][0] : plan.idx[0][it][0];
+      const int i1 = par ? plan.idx[1][it][1] : plan.idx[0][it][1];
+      const double v0 = i0 >= 0 ? src[i0] : 0.0, v1 = i1 >= 0 ? src[i1] : 0.0;
+      double *dst = run - par + 2 * (lane + 32 * it);          // 16-byte aligned
+      if (i0 > -2 && i1 > -2) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+      else if (i0 > -2) dst[0] = v0;
+      else if (i1 > -2) dst[1] = v1;
     }
-    __syncthreads();
-    flush_part<n * n, FIRST * L::COLW, NBLK * L::COLW, 0, TW, L::THREADS>(tl, var_out, b0, B, T1, t, tid);
-    bdw_var_passes<Fam, L, G + 1>(tiles, Ss, var_out, b0, B, T1, t, tid, blk, lane);
   }
 }
 
@@ -111,8 +143,9 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
   constexpr int p = L::p, n = L::n, PS = L::PS, REC = L::REC, TW = L::TW, NT = L::THREADS;
   extern __shared__ __align__(128) double smem[];
   double *ring = smem;
-  double *tiles = ring + 2 * REC;
-  uint64_t *bar = reinterpret_cast<uint64_t *>(tiles + 2 * kTile * TW);
+  double *tiles = ring + 2 * REC;                       // mean / draw tile (CTA-wide)
+  double *vtile = tiles + kTile * TW;                   // the systems' diagonal variance blocks (CTA-wide)
+  uint64_t *bar = reinterpret_cast<uint64_t *>(vtile + L::VT);
   const int tid = threadIdx.x, blk = tid / 32, lane = tid % 32;
   const long tile = blockIdx.x;
   const int N = P.n_eval;   // checkpoint interval 1: record r holds time index N - r, R = N records
@@ -137,6 +170,8 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
   }
   double mus[p], Ss[PS], x[p];
   int fail = 0;
+  BdwRunPlan<L> vplan;
+  if (DO_VAR) vplan.init(lane);
   const double *zb = DO_SIM ? a.z + (valid ? b : b0) * a.z_stride : nullptr;
   uint32_t phase = 0;
   for (int t = N; t >= 0; t--) {
@@ -167,8 +202,8 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
       }
       __syncthreads();
     }
-    // ---- pass 0: means and draws ----------------------------------------------------------
-    if (L::VW > 0) {
+    // ---- park this block's part of every output in the CTA tiles, one barrier, then store ----------
+    {
       double *row = tiles + lane * TW;
       if (DO_MEAN) {
 #pragma unroll
@@ -178,12 +213,12 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
         for (int i = 0; i < p; i++) row[(DO_MEAN ? n : 0) + blk * p + i] = x[i];
       }
+      if (DO_VAR) bdw_park_var<Fam, L>(vtile, Ss, blk, lane);
       __syncthreads();
       if (DO_MEAN) flush_part<n, 0, n, 0, TW, NT>(tiles, a.mu_out, b0, a.B, T1, t, tid);
       if (DO_SIM) flush_part<n, 0, n, (DO_MEAN ? n : 0), TW, NT>(tiles, a.x_out, b0, a.B, T1, t, tid);
+      if (DO_VAR) bdw_emit_var<Fam, L>(vtile, vplan, a.var_out, b0, a.B, T1, t, blk, lane);
     }
-    // ---- variance passes: PB blocks' columns at a time, alternating tiles ---------------------
-    if (DO_VAR) bdw_var_passes<Fam, L, 0>(tiles, Ss, a.var_out, b0, a.B, T1, t, tid, blk, lane);
   }
   if (valid && a.status && fail) atomicCAS(a.status + b, 0, fail);
 }
