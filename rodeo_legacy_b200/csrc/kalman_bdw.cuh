@@ -35,7 +35,7 @@ struct BdwLayout {
   static constexpr int VW = n * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0));   // "vector" pass width
   static constexpr int COLW = p * n;                                       // one block's variance columns
   static constexpr int TW = (VW + 1) / 2 * 2;                              // mean / draw tile row stride (even)
-  static constexpr int VT = DO_VAR ? kTile * nb * p * p : 0;               // CTA tile: the nb p x p blocks per system
+  static constexpr int VT = DO_VAR ? kTile * (nb * p * p + 1) : 0;         // CTA tile: the nb p x p blocks per system + a zero
   static constexpr int THREADS = nb * 32;
   static constexpr int SMEM_DOUBLES = 2 * REC + kTile * TW + VT + 2;
   static constexpr size_t smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
@@ -80,58 +80,72 @@ __device__ __forceinline__ int bdw_dispatch(int blk, const typename Fam::PriorT 
 template <class L>
 struct BdwRunPlan {
   static constexpr int NN = L::n * L::n, NQ = (NN + 2) / 2, NIT = (NQ + 31) / 32;
-  // for address parity par and piece q = lane + 32*it: tile index of its two doubles
-  // (-1: a structural zero, -2: outside the run)
-  short idx[2][NIT][2];
+  static constexpr int ZERO = L::nb * L::p * L::p;     // every tile row ends with a 0.0: structural zeros load it
+  static constexpr int ROWW = ZERO + 1;
+  // for address parity par and piece q = lane + 32*it: tile-row index of its two doubles, and what to
+  // store (2 bits per (par, it): 0 nothing, 1 both doubles, 2 the lower one only, 3 the upper one only)
+  int idx[2][NIT][2];
+  unsigned kind;
   __device__ __forceinline__ void init(int lane) {
     constexpr int p = L::p, n = L::n;
+    kind = 0;
 #pragma unroll
     for (int par = 0; par < 2; par++)
 #pragma unroll
-      for (int it = 0; it < NIT; it++)
+      for (int it = 0; it < NIT; it++) {
+        const int q = lane + 32 * it;
+        bool ok[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const int q = lane + 32 * it, r = 2 * q - par + h;      // double index inside the run: r = j*n + i
-          int v = -2;
-          if (q < NQ && r >= 0 && r < NN) {
+          const int r = 2 * q - par + h;                         // double index inside the run: r = j*n + i
+          ok[h] = q < NQ && r >= 0 && r < NN;
+          int v = ZERO;
+          if (ok[h]) {
             const int j = r / n, i = r - j * n;
-            v = (j / p == i / p) ? (j / p) * p * p + (j % p) * p + (i % p) : -1;
+            if (j / p == i / p) v = (j / p) * p * p + (j % p) * p + (i % p);
           }
-          idx[par][it][h] = (short)v;
+          idx[par][it][h] = v;
         }
+        const unsigned k = ok[0] && ok[1] ? 1u : ok[0] ? 2u : ok[1] ? 3u : 0u;
+        kind |= k << (2 * (par * NIT + it));
+      }
   }
 };
 
 template <class Fam, class L>
 __device__ __forceinline__ void bdw_park_var(double *vt, const double *Ss, int blk, int lane) {
   constexpr int p = L::p;
-  double *row = vt + lane * (L::nb * p * p) + blk * p * p;
+  double *row = vt + lane * BdwRunPlan<L>::ROWW + blk * p * p;
 #pragma unroll
   for (int jj = 0; jj < p; jj++)
 #pragma unroll
     for (int ii = 0; ii < p; ii++) row[jj * p + ii] = Ss[sidx<p>(ii, jj)];
 }
 
+template <class L, int PAR>
+__device__ __forceinline__ void bdw_emit_run(const double *src, const BdwRunPlan<L> &plan, double *run, int lane) {
+  using Plan = BdwRunPlan<L>;
+#pragma unroll
+  for (int it = 0; it < Plan::NIT; it++) {
+    const unsigned k = (plan.kind >> (2 * (PAR * Plan::NIT + it))) & 3u;
+    const double v0 = src[plan.idx[PAR][it][0]], v1 = src[plan.idx[PAR][it][1]];
+    double *dst = run - PAR + 2 * (lane + 32 * it);            // 16-byte aligned
+    if (k == 1u) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+    else if (k == 2u) dst[0] = v0;
+    else if (k == 3u) dst[1] = v1;
+  }
+}
+
 template <class Fam, class L>
 __device__ __forceinline__ void bdw_emit_var(const double *vt, const BdwRunPlan<L> &plan, double *var_out, long b0,
                                              long B, long T1, int t, int blk, int lane) {
-  constexpr int p = L::p, nb = L::nb;
   using Plan = BdwRunPlan<L>;
   const int rows = (int)(B - b0 < kTile ? B - b0 : kTile);
-  for (int s = blk; s < rows; s += nb) {
+  for (int s = blk; s < rows; s += L::nb) {
     double *run = var_out + ((b0 + s) * T1 + t) * (long)Plan::NN;
-    const int par = (int)((reinterpret_cast<uintptr_t>(run) >> 3) & 1);
-    const double *src = vt + s * (nb * p * p);
-#pragma unroll
-    for (int it = 0; it < Plan::NIT; it++) {
-      const int i0 = par ? plan.idx[1][it][0] : plan.idx[0][it][0];
-      const int i1 = par ? plan.idx[1][it][1] : plan.idx[0][it][1];
-      const double v0 = i0 >= 0 ? src[i0] : 0.0, v1 = i1 >= 0 ? src[i1] : 0.0;
-      double *dst = run - par + 2 * (lane + 32 * it);          // 16-byte aligned
-      if (i0 > -2 && i1 > -2) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
-      else if (i0 > -2) dst[0] = v0;
-      else if (i1 > -2) dst[1] = v1;
-    }
+    const double *src = vt + s * Plan::ROWW;
+    if ((reinterpret_cast<uintptr_t>(run) >> 3) & 1) bdw_emit_run<L, 1>(src, plan, run, lane);
+    else bdw_emit_run<L, 0>(src, plan, run, lane);
   }
 }
 
@@ -171,7 +185,10 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
   double mus[p], Ss[PS], x[p];
   int fail = 0;
   BdwRunPlan<L> vplan;
-  if (DO_VAR) vplan.init(lane);
+  if (DO_VAR) {
+    vplan.init(lane);
+    if (blk == 0) vtile[lane * BdwRunPlan<L>::ROWW + BdwRunPlan<L>::ZERO] = 0.0;   // ordered by the first CTA barrier
+  }
   const double *zb = DO_SIM ? a.z + (valid ? b : b0) * a.z_stride : nullptr;
   uint32_t phase = 0;
   for (int t = N; t >= 0; t--) {
