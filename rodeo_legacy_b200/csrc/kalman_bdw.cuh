@@ -34,10 +34,19 @@ struct BdwLayout {
   static constexpr int REC = NE * kTile;
   static constexpr int VW = n * ((DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0));   // "vector" pass width
   static constexpr int COLW = p * n;                                       // one block's variance columns
-  static constexpr int TW = (VW + 1) / 2 * 2;                              // mean / draw tile row stride (even)
+  static constexpr int KB = 4;                                             // time indices per stored mean / draw piece
+  using Runs = BlockedRuns<n, KB, nb * 32>;
+  static constexpr int NVEC = (DO_MEAN ? 1 : 0) + (DO_SIM ? 1 : 0);
+  // mean / draw outputs as sector-aligned 4-step blocks (BlockedRuns) when the kernel also writes variances
+  // (MSEIR solve_mv: 15.2 -> 14.2 ms); the draw-only kernels are register bound (two Cholesky factorisations
+  // per block and step) and measured slower with it (Lorenz63 solve_sim 5.74 -> 6.01 ms): they keep the
+  // one-step tile + 8-byte stores
+  static constexpr bool kBlocked = DO_VAR;
+  static constexpr int TW = (VW + 1) / 2 * 2;                              // one-step tile row stride (even)
+  static constexpr int TILES = kBlocked ? NVEC * Runs::DOUBLES : kTile * TW;
   static constexpr int VT = DO_VAR ? kTile * (nb * p * p + 1) : 0;         // CTA tile: the nb p x p blocks per system + a zero
   static constexpr int THREADS = nb * 32;
-  static constexpr int SMEM_DOUBLES = 2 * REC + kTile * TW + VT + 2;
+  static constexpr int SMEM_DOUBLES = 2 * REC + TILES + VT + 2;
   static constexpr size_t smem_bytes = (size_t)SMEM_DOUBLES * sizeof(double);
   // resident CTAs per SM to aim for: as many as shared memory allows, registers capped at 128
   static constexpr int BY_SMEM = (int)((227 * 1024) / (smem_bytes + 1024));
@@ -154,11 +163,12 @@ __global__ void __launch_bounds__(BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::THREA
                                   BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::MINB)
 kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   using L = BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
-  constexpr int p = L::p, n = L::n, PS = L::PS, REC = L::REC, TW = L::TW, NT = L::THREADS;
+  constexpr int p = L::p, n = L::n, PS = L::PS, REC = L::REC;
+  using Runs = typename L::Runs;
   extern __shared__ __align__(128) double smem[];
   double *ring = smem;
-  double *tiles = ring + 2 * REC;                       // mean / draw tile (CTA-wide)
-  double *vtile = tiles + kTile * TW;                   // the systems' diagonal variance blocks (CTA-wide)
+  double *tiles = ring + 2 * REC;                       // mean / draw rows: K-step blocks (BlockedRuns)
+  double *vtile = tiles + L::TILES;                     // the systems' diagonal variance blocks (CTA-wide)
   uint64_t *bar = reinterpret_cast<uint64_t *>(vtile + L::VT);
   const int tid = threadIdx.x, blk = tid / 32, lane = tid % 32;
   const long tile = blockIdx.x;
@@ -184,6 +194,9 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
   }
   double mus[p], Ss[PS], x[p];
   int fail = 0;
+  Runs rm, rx;
+  if (L::kBlocked && DO_MEAN) rm.init(tiles, a.mu_out, b0, a.B, T1, tid);
+  if (L::kBlocked && DO_SIM) rx.init(tiles + (DO_MEAN ? Runs::DOUBLES : 0), a.x_out, b0, a.B, T1, tid);
   BdwRunPlan<L> vplan;
   if (DO_VAR) {
     vplan.init(lane);
@@ -220,7 +233,16 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
       __syncthreads();
     }
     // ---- park this block's part of every output in the CTA tiles, one barrier, then store ----------
-    {
+    if constexpr (L::kBlocked) {
+      if (DO_MEAN) rm.template put_part<p>(lane, t, blk * p, mus);
+      if (DO_SIM) rx.template put_part<p>(lane, t, blk * p, x);
+      bdw_park_var<Fam, L>(vtile, Ss, blk, lane);
+      __syncthreads();
+      if (DO_MEAN) rm.store(t, tid);      // the 4-step blocks that became complete at this step
+      if (DO_SIM) rx.store(t, tid);
+      bdw_emit_var<Fam, L>(vtile, vplan, a.var_out, b0, a.B, T1, t, blk, lane);
+    } else {
+      constexpr int TW = L::TW, NT = L::THREADS;
       double *row = tiles + lane * TW;
       if (DO_MEAN) {
 #pragma unroll
@@ -230,11 +252,9 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
         for (int i = 0; i < p; i++) row[(DO_MEAN ? n : 0) + blk * p + i] = x[i];
       }
-      if (DO_VAR) bdw_park_var<Fam, L>(vtile, Ss, blk, lane);
       __syncthreads();
       if (DO_MEAN) flush_part<n, 0, n, 0, TW, NT>(tiles, a.mu_out, b0, a.B, T1, t, tid);
       if (DO_SIM) flush_part<n, 0, n, (DO_MEAN ? n : 0), TW, NT>(tiles, a.x_out, b0, a.B, T1, t, tid);
-      if (DO_VAR) bdw_emit_var<Fam, L>(vtile, vplan, a.var_out, b0, a.B, T1, t, blk, lane);
     }
   }
   if (valid && a.status && fail) atomicCAS(a.status + b, 0, fail);

@@ -301,9 +301,8 @@ struct BlockedRuns {
   double *tile, *out;
   long b0, B, T1;
   int N, r0;                 // r0 = (b0*T1) mod K
-  int soff[JN], doff[JN], rowj[JN];
   bool odd;
-  __device__ __forceinline__ void init(double *tile_, double *out_, long b0_, long B_, long T1_, int tid) {
+  __device__ __forceinline__ void init(double *tile_, double *out_, long b0_, long B_, long T1_, int) {
     tile = tile_;
     out = out_;
     b0 = b0_;
@@ -312,13 +311,6 @@ struct BlockedRuns {
     N = (int)T1_ - 1;
     r0 = (int)((b0_ * T1_) & (K - 1));
     odd = (T1_ & 1) != 0;
-#pragma unroll
-    for (int j = 0; j < JN; j++) {
-      const int q = j * NT + tid, i = q / PR, p = q - i * PR;
-      rowj[j] = q < CLS_PIECES ? i * K : -1;
-      soff[j] = i * K * RS + 2 * p;
-      doff[j] = i * K * (int)T1_ * W + 2 * p;
-    }
   }
   __device__ __forceinline__ void put(int s, int t, const double *v) const {
     const int slot = (int)(((b0 + s) * T1 + t) & (K - 1));
@@ -330,6 +322,14 @@ struct BlockedRuns {
 #pragma unroll
       for (int i = 0; i < W; i++) d[i] = v[i];
     }
+  }
+  // part of a run (entries off .. off+CNT-1), e.g. one diagonal block's share of the state vector
+  template <int CNT>
+  __device__ __forceinline__ void put_part(int s, int t, int off, const double *v) const {
+    const int slot = (int)(((b0 + s) * T1 + t) & (K - 1));
+    double *d = tile + s * RS + slot * W + off;
+#pragma unroll
+    for (int i = 0; i < CNT; i++) d[i] = v[i];
   }
   // any T1, trajectory ends: every piece looks up its row's state
   __device__ __noinline__ void store_general(int t, int tid) const {
@@ -358,11 +358,15 @@ struct BlockedRuns {
     const int cls = (int)((-(long)(r0 + t) * T1) & (K - 1));
     const double *src = tile + cls * RS;
     double *dst = out + ((b0 + cls) * T1 + t) * W;
-    const int rows_left = (int)(B - b0 - cls);                // rows b0 + cls + rowj exist while rowj < rows_left
+    const int rows_left = (int)(B - b0 - cls);                // row b0 + cls + i*K exists while i*K < rows_left
+    const int strideW = (int)T1 * W;
 #pragma unroll
-    for (int j = 0; j < JN; j++)
-      if (rowj[j] >= 0 && rowj[j] < rows_left)
-        *reinterpret_cast<double2 *>(dst + doff[j]) = *reinterpret_cast<const double2 *>(src + soff[j]);
+    for (int j = 0; j < JN; j++) {
+      const int q = j * NT + tid, i = q / PR, p = q - i * PR;  // piece p of the class's i-th row (few integer ops,
+      if (q < CLS_PIECES && i * K < rows_left)                 // cheaper than holding per-thread offset tables)
+        *reinterpret_cast<double2 *>(dst + (long)(i * K) * strideW + 2 * p) =
+            *reinterpret_cast<const double2 *>(src + i * K * RS + 2 * p);
+    }
   }
 };
 
