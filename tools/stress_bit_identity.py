@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Stress: repeat full-size solves and require bit-identical results.  With a shared prior the covariance path
+does not depend on theta / x0, so var must be bit-identical across the whole batch and across repetitions; mu
+must repeat bit-for-bit.  (This property test is what exposed the cross-proxy ring race)
+
+    python tools/stress_bit_identity.py [--reps 100]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from tests import workloads as wl
+
+
+def check(name, maker, B, reps, mode="mv"):
+    w, x0, th = maker(B)
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(1).standard_normal((n, w["N"])))
+    k = wl.make_kode(w, z_state=z)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(th).cuda()
+    ref_mu = ref_var0 = None
+    bad = 0
+    for r in range(reps):
+        if mode == "mv":
+            mu, var = k.solve_mv(x0d, theta=thd)
+        else:
+            _, mu, var = k.solve(x0d, theta=thd)
+        same = True
+        for lo in range(0, B, 4096):        # var identical across the batch (chunked compare: memory)
+            same &= bool((var[lo:lo + 4096] == var[0:1]).all())
+        if ref_mu is None:
+            ref_mu, ref_var0 = mu.clone(), var[0].clone()
+        same &= bool(torch.equal(mu, ref_mu)) and bool(torch.equal(var[0], ref_var0))
+        bad += (not same)
+        del mu, var
+    print(f"{name}: {reps} repetitions, {bad} mismatching", flush=True)
+    return bad
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=100)
+    a = ap.parse_args()
+    bad = check("fitz 65536 x 400 solve_mv", wl.fitz_batch, 65536, a.reps)
+    bad += check("fitz 65536 x 400 solve", wl.fitz_batch, 65536, max(1, a.reps // 4), mode="both")
+    bad += check("mseir 8192 x 1000 solve_mv", lambda B: wl.mseir_batch(B, N=1000), 8192, max(1, a.reps // 4))
+    bad += check("lorenz 8192 x 1000 solve", lambda B: wl.lorenz_batch(B, N=1000, tmax=4.0), 8192, max(1, a.reps // 4), mode="both")
+    sys.exit(1 if bad else 0)
