@@ -146,6 +146,7 @@ def cpu_baseline(seconds=10.0, chunk=1024, nthreads=0):
     import oracle
     from tests import workloads as wl
     oracle.build()
+    flags = oracle.select_timing_build()
     w, x0, theta = wl.fitz_batch(chunk * 64, seed=0)
     p = wl.make_oracle_problem(w)
     if nthreads <= 0:            # torchrun exports OMP_NUM_THREADS=1: ask for every usable core
@@ -162,7 +163,7 @@ def cpu_baseline(seconds=10.0, chunk=1024, nthreads=0):
             break
     return {"value": done / el, "unit": UNIT, "cores": int(cores), "kind": "port",
             "sample": f"{done} of the workload's solves (chunks of {chunk}), {el:.1f} s, "
-                      "C port of the reference arithmetic, gcc -O3, OpenMP over systems"}, done, el
+                      f"C port of the reference arithmetic, {flags}, OpenMP over systems"}, done, el
 
 
 def host_cores():
@@ -183,6 +184,7 @@ def run_reference(args):
     import oracle
     from tests import workloads as wl
     oracle.build()
+    flags = oracle.select_timing_build()
     w, x0, theta = wl.fitz_batch(chunk, seed=0)
     p = wl.make_oracle_problem(w)
     cores = host_cores()         # explicit: torchrun exports OMP_NUM_THREADS=1
@@ -195,7 +197,7 @@ def run_reference(args):
     el = time.perf_counter() - t0
     v = steps * chunk / el
     sample = (f"each step = {chunk} of the workload's 65536 solves; {steps} steps timed "
-              f"(capped at 20 so the run ends within minutes)")
+              f"(capped at 20 so the run ends within minutes); C port of the reference arithmetic, {flags}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

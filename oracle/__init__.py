@@ -30,11 +30,37 @@ _ip = ctypes.POINTER(ctypes.c_int)
 def build(force=False):
     """Compile liboracle.so with gcc (idempotent)."""
     src = os.path.join(_HERE, "kalman_oracle.c")
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)):
+    fast = os.path.join(_HERE, "_build", "liboracle_fast_v4.so")
+    if (not force and os.path.exists(_LIB_PATH) and os.path.exists(fast)
+            and os.path.getmtime(_LIB_PATH) >= os.path.getmtime(src)
+            and os.path.getmtime(fast) >= os.path.getmtime(src)):
         return _LIB_PATH
     subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
     return _LIB_PATH
+
+
+def select_timing_build():
+    """Switch this process to the fast-math timing build of the oracle (the reference's own compiler
+    flags, setup.py:37-42) at the widest ISA level the host supports.  For bench.py's CPU-baseline legs
+    ONLY: results may differ from the parity build in the last bits.  Returns a description."""
+    global _lib, _LIB_PATH
+    build()
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = line
+                    break
+    except OSError:
+        pass
+    v4 = all((" " + k) in flags for k in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
+    name = "liboracle_fast_v4.so" if v4 else "liboracle_fast_v3.so"
+    path = os.path.join(_HERE, "_build", name)
+    if not os.path.exists(path):
+        return "gcc -O3 -fno-fast-math (parity build; timing build missing)"
+    _LIB_PATH, _lib = path, None
+    return "gcc -O3 -ffast-math -march=x86-64-v%d -fopenmp (the reference's setup.py flags, ISA level pinned)" % (4 if v4 else 3)
 
 
 def lib():
