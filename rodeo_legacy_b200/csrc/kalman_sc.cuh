@@ -2,8 +2,8 @@
 //   kalman_sc_tables     one thread per diagonal block (or one thread, dense): covariance
 //                        recursion -> gain / Cholesky tables + the (N+1, n, n) variance output
 //   kalman_sc_forward    thread per system, mean-only filter, streams mu_filt (n doubles / step)
-//   kalman_sc_backward   warp per 32-system tile, mean-only smoother / sampler; next record
-//                        prefetched into registers, outputs through a shared-memory staging tile
+//   kalman_sc_backward   warp per 32-system tile, mean-only smoother / sampler; four records in flight
+//                        in a TMA ring, outputs stored as sector-aligned 4-step blocks (BlockedRuns)
 //   kalman_sc_loglik     mean-only smoother accumulating the thinned log-likelihood
 #pragma once
 #include "kalman_staged.cuh"

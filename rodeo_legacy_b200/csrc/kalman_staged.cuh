@@ -1,6 +1,7 @@
 // kalman_staged.cuh -- backward (smoother) kernel of the register family with the
 // filter history staged through shared memory by bulk async copies (TMA, cp.async.bulk +
-// mbarrier) and the outputs transposed through shared memory into coalesced 16-byte stores.
+// mbarrier) and the outputs transposed through shared memory: TMA tensor stores for n_state = 6,
+// coalesced 16-byte stores otherwise; the log-likelihood variant emits nothing per step.
 //
 // One warp owns one tile of 32 systems (one thread per system) for the whole backward pass:
 //   * its history record for one (checkpointed) time index is NE*32 contiguous doubles in HBM
@@ -9,9 +10,12 @@
 //     DRAM latency of the read stream is hidden without spending registers on prefetch;
 //     each lane then reads its own column of the record (bank-conflict free).
 //   * every lane writes the step's outputs (mean, covariance, draw) into its own row of a
-//     staging tile; the warp then stores the tile so that each system's contiguous run in
-//     the user-visible layout  out[b][t][...]  is written by neighbouring lanes as 16-byte
-//     pieces -- full 32-byte sectors instead of 32 scattered 8-byte stores per instruction.
+//     staging tile; the tile then leaves as one cp.async.bulk.tensor per array (TmaEmitter: the
+//     tensor map {W, T1, B} with box {W, 1, 32} describes exactly the 32 runs of a step), or the
+//     warp stores it so that each system's contiguous run in the user-visible layout
+//     out[b][t][...]  is written by neighbouring lanes as 16-byte pieces (StagedEmitter).
+//   * BlockedRuns (used by the shared-covariance and warp-per-block kernels) collects K steps of a short
+//     per-step run per system and stores them as one sector-aligned piece.
 //   * with checkpointing (CK > 1) the filter is re-run from each checkpoint record into CK-1
 //     scratch records in shared memory (same layout, each lane touches only its own column),
 //     which the smoother then consumes exactly like loaded records.
@@ -164,37 +168,6 @@ struct StagedLayout {
   // 2.5 -> 5.1 ms).
   static constexpr int MINB = 1;
 };
-
-// Store one output array from the staging tile: every system s of the tile owns a run of
-// W doubles at stage[s*ROW + OFF ..]; its destination is out + ((b0+s)*T1 + t)*W.
-template <int W, int OFF, int ROW>
-__device__ __forceinline__ void flush_runs(const double *stage, double *out, long b0, long B, long T1, int t,
-                                           int lane) {
-  constexpr bool V2 = (W % 2 == 0) && (OFF % 2 == 0);
-  if (V2) {
-    constexpr int C = W / 2;
-#pragma unroll
-    for (int q0 = 0; q0 < kTile * C; q0 += kTile) {
-      const int q = q0 + lane;
-      if (q < kTile * C) {
-        const int s = q / C, c = q - s * C;
-        if (b0 + s < B) {
-          const double2 v = *reinterpret_cast<const double2 *>(stage + s * ROW + OFF + 2 * c);
-          *reinterpret_cast<double2 *>(out + ((b0 + s) * T1 + t) * W + 2 * c) = v;
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int q0 = 0; q0 < kTile * W; q0 += kTile) {
-      const int q = q0 + lane;
-      if (q < kTile * W) {
-        const int s = q / W, c = q - s * W;
-        if (b0 + s < B) out[((b0 + s) * T1 + t) * W + c] = stage[s * ROW + OFF + c];
-      }
-    }
-  }
-}
 
 // Generic (any parity) store of columns [C0, C0+LEN) of every system's run of W doubles from a
 // staging tile (system s at tile[s*TW + OFF ..]) to out + ((b0+s)*T1 + t)*W + C0, by NTHREADS threads.
