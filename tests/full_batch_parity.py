@@ -22,12 +22,12 @@ from tests import workloads as wl
 from tests.common import traj_err, var_err
 
 
-def run(name, maker, B, mode, chunk, horizon=None):
+def run(name, maker, B, mode, chunk, horizon=None, dense=False):
     w, x0, th = maker(B)
     n = len(w["x0"])
     np.random.seed(2)
     z = np.asfortranarray(np.random.randn(n, w["N"])) if mode == "sim" else None
-    k = wl.make_kode(w, z_state=z)
+    k = wl.make_kode(w, z_state=z, force_dense=dense)
     po = wl.make_oracle_problem(w)
     x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(th).cuda()
     if mode == "mv":
@@ -60,11 +60,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C2,C3,C4")
     ap.add_argument("--chunk", type=int, default=1024)
+    ap.add_argument("--dense", action="store_true", help="force the general dense kernel families")
     a = ap.parse_args()
     sel = a.configs.split(",")
     if "C2" in sel:
-        run("C2 fitz solve_mv 65536 x 400", wl.fitz_batch, 65536, "mv", a.chunk)
+        run("C2 fitz solve_mv 65536 x 400", wl.fitz_batch, 65536, "mv", a.chunk, dense=a.dense)
     if "C4" in sel:
-        run("C4 mseir solve_mv 32768 x 1000", wl.mseir_batch, 32768, "mv", min(a.chunk, 512))
+        run("C4 mseir solve_mv 32768 x 1000", wl.mseir_batch, 32768, "mv", min(a.chunk, 512), dense=a.dense)
     if "C3" in sel:
-        run("C3 lorenz63 solve_sim 16384 x 5000", wl.lorenz_batch, 16384, "sim", a.chunk, horizon=1000)
+        run("C3 lorenz63 solve_sim 16384 x 5000", wl.lorenz_batch, 16384, "sim", a.chunk, horizon=1000, dense=a.dense)
