@@ -465,6 +465,30 @@ struct TmaEmitter {
   }
 };
 
+// Per-system priors: device arrays, batch-major, each system laid out like the constructor's arrays
+// (column-major); nullptr = keep the handle's shared value.
+template <int n, int m>
+__device__ __forceinline__ void load_batched_prior(Prior<n, m> &P, const BatchedPrior &bp, long b) {
+  if (bp.Q) {
+    const double *q = bp.Q + b * n * n;
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++) P.Q[i * n + j] = q[i + j * n];
+  }
+  if (bp.R) {
+    const double *r = bp.R + b * n * n;
+    for (int i = 0; i < n; i++)
+      for (int j = i; j < n; j++) P.R[sidx<n>(i, j)] = r[i + j * n];
+  }
+  if (bp.c) {
+    for (int i = 0; i < n; i++) P.c[i] = bp.c[b * n + i];
+  }
+  if (bp.W) {
+    const double *w = bp.W + b * m * n;
+    for (int a = 0; a < m; a++)
+      for (int j = 0; j < n; j++) P.W[a * n + j] = w[a + j * m];
+  }
+}
+
 // No per-step output at all: the thinned Gaussian log-likelihood of the smoothed mean (or of the draw) is
 // accumulated per system (examples/inference.py:54-56, 66-94) and one double per system leaves the kernel.
 template <class Fam, bool DO_SIM>
@@ -488,10 +512,11 @@ struct LoglikEmitter {
   }
 };
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK = false>
-__global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>::MINB)
-kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
-                       const __grid_constant__ StoreMaps maps) {
+// The whole backward pass of one warp-tile.  P is the kernel's __grid_constant__ prior (every coefficient an
+// immediate constant-bank operand after inlining) or, for per-system priors, a thread-private copy.
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
+__device__ __forceinline__ void staged_backward_body(const typename Fam::PriorT &P, const SolveArgs &a,
+                                                     const StoreMaps &maps) {
   using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
   using Ode = typename Fam::Ode;
   constexpr int n = Fam::n, NS = Fam::NS, NE = Fam::NE, REC = L::REC;
@@ -654,6 +679,25 @@ kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __g
 }
 
 template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK = false>
+__global__ void __launch_bounds__(kStagedThreads, StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>::MINB)
+kalman_backward_staged(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
+                       const __grid_constant__ StoreMaps maps) {
+  staged_backward_body<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(P, a, maps);
+}
+
+// Per-system priors (dense family, full history): every thread overlays its system's Q, c, R, W on a private
+// copy of the shared prior and runs the same body -- same TMA ring, same staged / TMA-store emission.
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+__global__ void __launch_bounds__(kStagedThreads)
+kalman_backward_staged_pp(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
+                          const __grid_constant__ SolveArgs a, const __grid_constant__ StoreMaps maps) {
+  const long b0 = ((long)blockIdx.x * kStagedWarps + threadIdx.x / 32) * kTile, b = b0 + threadIdx.x % 32;
+  typename Fam::PriorT Pl = P;
+  if (b0 < a.B) load_batched_prior(Pl, bp, b < a.B ? b : b0);
+  staged_backward_body<Fam, 1, DO_MEAN, DO_VAR, DO_SIM, false>(Pl, a, maps);
+}
+
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK = false>
 cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
   using L = StagedLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
   auto kern = kalman_backward_staged<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
@@ -670,6 +714,28 @@ cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaS
     if (DO_VAR && (e = encode_out_map(&maps.var, a.var_out, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
   }
   kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(make_prior<Fam>(h), a, maps);
+  return cudaGetLastError();
+}
+
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+cudaError_t launch_backward_staged_pp(const HostPrior &h, const BatchedPrior &bp, const SolveArgs &a, cudaStream_t s) {
+  using L = StagedLayout<Fam, 1, DO_MEAN, DO_VAR, DO_SIM, false>;
+  auto kern = kalman_backward_staged_pp<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
+  if (e != cudaSuccess) return e;
+  const long n_tiles = (a.B + kTile - 1) / kTile;
+  const unsigned grid = (unsigned)((n_tiles + kStagedWarps - 1) / kStagedWarps);
+  StoreMaps maps;
+  memset(&maps, 0, sizeof maps);
+  if (L::kTma) {
+    constexpr int n = Fam::n;
+    if (DO_MEAN && (e = encode_out_map(&maps.mu, a.mu_out, n, a.n_steps, a.B)) != cudaSuccess) return e;
+    if (DO_SIM && (e = encode_out_map(&maps.x, a.x_out, n, a.n_steps, a.B)) != cudaSuccess) return e;
+    if (DO_VAR && (e = encode_out_map(&maps.var, a.var_out, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
+  }
+  typename Fam::PriorT P;
+  fill_prior(P, h);
+  kern<<<grid, kStagedThreads, L::smem_bytes, s>>>(P, bp, a, maps);
   return cudaGetLastError();
 }
 

@@ -71,28 +71,6 @@ kalman_backward(const __grid_constant__ typename Fam::PriorT P, const __grid_con
 // BatchedPrior (registry.cuh) holds the device arrays.  The thread builds its private copy of the
 // prior (registers / local memory instead of the constant bank) and runs the same bodies.
 
-template <int n, int m>
-__device__ __forceinline__ void load_batched_prior(Prior<n, m> &P, const BatchedPrior &bp, long b) {
-  if (bp.Q) {
-    const double *q = bp.Q + b * n * n;
-    for (int i = 0; i < n; i++)
-      for (int j = 0; j < n; j++) P.Q[i * n + j] = q[i + j * n];
-  }
-  if (bp.R) {
-    const double *r = bp.R + b * n * n;
-    for (int i = 0; i < n; i++)
-      for (int j = i; j < n; j++) P.R[sidx<n>(i, j)] = r[i + j * n];
-  }
-  if (bp.c) {
-    for (int i = 0; i < n; i++) P.c[i] = bp.c[b * n + i];
-  }
-  if (bp.W) {
-    const double *w = bp.W + b * m * n;
-    for (int a = 0; a < m; a++)
-      for (int j = 0; j < n; j++) P.W[a * n + j] = w[a + j * m];
-  }
-}
-
 template <class Fam, bool UNROLL, int IG>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_forward_pp(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ BatchedPrior bp,
@@ -213,9 +191,15 @@ KernelSet make_kernel_set(const char *name) {
   k.wide_hist_elems = 0;
   if constexpr (!BD) {  // per-system priors: dense family only (a batched prior need not be structured)
     k.pp_forward = launch_forward_pp<Fam, UNROLL, IG_PROBDE>;
-    k.pp_backward[BK_MV] = launch_backward_pp<Fam, UNROLL, true, true, false, false>;
-    k.pp_backward[BK_SIM] = launch_backward_pp<Fam, UNROLL, false, false, true, false>;
-    k.pp_backward[BK_BOTH] = launch_backward_pp<Fam, UNROLL, true, true, true, false>;
+    if constexpr (UNROLL) {   // register family: the staged kernel with a thread-private prior (coalesced / TMA stores)
+      k.pp_backward[BK_MV] = launch_backward_staged_pp<Fam, true, true, false>;
+      k.pp_backward[BK_SIM] = launch_backward_staged_pp<Fam, false, false, true>;
+      k.pp_backward[BK_BOTH] = launch_backward_staged_pp<Fam, true, true, true>;
+    } else {
+      k.pp_backward[BK_MV] = launch_backward_pp<Fam, UNROLL, true, true, false, false>;
+      k.pp_backward[BK_SIM] = launch_backward_pp<Fam, UNROLL, false, false, true, false>;
+      k.pp_backward[BK_BOTH] = launch_backward_pp<Fam, UNROLL, true, true, true, false>;
+    }
     k.pp_backward[BK_LL_MEAN] = launch_backward_pp<Fam, UNROLL, true, false, false, true>;
     k.pp_backward[BK_LL_DRAW] = launch_backward_pp<Fam, UNROLL, false, false, true, true>;
   }
