@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -255,7 +256,7 @@ static long chunk_capacity(const rodeo_problem *p, long batch) {
   long cap = (long)(p->ws_limit / per);
   cap = cap / 1024 * 1024;                 // whole CTAs, 256 B aligned history rows
   if (cap < 1024) cap = 1024;
-  return std::min(cap, round_up(batch, 32));
+  return std::min(cap, round_up(batch, 256));
 }
 
 static int ensure_workspace_bytes(rodeo_problem *p, size_t need);
@@ -328,6 +329,16 @@ static int ensure_tables(rodeo_problem *p, const HostPrior &hp, cudaStream_t str
   return RODEO_OK;
 }
 
+// A/B knob for measurements: RODEO_CUDA_BACKWARD=staged selects the round-1 smoother (one thread per system,
+// one run per visit) where the thread-per-block kernel (kalman_tpb.cuh) replaced it.  Read once per process.
+static bool prefer_staged_backward() {
+  static const bool v = [] {
+    const char *e = getenv("RODEO_CUDA_BACKWARD");
+    return e && std::string(e) == "staged";
+  }();
+  return v;
+}
+
 // One pass over `batch` systems in chunks: forward kernel then backward kernel per chunk.
 static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const double *x0,
                       const double *theta, const double *z, long z_stride, double *x_out,
@@ -345,7 +356,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
                                : rodeo_cuda_history_bytes_per_system(p);
   long cap = (long)(p->ws_limit / per_system) / 1024 * 1024;
   if (cap < 1024) cap = 1024;
-  cap = std::min(cap, round_up(batch, 32));
+  cap = std::min(cap, round_up(batch, 256));   // whole 256-system blocks: the permuted history order pads to them
   int rc = ensure_workspace_bytes(p, per_system * (size_t)cap);
   if (rc) return rc;
   HostPrior hp{p->n, p->m, p->N, p->tmin, p->tmax, p->W.data(), p->Q.data(), p->c.data(), p->R.data()};
@@ -354,6 +365,14 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     if (var_out)   // ONE (N+1, n, n) array serves the whole batch in this mode
       CK(cudaMemcpyAsync(var_out, p->tab + ks->sc_table_var_offset(p->N), (size_t)T1 * n * n * sizeof(double),
                          cudaMemcpyDeviceToDevice, stream));
+  }
+  // which smoother runs: the current kernel, or the previous generation on request (A/B measurements)
+  launch_fn backward = nullptr;
+  bool perm = false;
+  if (!bp && !shared && !wide) {
+    const bool alt = prefer_staged_backward() && ks->backward_alt[slot][bk];
+    backward = alt ? ks->backward_alt[slot][bk] : ks->backward[slot][bk];
+    perm = !alt && ks->backward_perm[slot][bk];
   }
   const long n_chunks = (batch + cap - 1) / cap;
   if (p->timing) {
@@ -375,6 +394,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     a.z_stride = z_stride;
     a.hist = (double *)p->ws;
     a.ck = ck;
+    a.perm16 = perm ? 1 : 0;
     a.n_steps = p->N + 1;
     a.x_out = x_out ? x_out + off * T1 * n : nullptr;
     a.mu_out = mu_out ? mu_out + off * T1 * n : nullptr;
@@ -403,7 +423,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
                 : wide ? ks->wide_forward[p->ig](hp, a, stream) : ks->forward[p->ig](hp, a, stream));
       if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
       CK(shared ? ks->sc_backward[bk](hp, a, stream)
-                : wide ? ks->wide_backward[bk](hp, a, stream) : ks->backward[slot][bk](hp, a, stream));
+                : wide ? ks->wide_backward[bk](hp, a, stream) : backward(hp, a, stream));
     }
     if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
     p->launches += 2;

@@ -248,13 +248,27 @@ RD_UNROLL
 
 // One smoother step t+1 -> t (KalmanODE.pyx:452-461 / 417-425 / 381-392); zt_ptr = z[:, t-1].
 // The filtered covariance is re-read from the record where it is needed a second time instead
-// of being held in registers across the Cholesky / triangular solves.
-template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+// of being held in registers across the Cholesky / triangular solves (REREAD: the record lives in
+// shared or global memory; with REREAD = false it is a thread-private register array and stays live).
+template <bool REREAD>
+struct RecReader {
+  const volatile double *q;
+  RD_HD explicit RecReader(const double *p) : q(p) {}
+  RD_HD double operator[](int i) const { return q[i]; }
+};
+template <>
+struct RecReader<false> {
+  const double *q;
+  RD_HD explicit RecReader(const double *p) : q(p) {}
+  RD_HD double operator[](int i) const { return q[i]; }
+};
+
+template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool REREAD = true>
 RD_HD int smooth_step(const double *Q, const double *c, const double *R, const double *rec_mu,
                       const double *rec_S, const double *zt_ptr, double *mus, double *Ss, double *x,
                       double *dumpT = nullptr, double *dumpL = nullptr) {
   constexpr int NS = Sym<n>::size;
-  const volatile double *rec_S2 = rec_S;  // second reads: do not keep Sigma_f live
+  const RecReader<REREAD> rec_S2(rec_S);  // second reads: do not keep Sigma_f live
   double muf[n], mup[n], Sp[NS], T[n * n], invd[n];
   {
     double Sf[NS];

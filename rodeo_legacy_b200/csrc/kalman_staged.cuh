@@ -703,6 +703,7 @@ cudaError_t launch_backward_staged(const HostPrior &h, const SolveArgs &a, cudaS
   auto kern = kalman_backward_staged<Fam, CK, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
   if (e != cudaSuccess) return e;
+  if (a.perm16) return cudaErrorInvalidValue;   // the permuted history order belongs to kalman_tpb.cuh
   const long n_tiles = (a.B + kTile - 1) / kTile;
   const unsigned grid = (unsigned)((n_tiles + kStagedWarps - 1) / kStagedWarps);
   StoreMaps maps;

@@ -1,0 +1,418 @@
+// kalman_tpb.cuh -- backward (smoother) kernel of the block-diagonal family with one THREAD PER
+// DIAGONAL BLOCK and granule-aligned output through TMA tensor stores (round 2; replaces
+// kalman_staged.cuh for solve_mv / solve_sim / solve on two-block priors: the FitzHugh-Nagumo headline).
+//
+// Why (measured on B200, tools/microbench/write_pattern3.cu, FN solve_mv output = 8.83 GB):
+//   one 288-byte variance run + one 48-byte mean run per system and step (round 1)      2.43 ms  3.6 TB/s
+//   the same runs as TMA tensor / bulk stores, unaligned                                  2.5 ms
+//   ONLY whole 256-byte-aligned granules, each written once by the TMA                   1.54 ms  5.75 TB/s
+//   ... with the checkpoint-2 history read stream beside it                              1.93 ms  5.5 TB/s
+// The L2 slice hash uses address bits >= 8, so a 256-byte aligned granule lives in one slice and reaches
+// DRAM as one burst; a run that straddles granules reaches it as two partial writes at different times.
+//
+// Mapping: lane = blk * 16 + i; warp (q, j) owns the 16 systems b_i = 256 q + 16 i + j.  Sixteen systems
+// apart the trajectories are congruent modulo 256 bytes (16 * 8 * n doubles per step is a multiple of 256 for
+// even n), so the whole warp completes its output granules at the same steps: the bookkeeping is
+// warp-uniform and ONE cp.async.bulk.tensor serves all 16 systems.  The forward pass writes the history in
+// the matching permuted order (SolveArgs::perm16), so the warp's 16 systems are contiguous there.
+//   * the blocks of a system decouple in the smoother (kalman_common.cuh); only the ODE right-hand side
+//     couples them, in the re-run filter step of the checkpointed history: one shuffle per block.  Against one
+//     thread per system this doubles the resident warps per shared-memory byte and halves the FP64 chain.
+//   * history: each lane prefetches its block's p + p(p+1)/2 doubles of the NEXT checkpoint record into
+//     registers one group (CK steps) ahead (half-warp = 128 contiguous bytes per element row); no ring.
+//   * checkpoint interval CK in {1, 2}: for CK = 2 the filter is re-run from the checkpoint for one step in
+//     registers (same routines as the forward pass: bit-identical moments).
+//   * outputs: per output array the warp keeps NSLOT granule slots in shared memory, a slot being two TMA box
+//     images {16 doubles, 1, 16 systems} (2 x 2 KB, 128-byte swizzle: lane i's 16-byte chunk c sits at chunk
+//     c ^ (i & 7), which makes the row writes bank-conflict free).  A slot holds granule (x >> 8) % NSLOT of
+//     every system, x = byte offset inside the 16-system row.  Every lane writes its block's rows of the
+//     step's run (structural zeros included); when the run completes a granule, lane 0 issues one tensor
+//     store.  Trajectory ends (partial granules) and the systems of a last incomplete 16-system row are
+//     stored with plain 16-byte stores.
+// Warps never synchronise with each other.
+#pragma once
+#include <cstdint>
+
+#include "kalman_staged.cuh"
+
+namespace rodeo {
+
+constexpr int kGranule = 256;
+constexpr int kSlotBytes = 16 * kGranule;     // one granule of 16 systems
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+
+// Tensor map of one output array for the granule stores: W doubles per (system, time index).
+// Byte address = k * PITCH + x with k = system / 16 and x the offset inside the 16-system row,
+// PITCH = 16 * T1 * W * 8.  Dimensions {16 doubles, x / 128, k < B / 16}, box {16, 1, 16}: half a granule of
+// 16 systems, [system][128 bytes] in shared memory (two stores per granule).
+inline cudaError_t encode_granule_map(CUtensorMap *m, double *base, int W, long T1, long B) {
+  memset(m, 0, sizeof *m);
+  if (!base || B < 16) return cudaSuccess;     // no complete 16-system row: only plain stores are used
+  encode_tiled_fn enc = tensor_map_encoder();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t pitch = (cuuint64_t)16 * T1 * W * 8;
+  const cuuint64_t dims[3] = {16, pitch / 128, (cuuint64_t)(B / 16)};
+  const cuuint64_t strides[2] = {128, pitch};
+  const cuuint32_t box[3] = {16, 1, 16};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// shared -> global tensor store of one box, source given as a shared-state-space address
+__device__ __forceinline__ void tma_store_3d_s(const CUtensorMap *map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+struct GranuleMaps {
+  alignas(64) CUtensorMap mu, var, x;
+};
+
+// One output stream (W doubles per system and step) of one warp.  All members are warp-uniform except
+// tile_i / i7s / out_i (the lane's system).
+template <int W>
+struct GranuleStream {
+  static constexpr int RUN = W * 8;                                  // bytes per system and step
+  static constexpr int SLACK = kGranule - cgcd(RUN, kGranule);       // most bytes left pending after an emission
+  static constexpr int NSLOT = (SLACK + RUN + kGranule - 1) / kGranule;
+  static constexpr int UNITS = 2 * NSLOT;                            // 128-byte units per system in the slots
+  static constexpr int BYTES = NSLOT * kSlotBytes;
+  static_assert(W % 2 == 0, "granule stores need 16-byte run boundaries (even n_state)");
+  // row coordinates are 32-bit: the launcher checks 16 * T1 * RUN < 2^31
+  int x;           // offset of the current run inside the 16-system row (bytes): (j * T1 + t) * RUN
+  int Fx;          // everything at or above Fx (a granule boundary) is stored or not ours
+  int x_end;       // end of this warp's trajectories inside the row: (j + 1) * T1 * RUN
+  uint32_t tile;   // shared address of the slots (1024-byte aligned)
+  uint32_t tile_i; // tile + i * 128
+  uint32_t i7s;    // (i & 7) << 4: the swizzle of this lane's row
+  char *out_i;     // array + (system / 16) * PITCH: this lane's row base in global memory
+  __device__ __forceinline__ void init(uint32_t tile_, int i, double *out, long k_row, int j, long T1) {
+    x_end = (int)((j + 1) * T1 * RUN);
+    x = x_end;
+    Fx = (x_end + kGranule - 1) & ~(kGranule - 1);
+    tile = tile_;
+    tile_i = tile + (uint32_t)i * 128u;
+    i7s = (uint32_t)(i & 7) << 4;
+    out_i = reinterpret_cast<char *>(out) + k_row * (16 * T1 * RUN);
+  }
+  __device__ __forceinline__ void advance() { x -= RUN; }
+  // shared address of byte xx (a multiple of 8) of this lane's system
+  __device__ __forceinline__ uint32_t phys(int xx) const {
+    const uint32_t u = (uint32_t)xx;
+    return tile_i + (((u >> 7) % UNITS) << 11) + (((u & 0x70u) ^ i7s) | (u & 8u));
+  }
+  // CNT doubles of the current run starting at byte offset rb (lane dependent) of the run
+  template <int CNT>
+  __device__ __forceinline__ void put_pairs(int rb, const double *v) const {
+    const int xb = x + rb;
+#pragma unroll
+    for (int k = 0; k < CNT; k += 2)
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(phys(xb + 8 * k)), "d"(v[k]), "d"(v[k + 1]) : "memory");
+  }
+  template <int CNT>
+  __device__ __forceinline__ void put_singles(int rb, const double *v) const {
+    const int xb = x + rb;
+#pragma unroll
+    for (int k = 0; k < CNT; k++) asm volatile("st.shared.f64 [%0], %1;" ::"r"(phys(xb + 8 * k)), "d"(v[k]) : "memory");
+  }
+  // bytes [xa, xb) of this lane's system with plain 16-byte loads / stores (generic proxy)
+  __device__ __forceinline__ void copy_lsu(int xa, int xb) const {
+    for (int xx = xa; xx < xb; xx += 16) {
+      double v0, v1;
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(phys(xx)));
+      *reinterpret_cast<double2 *>(out_i + xx) = make_double2(v0, v1);
+    }
+  }
+  // After the run of time index t is in the slots (and fenced): store what it completed.
+  //   full_row: this warp has systems in complete 16-system rows (lane 0 issues the tensor stores)
+  //   mine:     this lane stores its system's partial granules (one lane per valid system)
+  //   tail_row: this lane's system sits in the last, incomplete row: it stores whole granules itself too
+  __device__ __forceinline__ void emit(const CUtensorMap *map, int t, int row0, bool full_row, bool lane0, bool mine,
+                                       bool tail_row) {
+    const int c = (t == 0) ? x : (x + kGranule - 1) & ~(kGranule - 1);
+    for (int g0 = (c + kGranule - 1) & ~(kGranule - 1); g0 < Fx; g0 += kGranule) {
+      if (g0 + kGranule > x_end) {                     // the top granule is shared with the next trajectory
+        if (mine) copy_lsu(g0, x_end);
+      } else {
+        if (full_row && lane0) {
+          const uint32_t src = tile + ((((uint32_t)g0 >> 8) % NSLOT) << 12);
+          tma_store_3d_s(map, src, 0, g0 >> 7, row0);
+          tma_store_3d_s(map, src + 2048u, 0, (g0 >> 7) + 1, row0);
+        }
+        if (mine && tail_row) copy_lsu(g0, g0 + kGranule);
+      }
+    }
+    if (t == 0 && (c & (kGranule - 1))) {              // the bottom granule is shared with the previous trajectory
+      const int top = (c + kGranule - 1) & ~(kGranule - 1);
+      if (mine) copy_lsu(c, top < x_end ? top : x_end);
+    }
+    Fx = (c + kGranule - 1) & ~(kGranule - 1);
+  }
+};
+
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+struct TpbLayout {
+  static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
+  static_assert(nb == 2, "thread-per-block smoother: two diagonal blocks (16 systems x 2 blocks per warp)");
+  static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
+  using SVec = GranuleStream<n>;
+  using SVar = GranuleStream<n * n>;
+  static constexpr int OFF_MEAN = 0;
+  static constexpr int OFF_X = OFF_MEAN + (DO_MEAN ? SVec::BYTES : 0);
+  static constexpr int OFF_VAR = OFF_X + (DO_SIM ? SVec::BYTES : 0);
+  static constexpr int WARP_BYTES = OFF_VAR + (DO_VAR ? SVar::BYTES : 0);      // a multiple of 4096
+  static constexpr int WARPS = 2;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr size_t smem_bytes = (size_t)WARPS * WARP_BYTES + 1024;      // + alignment slack (1024-byte swizzle atoms)
+};
+
+// The prior of the lane's block: immediate constant-bank operands when every block has the same Q, R, w, c
+// (what ibm_init with equal sigma / n_deriv_prior gives, every BASELINE config), per-lane register copies otherwise.
+template <class Fam, bool UNIFORM>
+struct BlockPrior;
+template <class Fam>
+struct BlockPrior<Fam, true> {
+  const typename Fam::PriorT &P;
+  __device__ __forceinline__ BlockPrior(const typename Fam::PriorT &P_, int) : P(P_) {}
+  __device__ __forceinline__ const double *Q() const { return P.Q[0]; }
+  __device__ __forceinline__ const double *R() const { return P.R[0]; }
+  __device__ __forceinline__ const double *w() const { return P.w[0]; }
+  __device__ __forceinline__ const double *c() const { return P.c; }
+};
+template <class Fam>
+struct BlockPrior<Fam, false> {
+  static constexpr int p = Fam::p, PS = Fam::PS;
+  double q_[p * p], r_[PS], w_[p], c_[p];
+  __device__ __forceinline__ BlockPrior(const typename Fam::PriorT &P, int blk) {
+#pragma unroll
+    for (int i = 0; i < p * p; i++) q_[i] = P.Q[blk][i];
+#pragma unroll
+    for (int i = 0; i < PS; i++) r_[i] = P.R[blk][i];
+#pragma unroll
+    for (int i = 0; i < p; i++) {
+      w_[i] = P.w[blk][i];
+      c_[i] = P.c[blk * p + i];
+    }
+  }
+  __device__ __forceinline__ const double *Q() const { return q_; }
+  __device__ __forceinline__ const double *R() const { return r_; }
+  __device__ __forceinline__ const double *w() const { return w_; }
+  __device__ __forceinline__ const double *c() const { return c_; }
+};
+
+__device__ __forceinline__ double ld_once(const double *p) {
+  double v;   // volatile: loaded where it is written and kept (never re-loaded inside the time loop)
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;   // volatile: keeps the prefetch where it is written (a group ahead of its use)
+  asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+template <class Fam, int CK, bool UNIFORM, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+__global__ void __launch_bounds__(TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::THREADS)
+kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
+                    const __grid_constant__ GranuleMaps maps) {
+  using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
+  using Ode = typename Fam::Ode;
+  constexpr int p = L::p, nb = L::nb, n = L::n, PS = L::PS, NE = Fam::NE;
+  constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+  constexpr unsigned kFull = 0xffffffffu;
+  extern __shared__ unsigned char smem_raw[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long wg = (long)blockIdx.x * L::WARPS + warp;     // warp index in the grid
+  const long q = wg >> 4;
+  const int j = (int)(wg & 15);
+  if (256 * q + j >= a.B) return;                          // warp-uniform; warps are independent
+  const int blk = lane >> 4, i = lane & 15;
+  const long b = 256 * q + 16 * i + j;                     // this lane's system
+  const bool valid = b < a.B;
+  const long bs = valid ? b : 256 * q + j;                 // a safe system for the loads of idle lanes
+  const long upos = 256 * q + 16 * j + i;                  // its position in the (permuted) history
+  const int N = P.n_eval, R = n_records(N, CK);
+  const long T1 = (long)N + 1;
+  const BlockPrior<Fam, UNIFORM> bp(P, blk);
+
+  // ---- output streams -------------------------------------------------------------------------------
+  const uint32_t tile = ((smem_u32(smem_raw) + 1023u) & ~1023u) + (uint32_t)warp * L::WARP_BYTES;
+  const long k_row = 16 * q + i;                           // b / 16
+  const long full_rows = a.B / 16;
+  const bool full_row = 16 * q < full_rows;                // the tensor stores of this warp have rows to write
+  const bool tail_row = k_row >= full_rows;                // (valid lanes) stored with plain stores only
+  const bool mine = valid && blk == 0, lane0 = lane == 0;
+  typename L::SVec sm, sx;
+  typename L::SVar sv;
+  if (DO_MEAN) sm.init(tile + L::OFF_MEAN, i, a.mu_out, k_row, j, T1);
+  if (DO_SIM) sx.init(tile + L::OFF_X, i, a.x_out, k_row, j, T1);
+  if (DO_VAR) sv.init(tile + L::OFF_VAR, i, a.var_out, k_row, j, T1);
+
+  auto emit = [&](int t, const double *mus, const double *Ss, const double *x) {
+    if (lane0) tma_wait_read();   // the earlier tensor stores have left the slots
+    __syncwarp();
+    if (DO_MEAN) {
+      sm.advance();
+      sm.template put_singles<p>(blk * p * 8, mus);
+    }
+    if (DO_SIM) {
+      sx.advance();
+      sx.template put_singles<p>(blk * p * 8, x);
+    }
+    if (DO_VAR) {
+      sv.advance();
+      // rows blk*p .. blk*p+p-1 of the n x n matrix (the reference's var[t][j][i]; symmetric), zeros outside the block
+#pragma unroll
+      for (int jj = 0; jj < p; jj++) {
+        double row[n];
+#pragma unroll
+        for (int c = 0; c < n; c++) row[c] = (blk == c / p) ? Ss[sidx<p>(c % p, jj)] : 0.0;
+        sv.template put_pairs<n>((blk * p + jj) * n * 8, row);
+      }
+    }
+    fence_proxy_async();   // the rows (generic proxy) become visible to the tensor stores (async proxy) ...
+    __syncwarp();          // ... of every lane, before lane 0 issues them
+    const int row0 = (int)(16 * q);
+    if (DO_VAR) sv.emit(&maps.var, t, row0, full_row, lane0, mine, tail_row);
+    if (DO_MEAN) sm.emit(&maps.mu, t, row0, full_row, lane0, mine, tail_row);
+    if (DO_SIM) sx.emit(&maps.x, t, row0, full_row, lane0, mine, tail_row);
+    if (lane0) tma_commit();
+  };
+
+  // ---- history: this block's elements of record r --------------------------------------------------------
+  const double *hb = a.hist + hist_offset(upos, 0, R, NE);
+  auto load_rec = [&](int r, double *mu, double *S) {
+    const double *h = hb + (size_t)r * NE * kTile;
+#pragma unroll
+    for (int e = 0; e < p; e++) mu[e] = ld_stream(h + (blk * p + e) * kTile);
+#pragma unroll
+    for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
+  };
+
+  // theta and x0 are loaded ONCE with volatile loads: left to the compiler, the x0 load of the last group
+  // (base < 1) is speculated into every group and its L2 latency lands on the critical path
+  double th[NT], x0b[p];
+#pragma unroll
+  for (int e = 0; e < p; e++) x0b[e] = ld_once(a.x0 + bs * n + blk * p + e);
+#pragma unroll
+  for (int e = 0; e < NT; e++) th[e] = (Ode::n_theta > 0 && CK > 1) ? ld_once(a.theta + bs * Ode::n_theta + e) : 0.0;
+  const double *zb = DO_SIM ? a.z + bs * a.z_stride + blk * p : nullptr;
+
+  double mus[p], Ss[PS], x[p];
+  double cm[p], cS[PS], nm[p], nS[PS];     // current / prefetched checkpoint record (this block)
+  int fail = 0;
+  load_rec(0, cm, cS);
+  if (R > 1) load_rec(1, nm, nS);
+  {  // terminal time index N = record 0
+    fail = reg::smooth_terminal<p, 1, DO_MEAN, DO_VAR, DO_SIM>(cm, cS, DO_SIM ? zb + (long)(N - 1) * n : nullptr, mus, Ss, x);
+    emit(N, mus, Ss, x);
+  }
+  int r = 1;
+  for (int t_hi = N; t_hi > 1;) {   // this group smooths time indices t_hi-1 .. max(t_hi-CK, 1)
+    const int base = t_hi - CK;
+    if (base >= 1) {
+#pragma unroll
+      for (int e = 0; e < p; e++) cm[e] = nm[e];
+#pragma unroll
+      for (int e = 0; e < PS; e++) cS[e] = nS[e];
+      if (r + 1 < R) load_rec(r + 1, nm, nS);            // one group ahead
+    }
+    if (CK == 2) {
+      const int t0 = base >= 1 ? base : 0;
+      if (base < 1) {   // the known initial state (KalmanODE.pyx:293-297)
+#pragma unroll
+        for (int e = 0; e < p; e++) cm[e] = x0b[e];
+#pragma unroll
+        for (int e = 0; e < PS; e++) cS[e] = 0.0;
+      }
+      if (t_hi - 1 > t0) {
+        // re-run the filter t0 -> t0 + 1 (BdFam::step, this block's share; the right-hand side needs every
+        // block's predicted first component: one shuffle per block)
+        double fm[p], fS[PS];
+        reg::predict_mean<p>(bp.Q(), bp.c(), cm, fm);
+        reg::predict_var<p, false>(bp.Q(), bp.R(), cS, fS, nullptr);
+        double X[n], y[Fam::m];
+#pragma unroll
+        for (int e = 0; e < n; e++) X[e] = 0.0;
+#pragma unroll
+        for (int k = 0; k < nb; k++) X[k * p] = __shfl_sync(kFull, fm[0], k * 16 + i);
+        const double tt = P.tmin + (P.tmax - P.tmin) * (t0 + 1) / P.n_eval;
+        Ode::template eval<n>(X, tt, th, y);
+        double ya = y[0];
+#pragma unroll
+        for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
+        reg::update_block<p>(bp.w(), fm, fS, ya, false);
+        const int t = t0 + 1;
+        const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false>(
+            bp.Q(), bp.c(), bp.R(), fm, fS, DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
+        if (f && !fail) fail = f;
+        emit(t, mus, Ss, x);
+      }
+    }
+    if (base >= 1) {
+      const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false>(
+          bp.Q(), bp.c(), bp.R(), cm, cS, DO_SIM ? zb + (long)(base - 1) * n : nullptr, mus, Ss, x);
+      if (f && !fail) fail = f;
+      emit(base, mus, Ss, x);
+    }
+    t_hi = base >= 1 ? base : 1;
+    r++;
+  }
+  {  // time index 0: the initial state is known, Sigma_0 = 0 (KalmanODE.pyx:445, 409)
+#pragma unroll
+    for (int e = 0; e < p; e++) {
+      const double v = x0b[e];
+      mus[e] = v;
+      x[e] = v;
+    }
+#pragma unroll
+    for (int e = 0; e < PS; e++) Ss[e] = 0.0;
+    emit(0, mus, Ss, x);
+  }
+  if (lane0) tma_wait_all();
+  if (valid && a.status && fail) atomicCAS(a.status + b, 0, blk * p + fail);
+}
+
+// every block has the same Q, R, w and c?
+template <class Fam>
+inline bool blocks_uniform(const typename Fam::PriorT &P) {
+  constexpr int p = Fam::p, nb = Fam::nb, PS = Fam::PS;
+  for (int k = 1; k < nb; k++) {
+    for (int i = 0; i < p * p; i++)
+      if (P.Q[k][i] != P.Q[0][i]) return false;
+    for (int i = 0; i < PS; i++)
+      if (P.R[k][i] != P.R[0][i]) return false;
+    for (int i = 0; i < p; i++)
+      if (P.w[k][i] != P.w[0][i] || P.c[k * p + i] != P.c[i]) return false;
+  }
+  return true;
+}
+
+// Needs SolveArgs::perm16 = 1 (the forward pass wrote the history in the permuted order).
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+cudaError_t launch_backward_tpb(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
+  if (!a.perm16) return cudaErrorInvalidValue;
+  if ((double)16 * a.n_steps * Fam::n * Fam::n * 8 >= 2147483648.0) return cudaErrorInvalidValue;   // 32-bit row coordinates
+  const typename Fam::PriorT P = make_prior<Fam>(h);
+  const bool uni = blocks_uniform<Fam>(P);
+  auto kern = uni ? kalman_backward_tpb<Fam, CK, true, DO_MEAN, DO_VAR, DO_SIM>
+                  : kalman_backward_tpb<Fam, CK, false, DO_MEAN, DO_VAR, DO_SIM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
+  if (e != cudaSuccess) return e;
+  GranuleMaps maps;
+  constexpr int n = Fam::n;
+  if ((e = encode_granule_map(&maps.mu, DO_MEAN ? a.mu_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
+  if ((e = encode_granule_map(&maps.x, DO_SIM ? a.x_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
+  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
+  const long n_warps = (a.B + 255) / 256 * 16;
+  const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
+  kern<<<grid, L::THREADS, L::smem_bytes, s>>>(P, a, maps);
+  return cudaGetLastError();
+}
+
+}  // namespace rodeo

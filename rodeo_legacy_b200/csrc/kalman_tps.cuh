@@ -34,6 +34,7 @@ struct SolveArgs {
   long z_stride;       // 0: shared, n*N: per system
   double *hist;        // [ceil(B/32)][R][NE][32], R = n_records(N, ck)
   int ck;              // checkpoint interval: records exist for time indices N, N-ck, N-2ck, ... >= 1
+  int perm16;          // history position of system b is perm16(b) (kalman_common.cuh), else b
   int n_steps;         // N + 1 (time points per system in the outputs)
   double *x_out, *mu_out, *var_out;
   int *status;

@@ -156,6 +156,7 @@ RD_UNROLL
 RD_UNROLL
   for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
   const int N = P.n_eval, ck = a.ck, R = n_records(N, ck);
+  const long hpos = a.perm16 ? perm16(b) : b;     // position of this system in the history
   const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
   int fail = 0;
   for (int t = 0; t < N; t++) {
@@ -163,7 +164,7 @@ RD_UNROLL
     if (f && !fail) fail = f;
     const int back = N - (t + 1);                 // distance of time index t+1 from the end
     if (back % ck == 0) {
-      double *h = a.hist + hist_offset(b, back / ck, R, NE);
+      double *h = a.hist + hist_offset(hpos, back / ck, R, NE);
 RD_UNROLL
       for (int i = 0; i < n; i++) h[i * kTile] = mu[i];
 RD_UNROLL
@@ -233,6 +234,7 @@ RD_HD void backward_body(const typename Fam::PriorT &P, const SolveArgs &a, long
   constexpr int n = Fam::n, NS = Fam::NS, NE = Fam::NE;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
   const int N = P.n_eval, R = n_records(N, CK);
+  const long hpos = a.perm16 ? perm16(b) : b;     // position of this system in the history
   double mus[n], Ss[NS], x[n], th[NT];
   int fail = 0;
   double lp = 0.0;
@@ -243,7 +245,7 @@ RD_UNROLL
     for (int i = 0; i < NT; i++) th[i] = (Ode::n_theta > 0) ? a.theta[b * Ode::n_theta + i] : 0.0;
   }
   {  // terminal time index N = record 0
-    const double *rec = a.hist + hist_offset(b, 0, R, NE);
+    const double *rec = a.hist + hist_offset(hpos, 0, R, NE);
     fail = Fam::template bw_terminal<kTile, DO_MEAN, DO_VAR, DO_SIM>(P, rec, DO_SIM ? zb + (long)(N - 1) * n : nullptr,
                                                                      mus, Ss, x);
     emit_time<Fam, DO_MEAN, DO_VAR, DO_SIM, LOGLIK>(a, b, N, mus, Ss, x, lp, d);
@@ -252,7 +254,7 @@ RD_UNROLL
   for (int t_hi = N; t_hi > 1;) {   // times t_hi-1 .. max(t_hi-CK, 1) are smoothed in this group
     const int base = t_hi - CK;      // checkpointed time index of the group, if >= 1
     if (CK == 1) {
-      const double *rec = a.hist + hist_offset(b, r, R, NE);
+      const double *rec = a.hist + hist_offset(hpos, r, R, NE);
       int f = Fam::template bw_step<kTile, DO_MEAN, DO_VAR, DO_SIM>(P, rec, DO_SIM ? zb + (long)(base - 1) * n : nullptr,
                                                                     mus, Ss, x);
       if (f && !fail) fail = f;
@@ -264,7 +266,7 @@ RD_UNROLL
       const int t0 = base >= 1 ? base : 0;
       const int nfwd = t_hi - 1 - t0;  // recomputed time indices t0+1 .. t_hi-1
       if (base >= 1) {
-        const double *rec = a.hist + hist_offset(b, r, R, NE);
+        const double *rec = a.hist + hist_offset(hpos, r, R, NE);
 RD_UNROLL
         for (int i = 0; i < NE; i++) cur[i] = rec[i * kTile];
       } else {

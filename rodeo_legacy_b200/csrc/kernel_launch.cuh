@@ -51,12 +51,14 @@ inline typename Fam::PriorT make_prior(const HostPrior &h) {
 #include "kalman_staged.cuh"
 #include "kalman_bdw.cuh"
 #include "kalman_sc.cuh"
+#include "kalman_tpb.cuh"
 namespace rodeo {
 
 template <class Fam, bool UNROLL, int IG>
 __global__ void __launch_bounds__(kThreadsPerBlock)
 kalman_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
-  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;   // history position (coalesced stores)
+  const long b = a.perm16 ? perm16(u) : u;
   if (b < a.B) Bodies<UNROLL>::template forward<Fam, IG>(P, a, b);
 }
 
@@ -97,7 +99,8 @@ inline dim3 grid_for(long B) { return dim3((unsigned)((B + kThreadsPerBlock - 1)
 
 template <class Fam, bool UNROLL, int IG>
 cudaError_t launch_forward(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
-  kalman_forward<Fam, UNROLL, IG><<<grid_for(a.B), kThreadsPerBlock, 0, s>>>(make_prior<Fam>(h), a);
+  kalman_forward<Fam, UNROLL, IG><<<grid_for(a.perm16 ? (a.B + 255) / 256 * 256 : a.B), kThreadsPerBlock, 0, s>>>(
+      make_prior<Fam>(h), a);
   return cudaGetLastError();
 }
 
@@ -137,6 +140,17 @@ void fill_backward(KernelSet &k) {
     } else {
       return;   // leaves this slot empty: the API falls back to interval 1 for this family
     }
+  } else if constexpr (UNROLL && BD && Ode::n_meas == 2 && (CK == 1 || CK == 2)) {
+    // two diagonal blocks (FitzHugh-Nagumo): one thread per block, history prefetched into registers,
+    // outputs as whole 256-byte-aligned granules through TMA tensor stores (kalman_tpb.cuh); these
+    // launchers need the history in the permuted order (backward_perm -> SolveArgs::perm16)
+    k.backward[CKI][BK_MV] = launch_backward_tpb<Fam, CK, true, true, false>;
+    k.backward[CKI][BK_SIM] = launch_backward_tpb<Fam, CK, false, false, true>;
+    k.backward[CKI][BK_BOTH] = launch_backward_tpb<Fam, CK, true, true, true>;
+    k.backward_perm[CKI][BK_MV] = k.backward_perm[CKI][BK_SIM] = k.backward_perm[CKI][BK_BOTH] = true;
+    k.backward_alt[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
+    k.backward_alt[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
+    k.backward_alt[CKI][BK_BOTH] = launch_backward_staged<Fam, CK, true, true, true>;
   } else if constexpr (UNROLL) {  // registers: history and outputs staged through shared memory
     k.backward[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
     k.backward[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
@@ -170,7 +184,10 @@ KernelSet make_kernel_set(const char *name) {
   k.forward[IG_SCHOBERT] = launch_forward<Fam, UNROLL, IG_SCHOBERT>;
   k.forward[IG_CHKREBTII] = launch_forward<Fam, UNROLL, IG_CHKREBTII>;
   for (int c = 0; c < kNumCk; c++)
-    for (int b = 0; b < BK_COUNT; b++) k.backward[c][b] = nullptr;
+    for (int b = 0; b < BK_COUNT; b++) {
+      k.backward[c][b] = k.backward_alt[c][b] = nullptr;
+      k.backward_perm[c][b] = false;
+    }
   fill_backward<Fam, Ode, BD, UNROLL, 1, 0>(k);
   if constexpr (UNROLL) {  // checkpointed history for the register families only
     fill_backward<Fam, Ode, BD, UNROLL, 2, 1>(k);

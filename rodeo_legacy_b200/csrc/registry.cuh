@@ -33,6 +33,9 @@ struct KernelSet {
   const char *name;
   launch_fn forward[3];           // by interrogation variant
   launch_fn backward[kNumCk][BK_COUNT];  // by checkpoint slot and BackwardKind (nullptr: not compiled)
+  // the previous generation of a kernel where one is kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
+  launch_fn backward_alt[kNumCk][BK_COUNT];
+  bool backward_perm[kNumCk][BK_COUNT];  // backward[][] wants the history in the permuted order (SolveArgs::perm16)
   int hist_elems;                 // doubles of history per system per step
   // shared-covariance mode (kalman_sc.cuh); all nullptr when not compiled for this set
   cudaError_t (*sc_tables)(const HostPrior &, int zero_H, double *tab, int *fail_out, cudaStream_t);
