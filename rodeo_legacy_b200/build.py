@@ -23,7 +23,9 @@ NVCC_FLAGS = [
 ] + (["-DRODEO_DEBUG_RING"] if os.environ.get("RODEO_DEBUG_RING") else []) \
   + (["-DRODEO_DEBUG_POISON"] if os.environ.get("RODEO_DEBUG_POISON") else []) \
   + ([f"-DRODEO_BDW_MIN_BLOCKS={os.environ['RODEO_BDW_MIN_BLOCKS']}"] if os.environ.get("RODEO_BDW_MIN_BLOCKS") else []) \
-  + ([f"-DRODEO_STAGED_WARPS={os.environ['RODEO_STAGED_WARPS']}"] if os.environ.get("RODEO_STAGED_WARPS") else [])
+  + ([f"-DRODEO_STAGED_WARPS={os.environ['RODEO_STAGED_WARPS']}"] if os.environ.get("RODEO_STAGED_WARPS") else []) \
+  + ([f"-DRODEO_TPB_WARPS={os.environ['RODEO_TPB_WARPS']}"] if os.environ.get("RODEO_TPB_WARPS") else []) \
+  + ([f"-DRODEO_TPB_MAXNREG={os.environ['RODEO_TPB_MAXNREG']}"] if os.environ.get("RODEO_TPB_MAXNREG") else [])
 
 
 def nvcc():

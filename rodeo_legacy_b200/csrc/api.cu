@@ -420,7 +420,9 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
       CK(wide_pp ? ks->wide_pp_backward[bk](hp, c, a, stream) : ks->pp_backward[bk](hp, c, a, stream));
     } else {
       CK(shared ? ks->sc_forward(hp, a, stream)
-                : wide ? ks->wide_forward[p->ig](hp, a, stream) : ks->forward[p->ig](hp, a, stream));
+                : wide ? ks->wide_forward[p->ig](hp, a, stream)
+                       : (perm && ks->forward_perm[p->ig]) ? ks->forward_perm[p->ig](hp, a, stream)
+                                                           : ks->forward[p->ig](hp, a, stream));
       if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
       CK(shared ? ks->sc_backward[bk](hp, a, stream)
                 : wide ? ks->wide_backward[bk](hp, a, stream) : backward(hp, a, stream));

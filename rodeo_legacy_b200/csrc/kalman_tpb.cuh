@@ -165,8 +165,15 @@ struct TpbLayout {
   static constexpr int OFF_X = OFF_MEAN + (DO_MEAN ? SVec::BYTES : 0);
   static constexpr int OFF_VAR = OFF_X + (DO_SIM ? SVec::BYTES : 0);
   static constexpr int WARP_BYTES = OFF_VAR + (DO_VAR ? SVar::BYTES : 0);      // a multiple of 4096
-  static constexpr int WARPS = 2;
+#ifndef RODEO_TPB_WARPS
+#define RODEO_TPB_WARPS 2
+#endif
+#ifndef RODEO_TPB_MINB
+#define RODEO_TPB_MINB 1
+#endif
+  static constexpr int WARPS = RODEO_TPB_WARPS;
   static constexpr int THREADS = WARPS * 32;
+  static constexpr int MINB = RODEO_TPB_MINB;
   static constexpr size_t smem_bytes = (size_t)WARPS * WARP_BYTES + 1024;      // + alignment slack (1024-byte swizzle atoms)
 };
 
@@ -217,6 +224,9 @@ __device__ __forceinline__ double ld_stream(const double *p) {
 
 template <class Fam, int CK, bool UNIFORM, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 __global__ void __launch_bounds__(TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::THREADS)
+#ifdef RODEO_TPB_MAXNREG
+__maxnreg__(RODEO_TPB_MAXNREG)
+#endif
 kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
                     const __grid_constant__ GranuleMaps maps) {
   using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
@@ -390,6 +400,108 @@ inline bool blocks_uniform(const typename Fam::PriorT &P) {
       if (P.w[k][i] != P.w[0][i] || P.c[k * p + i] != P.c[i]) return false;
   }
   return true;
+}
+
+// Forward filter with the same mapping (lane = blk * 16 + i, warp (q, j) owns systems 256 q + 16 i + j): each lane
+// runs its block's predict / update (BdFam::step, same routines: bit-identical moments), the blocks exchange the
+// first component of the predicted mean (or of the chkrebtii draw) for the right-hand side with one shuffle
+// each, and the filtered records go to the permuted history position 256 q + 16 j + i: a half-warp stores
+// 128 contiguous bytes per element row.  Half the dependent FP64 chain per step and twice the warps of the
+// thread-per-system kernel (which stays for the unpermuted order).
+template <class Fam, int IG, bool UNIFORM>
+__global__ void __launch_bounds__(128)
+kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  using Ode = typename Fam::Ode;
+  constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS, NE = Fam::NE;
+  constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(nb == 2, "thread-per-block forward: two diagonal blocks");
+  const int lane = threadIdx.x % 32;
+  const long wg = ((long)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const long q = wg >> 4;
+  const int j = (int)(wg & 15);
+  if (256 * q + j >= a.B) return;
+  const int blk = lane >> 4, i = lane & 15;
+  const long b = 256 * q + 16 * i + j;
+  const bool valid = b < a.B;
+  const long bs = valid ? b : 256 * q + j;
+  const long upos = 256 * q + 16 * j + i;
+  const BlockPrior<Fam, UNIFORM> bp(P, blk);
+  const int N = P.n_eval, ck = a.ck, R = n_records(N, ck);
+  double mu[p], S[PS], th[NT];
+#pragma unroll
+  for (int e = 0; e < p; e++) mu[e] = a.x0[bs * n + blk * p + e];
+#pragma unroll
+  for (int e = 0; e < PS; e++) S[e] = 0.0;
+#pragma unroll
+  for (int e = 0; e < NT; e++) th[e] = (Ode::n_theta > 0) ? a.theta[bs * Ode::n_theta + e] : 0.0;
+  const double *zb = (IG == IG_CHKREBTII) ? a.z + bs * a.z_stride + blk * p : nullptr;
+  double *hb = a.hist + hist_offset(upos, 0, R, NE);
+  int t_fail = 0x7fffffff;     // first time index at which this block's innovation variance was not positive
+  int back = N - 1;            // distance of time index t + 1 from the end
+  int until = back % ck;       // steps until the next stored record
+  for (int t = 0; t < N; t++, back--) {
+    double mup[p], Sp[PS];
+    reg::predict_mean<p>(bp.Q(), bp.c(), mu, mup);
+    reg::predict_var<p, false>(bp.Q(), bp.R(), S, Sp, nullptr);
+    double X[n], y[Fam::m], lead = mup[0];
+    int f = 0;
+    if (IG == IG_CHKREBTII) {   // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
+      double xs[p], V[PS], zt[p];
+#pragma unroll
+      for (int e = 0; e < PS; e++) V[e] = Sp[e];
+#pragma unroll
+      for (int e = 0; e < p; e++) zt[e] = zb[(long)t * n + e];
+      f = reg::state_sim<p>(xs, mup, V, zt);
+      lead = xs[0];
+    }
+#pragma unroll
+    for (int e = 0; e < n; e++) X[e] = 0.0;
+#pragma unroll
+    for (int k = 0; k < nb; k++) X[k * p] = __shfl_sync(kFull, lead, k * 16 + i);
+    const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / P.n_eval;
+    Ode::template eval<n>(X, tt, th, y);
+    double ya = y[0];
+#pragma unroll
+    for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
+    const int f2 = reg::update_block<p>(bp.w(), mup, Sp, ya, IG == IG_SCHOBERT);
+    if ((f | f2) && t_fail == 0x7fffffff) t_fail = t;
+#pragma unroll
+    for (int e = 0; e < p; e++) mu[e] = mup[e];
+#pragma unroll
+    for (int e = 0; e < PS; e++) S[e] = Sp[e];
+    if (until == 0) {
+      double *h = hb + (size_t)(back / ck) * NE * kTile;
+#pragma unroll
+      for (int e = 0; e < p; e++) __stcs(h + (blk * p + e) * kTile, mu[e]);
+#pragma unroll
+      for (int e = 0; e < PS; e++) __stcs(h + (n + blk * PS + e) * kTile, S[e]);
+      until = ck;
+    }
+    until--;
+  }
+  // status = 1 + index of the first block (in (time, block) order) that failed, as BdFam::step reports it
+  int best_t = t_fail, best_blk = blk;
+#pragma unroll
+  for (int k = 0; k < nb; k++) {
+    const int tk = __shfl_sync(kFull, t_fail, k * 16 + i);
+    if (tk < best_t || (tk == best_t && k < best_blk)) {
+      best_t = tk;
+      best_blk = k;
+    }
+  }
+  if (valid && blk == 0 && a.status) a.status[b] = best_t == 0x7fffffff ? 0 : best_blk + 1;
+}
+
+template <class Fam, int IG>
+cudaError_t launch_forward_tpb(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  if (!a.perm16) return cudaErrorInvalidValue;
+  const typename Fam::PriorT P = make_prior<Fam>(h);
+  const long n_warps = (a.B + 255) / 256 * 16;
+  const unsigned grid = (unsigned)((n_warps + 3) / 4);
+  if (blocks_uniform<Fam>(P)) kalman_forward_tpb<Fam, IG, true><<<grid, 128, 0, s>>>(P, a);
+  else kalman_forward_tpb<Fam, IG, false><<<grid, 128, 0, s>>>(P, a);
+  return cudaGetLastError();
 }
 
 // Needs SolveArgs::perm16 = 1 (the forward pass wrote the history in the permuted order).

@@ -183,6 +183,12 @@ KernelSet make_kernel_set(const char *name) {
   k.forward[IG_PROBDE] = launch_forward<Fam, UNROLL, IG_PROBDE>;
   k.forward[IG_SCHOBERT] = launch_forward<Fam, UNROLL, IG_SCHOBERT>;
   k.forward[IG_CHKREBTII] = launch_forward<Fam, UNROLL, IG_CHKREBTII>;
+  k.forward_perm[0] = k.forward_perm[1] = k.forward_perm[2] = nullptr;
+  if constexpr (UNROLL && BD && Ode::n_meas == 2) {   // thread-per-block forward (kalman_tpb.cuh)
+    k.forward_perm[IG_PROBDE] = launch_forward_tpb<Fam, IG_PROBDE>;
+    k.forward_perm[IG_SCHOBERT] = launch_forward_tpb<Fam, IG_SCHOBERT>;
+    k.forward_perm[IG_CHKREBTII] = launch_forward_tpb<Fam, IG_CHKREBTII>;
+  }
   for (int c = 0; c < kNumCk; c++)
     for (int b = 0; b < BK_COUNT; b++) {
       k.backward[c][b] = k.backward_alt[c][b] = nullptr;

@@ -32,6 +32,7 @@ struct KernelSet {
   bool registers;                 // fully unrolled register kernels (else rolled / local memory)
   const char *name;
   launch_fn forward[3];           // by interrogation variant
+  launch_fn forward_perm[3];      // forward pass that writes the permuted history order (nullptr: forward[] honours perm16)
   launch_fn backward[kNumCk][BK_COUNT];  // by checkpoint slot and BackwardKind (nullptr: not compiled)
   // the previous generation of a kernel where one is kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
   launch_fn backward_alt[kNumCk][BK_COUNT];
