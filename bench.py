@@ -8,11 +8,17 @@ n_eval 400, 65,536 theta draws per GPU, solve_mv (posterior mean + variance for 
 system and time point).  For N > 1 launch under torchrun (one rank per GPU); the batch is
 replicated per rank (weak scaling), no collective on the data path.
 
-Prints ONE JSON line (rank 0).  `value` times the device-pointer entry point with inputs
-resident in HBM; `e2e` times the host-buffer entry point (pinned host buffers, H2D of the
-inputs and D2H of every output inside the timed region); `roofline` is the dominant
-(backward) kernel against the measured HBM bandwidth with SURVEY section 8(d)'s algorithmic bytes;
-`cpu_baseline` is the C oracle (a port of the reference's arithmetic) on the host cores.
+Prints ONE JSON line (rank 0):
+  value        device-pointer entry point, inputs resident in HBM, CUDA events, max over ranks
+  e2e          host-buffer entry point (pinned host buffers; H2D of the inputs and D2H of every output inside the
+               timed region), the SAME 65,536-system batch per GPU at every N, with a per-rank H2D / D2H probe
+  roofline     the dominant (smoother) kernel: `frac` = DRAM bytes it moves / its average time over the timed
+               steps / measured HBM copy bandwidth -- the bytes are computed from the data layout (history records
+               read + outputs written) and checked against the committed ncu figure; `algorithmic_frac` keeps
+               SURVEY section 8(d)'s reference-layout bytes beside it.  The forward kernel has the same block.
+  c5_sweep     BASELINE configs[4]: the 1,048,576-theta log-likelihood sweep, STRONG-scaled (sharded over the N ranks)
+               with its one NCCL all_gather (8 bytes per system) inside the CUDA-event region
+  cpu_baseline the C oracle (a port of the reference's arithmetic) on the host cores (N = 1 only)
 `--impl reference` times that CPU port alone with all host threads.
 """
 import argparse
@@ -28,6 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "batched KalmanODE solves/sec (FitzHugh-Nagumo, 64k theta)"
 UNIT = "solves/s"
 BATCH = 65536
+C5_TOTAL = 1 << 20
 N_EVAL, N_STATE, N_MEAS = 400, 6, 2
 # SURVEY section 8(d), general mode, per system per step: the reference's four dense history
 # arrays written once by the filter and read once by the smoother, plus the solve_mv output.
@@ -36,44 +43,35 @@ OUT_BYTES_STEP = 8 * (N_STATE + N_STATE * N_STATE)                   # 336
 ALG_BYTES_SOLVE = N_EVAL * (2 * HIST_BYTES_STEP + OUT_BYTES_STEP)    # 672,000
 ALG_BYTES_BACKWARD = N_EVAL * (HIST_BYTES_STEP + OUT_BYTES_STEP)     # the smoother kernel's share
 ALG_BYTES_FORWARD = N_EVAL * HIST_BYTES_STEP
+REF_FLOPS_PER_SOLVE = 3621 * 400          # SURVEY 8(d), C2, general mode
 
 
 def workload_config(extra=None):
     c = {"workload": "fitzhugh-nagumo solve_mv, n_state 6, n_meas 2, n_eval 400, "
                      "65536 theta draws per GPU (BASELINE configs[1])",
          "batch_per_gpu": BATCH, "n_eval": N_EVAL, "mode": "solve_mv", "prior": "ibm q=3, sigma 0.1",
-         "l2": "no flush: each step streams >3.7 GB of filter history (written, then read back) and "
-               "8.8 GB of output per GPU, >100x the 126 MB L2"}
+         "l2": "no flush: each step streams >1.8 GB of filter history (written, then read back) and "
+               "8.8 GB of output per GPU, >80x the 126 MB L2"}
     if extra:
         c.update(extra)
     return c
 
 
-REF_FLOPS_PER_SOLVE = 3621 * 400          # SURVEY 8(d), C2, general mode
+def layout_traffic(kode, B):
+    """DRAM bytes one launch of each kernel moves, FROM THE DATA LAYOUT: the forward
+    kernel writes, and the smoother reads, R records of `hist_doubles` doubles per system (R = checkpointed time
+    indices); the smoother writes the solve_mv output.  Inputs (x0, theta) are < 0.1 %."""
+    hist = kode.history_bytes_per_system * B
+    out = (N_EVAL + 1) * OUT_BYTES_STEP * B
+    return {"forward": hist, "backward": hist + out, "history": hist, "output": out}
 
 
-def measured_traffic(kernel_key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/traffic.json, written by tools/ncu_traffic.py from `ncu --set full`), or None."""
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch from the committed ncu capture of HEAD's kernels (profiles/traffic.json, written by
+    tools/ncu_traffic.py from `ncu --set full`), or None: cross-check of layout_traffic(), not its source."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             return json.load(f).get(kernel_key)
-    except Exception:
-        return None
-
-
-def write_pattern_peak():
-    """GB/s a no-compute kernel reaches writing the variance OUTPUT PATTERN of this workload (65,536
-    interleaved streams of 288-byte runs, tools/microbench/write_pattern.cu), measured live; None if
-    the binary is missing.  The output layout [b][t][n][n] is the reference's; this is what the memory
-    system sustains for it, against 7.4 TB/s for a contiguous fill."""
-    exe = os.path.join(ROOT, "tools", "microbench", "write_pattern")
-    if not os.path.exists(exe):
-        return None
-    try:
-        import subprocess
-        out = subprocess.run([exe, "--quick"], capture_output=True, text=True, timeout=60).stdout
-        return float(json.loads(out.strip().splitlines()[0])["GBps"])
     except Exception:
         return None
 
@@ -139,16 +137,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def oracle_problem(w):
+    import oracle
+    return oracle.Problem(w["ode"], w["W"], w["tmin"], w["tmax"], w["N"], w["Q"], w["c"], w["R"])
+
+
 def cpu_baseline(seconds=10.0, chunk=1024, nthreads=0):
     """The C oracle (port of rodeo/eigen/KalmanTV.h + KalmanTVODE.h), OpenMP over the batch,
     on a bounded sample of the SAME workload: chunks of `chunk` solves until `seconds` elapse."""
-    import numpy as np
     import oracle
-    from tests import workloads as wl
+    from rodeo_legacy_b200 import workloads as wl
     oracle.build()
     flags = oracle.select_timing_build()
     w, x0, theta = wl.fitz_batch(chunk * 64, seed=0)
-    p = wl.make_oracle_problem(w)
+    p = oracle_problem(w)
     if nthreads <= 0:            # torchrun exports OMP_NUM_THREADS=1: ask for every usable core
         nthreads = host_cores()
     cores = nthreads
@@ -180,13 +182,12 @@ def run_reference(args):
     if rank != 0:
         return
     chunk = 2048
-    import numpy as np
     import oracle
-    from tests import workloads as wl
+    from rodeo_legacy_b200 import workloads as wl
     oracle.build()
     flags = oracle.select_timing_build()
     w, x0, theta = wl.fitz_batch(chunk, seed=0)
-    p = wl.make_oracle_problem(w)
+    p = oracle_problem(w)
     cores = host_cores()         # explicit: torchrun exports OMP_NUM_THREADS=1
     for _ in range(max(1, min(args.warmup, 2))):
         oracle.solve_batch(p, x0, theta, None, oracle.MODE_MV, cores)
@@ -222,9 +223,42 @@ def host_memory_ok(nbytes):
                 if s.isdigit():
                     lim = int(s)
         cap = min(x for x in (avail, lim) if x is not None)
-        return nbytes * 2.5 < cap
+        return nbytes * 1.25 < cap
     except Exception:
         return False
+
+
+def bind_near_gpu(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` BEFORE any pinned host memory is
+    allocated (first-touch places the staging buffers on that NUMA node).  Returns a short description."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus [{cpus[0]}..{cpus[-1]}] (nvmlDeviceSetCpuAffinity)"
+    except Exception as e:
+        return f"unbound ({type(e).__name__})"
+
+
+def copy_probe(torch, nbytes=1 << 30, reps=3):
+    """H2D / D2H GB/s of this rank between pinned host memory and its GPU (best of `reps`), all ranks at once."""
+    host = torch.empty(nbytes // 8, dtype=torch.float64, pin_memory=True)
+    dev = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    out = {}
+    for name, (dst, src) in {"h2d": (dev, host), "d2h": (host, dev)}.items():
+        best = 0.0
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[name] = best
+    del host, dev
+    return out
 
 
 def main():
@@ -238,6 +272,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the dense / shared-covariance / C5 side measurements")
     ap.add_argument("--dense", action="store_true",
                     help="force the general dense kernel family (default: block-diagonal is auto-selected)")
     args = ap.parse_args()
@@ -249,12 +284,14 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from tests import workloads as wl
+    from rodeo_legacy_b200 import workloads as wl
+    from rodeo_legacy_b200.dist import gather_batch, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    binding = bind_near_gpu(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -263,6 +300,15 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(v):
+        return -max_over_ranks(-v)
 
     B = args.batch
     w, x0, theta = wl.fitz_batch(B, seed=rank)
@@ -275,11 +321,10 @@ def main():
     for _ in range(args.warmup):
         mu, var = k.solve_mv(x0d, theta=thd)
     barrier()
-    k.set_timing(True)
+    k.set_timing(True)           # per-kernel events inside the library, on the launching stream, EVERY timed step
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = k.launch_count
-    fwd_ms = bwd_ms = 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -290,29 +335,30 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
     launches = k.launch_count - launches0
-    # per-kernel device times of the last timed step (events on the launching stream)
-    f, b = k.last_kernel_ms()
-    fwd_ms, bwd_ms = f, b
+    f_tot, b_tot, n_timed = k.kernel_ms_total()
+    fwd_ms, bwd_ms = f_tot / n_timed, b_tot / n_timed      # averages over the timed steps
     k.set_timing(False)
     status_bad = int(k.status.abs().sum())
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = max_over_ranks(ms)
     value = world * B * args.steps / (ms * 1e-3)
+    traffic = layout_traffic(k, B)
+    del mu, var
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the host-buffer entry point ------------------------------------
+    # ---- end to end through the host-buffer entry point: the same batch per GPU at every N ------------
     e2e = None
     if not args.no_e2e:
-        del mu, var
-        torch.cuda.empty_cache()
-        # several ranks share one host: keep the pinned footprint of the e2e leg modest there
-        # (throughput is PCIe-bound per GPU and does not depend on the batch size)
-        Be = B if world == 1 else min(B, 16384)
-        out_bytes = Be * (N_EVAL + 1) * (N_STATE + N_STATE * N_STATE) * 8
-        while Be > 4096 and not host_memory_ok(out_bytes * max(1, min(world, 8))):
-            Be //= 2
-            out_bytes = Be * (N_EVAL + 1) * (N_STATE + N_STATE * N_STATE) * 8
+        Be = B
+        out_bytes = Be * (N_EVAL + 1) * OUT_BYTES_STEP
+        fits = host_memory_ok(out_bytes * world + (1 << 30) * world)
+        fits = min_over_ranks(1.0 if fits else 0.0) > 0.5
+        if not fits:       # never silently: the reduced batch is named in the line
+            while Be > 4096 and not host_memory_ok(out_bytes * world):
+                Be //= 2
+                out_bytes = Be * (N_EVAL + 1) * OUT_BYTES_STEP
+            Be = int(min_over_ranks(float(Be)))
+            out_bytes = Be * (N_EVAL + 1) * OUT_BYTES_STEP
+        probe = copy_probe(torch)
         pin = lambda *s: torch.empty(s, dtype=torch.float64, pin_memory=True)
         x0p, thp = pin(Be, N_STATE), pin(Be, 3)
         x0p.copy_(torch.from_numpy(x0[:Be]))
@@ -325,25 +371,62 @@ def main():
         for _ in range(args.e2e_steps):
             k.solve_mv_into(x0n, thn, mun, varn)       # synchronous: returns with results on the host
         barrier()
-        el = time.perf_counter() - t0
-        te = torch.tensor([el], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        el = float(te.item())
+        el = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * Be * args.e2e_steps / el, "unit": UNIT,
                "h2d_bytes_per_step": Be * (N_STATE + 3) * 8,
                "d2h_bytes_per_step": out_bytes + Be * 4,
                "batch_per_gpu": Be, "steps": args.e2e_steps, "ms_per_step": 1e3 * el / args.e2e_steps,
-               "host_buffers": "pinned", "checksum": float(mun[:, -1, 0].sum())}
-        del mup, varp
+               "host_buffers": "pinned", "cpu_binding": binding,
+               "copy_probe_GBps": {"h2d_min_over_ranks": min_over_ranks(probe["h2d"]),
+                                   "d2h_min_over_ranks": min_over_ranks(probe["d2h"]),
+                                   "d2h_sum_over_ranks": None, "note": "1 GiB pinned <-> device, all ranks at once"},
+               "d2h_GBps_achieved_per_gpu": (out_bytes + Be * 4) * args.e2e_steps / el / 1e9,
+               "limiter": "PCIe D2H of the full (B, N+1, n, n) variance output: the step moves 8.83 GB per GPU to the host",
+               "checksum": float(mun[:, -1, 0].sum())}
+        t = torch.tensor([probe["d2h"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e["copy_probe_GBps"]["d2h_sum_over_ranks"] = float(t.item())
+        del mup, varp, x0p, thp
 
-    # ---- the general dense kernel family on the same workload (extra line, fewer steps) -------
-    dense = None
-    if not args.dense and world == 1:
-        try:
-            del mu, var
-        except NameError:
-            pass
+    # ---- BASELINE configs[4]: 1,048,576-theta log-likelihood sweep, sharded over the ranks, one NCCL gather ----
+    c5 = None
+    if not args.no_extras and not args.dense:
+        torch.cuda.empty_cache()
+        lo, hi = shard_range(C5_TOTAL, rank, world)
+        th5 = torch.from_numpy(wl.fitz_sweep_theta(C5_TOTAL, lo, hi, w)).cuda()
+        x05 = torch.from_numpy(np.tile(w["x0"], (hi - lo, 1))).cuda()
+        Y, ind, sind = wl.fitz_observations(k, w)
+        reps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            ll = gather_batch(k.loglik(x05, th5, Y, ind, sind, 0.2), C5_TOTAL)
+        barrier()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        tot = gat = 0.0
+        for _ in range(reps):
+            barrier()
+            c0.record()
+            ll_local = k.loglik(x05, th5, Y, ind, sind, 0.2)
+            c1.record()
+            ll = gather_batch(ll_local, C5_TOTAL)          # all_gather_into_tensor, 8 bytes per system
+            c2.record()
+            torch.cuda.synchronize()
+            tot += max_over_ranks(c0.elapsed_time(c2))
+            gat += max_over_ranks(c1.elapsed_time(c2))
+        c5_ms, gather_ms = tot / reps, gat / reps
+        c5 = {"workload": "fitzhugh-nagumo log-likelihood sweep, 1,048,576 theta, thinned to t = 1..40, gamma 0.2 "
+                          "(BASELINE configs[4]; examples/inference.py:85-94)",
+              "value": C5_TOTAL / (c5_ms * 1e-3), "unit": UNIT, "scaling": "strong", "n_gpus": world,
+              "ms_per_sweep": c5_ms, "gather_ms": gather_ms, "systems_per_gpu": hi - lo, "reps": reps,
+              "parallelism": f"sharded x{world} (contiguous slices), one all_gather_into_tensor of 8 B/system "
+                             "inside the timed region" if world > 1 else "one GPU, no collective",
+              "gathered": int(ll.numel()), "argmax_theta_index": int(ll.argmax()),
+              "loglik_checksum": float(ll.sum())}
+        del th5, x05, ll
+
+    # ---- side measurements on one GPU: other kernel families, other entry points ------------------------
+    dense = shared = e2e_other = None
+    if world == 1 and not args.no_extras and not args.dense:
         torch.cuda.empty_cache()
         kd = wl.make_kode(w, force_dense=True)
         kd.reserve(B)
@@ -359,23 +442,17 @@ def main():
         d1.record()
         torch.cuda.synchronize()
         dms = d0.elapsed_time(d1) / nd
-        df, db = kd.last_kernel_ms()
+        df, db, dn = kd.kernel_ms_total()
+        dtr = layout_traffic(kd, B)
         dense = {"family": "/".join(kd.kernel_family), "value": B / (dms * 1e-3), "unit": UNIT,
-                 "ms_per_step": dms, "forward_kernel_ms": df, "backward_kernel_ms": db, "steps": nd,
-                 "backward_achieved_GBps": ALG_BYTES_BACKWARD * B / (db * 1e-3) / 1e9}
+                 "ms_per_step": dms, "forward_kernel_ms": df / dn, "backward_kernel_ms": db / dn, "steps": nd,
+                 "backward_traffic": dtr["backward"],
+                 "backward_frac": dtr["backward"] / (db / dn * 1e-3) / 1e9 / peaks()[0]}
         del kd
         torch.cuda.empty_cache()
 
-    # ---- shared-covariance mode on the same workload: a DIFFERENT amount of work per system
-    # (covariances once per prior, mean recursions per system; var returned as one shared array),
-    # reported on its own line with its own byte count -- never against the general-mode roofline
-    shared = None
-    if world == 1 and not args.dense:
-        try:
-            del mu, var
-        except NameError:
-            pass
-        torch.cuda.empty_cache()
+        # shared-covariance mode: a DIFFERENT amount of work per system (covariances once per prior, mean
+        # recursions per system; var returned as one shared array) -- its own line, its own byte count
         ks = wl.make_kode(w, shared_cov=True)
         for _ in range(3):
             ks.solve_mv(x0d, theta=thd)
@@ -389,35 +466,59 @@ def main():
         s1.record()
         torch.cuda.synchronize()
         sms = s0.elapsed_time(s1) / ns
-        sf, sb = ks.last_kernel_ms()
+        sf, sb, sn = ks.kernel_ms_total()
         sc_bytes = N_EVAL * 8 * 3 * N_STATE * B          # mu_filt written + read, mu_smooth written
         shared = {"mode": "shared covariance (SURVEY F5): tables cached per prior, mean recursions per system, "
                           "var = one (N+1,n,n) array for the batch",
-                  "value": B / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms, "forward_kernel_ms": sf,
-                  "backward_kernel_ms": sb, "steps": ns,
+                  "value": B / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms, "forward_kernel_ms": sf / sn,
+                  "backward_kernel_ms": sb / sn, "steps": ns,
                   "algorithmic_bytes_per_step": sc_bytes, "achieved_GBps": sc_bytes / (sms * 1e-3) / 1e9,
                   "frac_of_hbm_peak": sc_bytes / (sms * 1e-3) / 1e9 / peaks()[0]}
         if not args.no_e2e:
-            Bs = B
             pin = lambda *s_: torch.empty(s_, dtype=torch.float64, pin_memory=True)
-            x0p, thp = pin(Bs, N_STATE), pin(Bs, 3)
+            x0p, thp = pin(B, N_STATE), pin(B, 3)
             x0p.copy_(torch.from_numpy(x0))
             thp.copy_(torch.from_numpy(theta))
-            mup, varp = pin(Bs, N_EVAL + 1, N_STATE), pin(N_EVAL + 1, N_STATE, N_STATE)
+            mup, varp = pin(B, N_EVAL + 1, N_STATE), pin(N_EVAL + 1, N_STATE, N_STATE)
             ks.solve_mv_into(x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy())
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 ks.solve_mv_into(x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy())
             el = time.perf_counter() - t0
-            shared["e2e"] = {"value": Bs * args.e2e_steps / el, "unit": UNIT,
-                             "h2d_bytes_per_step": Bs * (N_STATE + 3) * 8,
-                             "d2h_bytes_per_step": Bs * (N_EVAL + 1) * N_STATE * 8
-                                                   + (N_EVAL + 1) * N_STATE * N_STATE * 8 + Bs * 4,
+            shared["e2e"] = {"value": B * args.e2e_steps / el, "unit": UNIT,
+                             "h2d_bytes_per_step": B * (N_STATE + 3) * 8,
+                             "d2h_bytes_per_step": B * (N_EVAL + 1) * N_STATE * 8
+                                                   + (N_EVAL + 1) * N_STATE * N_STATE * 8 + B * 4,
                              "ms_per_step": 1e3 * el / args.e2e_steps}
             del mup, varp
         del ks
         torch.cuda.empty_cache()
+
+        # the other two entry points end to end (host buffers in, host buffers out), general mode
+        if not args.no_e2e:
+            z = np.asfortranarray(np.random.default_rng(2).standard_normal((N_STATE, N_EVAL)))
+            kz = wl.make_kode(w, z_state=z)
+            xs = kz.solve_sim(x0, theta=theta)                 # NumPy in -> NumPy out (pageable result)
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                xs = kz.solve_sim(x0, theta=theta)
+            el_sim = (time.perf_counter() - t0) / args.e2e_steps
+            Y, ind, sind = wl.fitz_observations(kz, w)
+            lln = kz.loglik(x0, theta, Y, ind, sind, 0.2)      # NumPy in -> NumPy out
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                lln = kz.loglik(x0, theta, Y, ind, sind, 0.2)
+            el_ll = (time.perf_counter() - t0) / args.e2e_steps
+            e2e_other = {
+                "solve_sim": {"value": B / el_sim, "unit": UNIT, "ms_per_step": 1e3 * el_sim,
+                              "h2d_bytes_per_step": B * (N_STATE + 3) * 8 + z.nbytes,
+                              "d2h_bytes_per_step": B * (N_EVAL + 1) * N_STATE * 8 + B * 4,
+                              "host_buffers": "pageable NumPy arrays (the call a reference user makes)"},
+                "loglik": {"value": B / el_ll, "unit": UNIT, "ms_per_step": 1e3 * el_ll,
+                           "h2d_bytes_per_step": B * (N_STATE + 3) * 8, "d2h_bytes_per_step": B * 12,
+                           "host_buffers": "pageable NumPy arrays", "checksum": float(np.sum(lln))}}
+            del kz, xs
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
@@ -427,42 +528,50 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         key = "backward_mv_fitz6_" + ("dense" if args.dense else "blockdiag")
-        traffic = measured_traffic(key)
-        wpat = write_pattern_peak()
-        f64 = fp64_peak()
-        bwd_gbs = ALG_BYTES_BACKWARD * B / (bwd_ms * 1e-3) / 1e9
-        fwd_gbs = ALG_BYTES_FORWARD * B / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None
-        step_gbs = ALG_BYTES_SOLVE * B * args.steps / (ms * 1e-3) / 1e9
+        tr_ncu = ncu_traffic(key)
+        tr = traffic["backward"]
+        if tr_ncu:       # the layout figure must describe what the hardware counted for this kernel
+            assert abs(tr - tr_ncu) <= 0.03 * tr_ncu, (tr, tr_ncu)
+        f64 = fp64_peak() if not args.no_extras else None
+        bwd_s, fwd_s = bwd_ms * 1e-3, fwd_ms * 1e-3
+        step_s = ms * 1e-3 / args.steps
+        kname = "kalman_backward_tpb" if family == "blockdiag/registers" else "kalman_backward_staged"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config({"parallelism": f"batch replicated x{world} (weak), no collective"}),
-            "roofline": {"bound": "hbm", "kernel": f"kalman_backward_staged (smoother, solve_mv, {family})",
-                         "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "dram_frac": (traffic / (bwd_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                         "write_pattern_peak": wpat,
-                         "frac_of_write_pattern_peak": (traffic / (bwd_ms * 1e-3) / 1e9 / wpat) if traffic and wpat else None,
-                         "note": "achieved = SURVEY 8(d) algorithmic bytes (the reference's four dense "
-                                 "history arrays + solve_mv output) / kernel time; the kernel moves fewer "
-                                 "bytes (traffic) because predicted moments are recomputed and covariances "
-                                 "are stored packed, so frac can exceed 1; dram_frac = traffic / time / peak; "
-                                 "write_pattern_peak = GB/s of a no-compute kernel writing this workload's "
-                                 "288-byte-run output pattern (tools/microbench/write_pattern.cu, measured in "
-                                 "this run): 82 % of the kernel's traffic is that pattern",
+            "config": workload_config({"parallelism": f"batch replicated x{world} (weak), no collective on the "
+                                                      "solve_mv path; the sharded sweep with its NCCL gather is c5_sweep"}),
+            "roofline": {"bound": "hbm", "kernel": f"{kname} (smoother, solve_mv, {family})",
+                         "achieved": tr / bwd_s / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": tr / bwd_s / 1e9 / peak, "traffic": tr, "peak_source": peak_src,
+                         "traffic_source": "data layout: history records read (%d B) + solve_mv output written (%d B) per "
+                                           "launch; cross-checked against the committed ncu capture" %
+                                           (traffic["history"], traffic["output"]),
+                         "traffic_ncu": tr_ncu, "kernel_ms": bwd_ms,
+                         "kernel_ms_source": f"CUDA events on the launching stream, mean of {n_timed} timed steps",
+                         "algorithmic_bytes_per_launch": ALG_BYTES_BACKWARD * B,
+                         "algorithmic_frac": ALG_BYTES_BACKWARD * B / bwd_s / 1e9 / peak,
+                         "algorithmic_note": "SURVEY 8(d) bytes (the reference's four dense history arrays + the output); "
+                                             "the kernel moves fewer because predicted moments are recomputed, covariances "
+                                             "are stored packed per block and every second record is re-run (checkpoint 2)",
+                         "forward": {"kernel": "kalman_forward_tpb" if family == "blockdiag/registers" else "kalman_forward",
+                                     "kernel_ms": fwd_ms, "traffic": traffic["forward"],
+                                     "achieved": traffic["forward"] / fwd_s / 1e9,
+                                     "frac": traffic["forward"] / fwd_s / 1e9 / peak,
+                                     "algorithmic_frac": ALG_BYTES_FORWARD * B / fwd_s / 1e9 / peak},
+                         "whole_step": {"ms": ms / args.steps, "traffic": traffic["forward"] + tr,
+                                        "frac": (traffic["forward"] + tr) / step_s / 1e9 / peak,
+                                        "algorithmic_frac": ALG_BYTES_SOLVE * B / step_s / 1e9 / peak},
                          "fp64": {"peak_TFLOPs": f64, "source": "tools/microbench/fp64_peak.cu, measured in this run "
                                                                 "(nominal 37.2)",
                                   "reference_flops_per_solve": REF_FLOPS_PER_SOLVE,
                                   "reference_equivalent_TFLOPs": value / world * REF_FLOPS_PER_SOLVE / 1e12,
                                   "note": "SURVEY 8(d): 3621 flop/step x 400 steps as the reference's dense "
                                           "KalmanTV executes them; the block-diagonal kernels skip the structural "
-                                          "zeros, so this can exceed the peak -- the second bound, never the binding one"},
-                         "algorithmic_bytes_per_launch": ALG_BYTES_BACKWARD * B,
-                         "kernel_ms": bwd_ms, "forward_kernel_ms": fwd_ms,
-                         "forward_achieved": fwd_gbs,
-                         "whole_step_achieved": step_gbs, "whole_step_frac": step_gbs / peak},
-            "kernel_family": family, "dense_path": dense, "shared_covariance_path": shared,
+                                          "zeros, so this can exceed the peak -- the second bound, never the binding one"}},
+            "kernel_family": family, "c5_sweep": c5, "dense_path": dense, "shared_covariance_path": shared,
+            "e2e_other_entry_points": e2e_other,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "status_nonzero": status_bad,
         }

@@ -47,7 +47,9 @@
  *     rodeo_cuda_last_error() gives the message (thread-local).  Per-system Cholesky
  *     failures (non-positive pivot; silently ignored by the reference) are reported
  *     in `status` (0 = ok, k+1 = first failed pivot index) and do not fail the call.
- *   - A handle is not thread-safe; one solve in flight per handle.
+ *   - A handle is not thread-safe; one solve in flight per handle.  Different handles may be
+ *     created and used from different threads.  rodeo_cuda_problem_destroy leaves the calling
+ *     thread's current CUDA device as it found it.
  */
 #ifndef RODEO_CUDA_H
 #define RODEO_CUDA_H
@@ -112,7 +114,9 @@ typedef struct {
 int rodeo_cuda_abi_version(void);
 const char *rodeo_cuda_last_error(void);
 
-/* n_meas / n_theta of a registered RHS, or RODEO_E_INVALID */
+/* n_meas / n_theta of a registered RHS, or RODEO_E_INVALID; ids run 0 .. rodeo_cuda_ode_count() - 1
+ * (all three come from the compiled device functors, csrc/ode_functors.cuh) */
+int rodeo_cuda_ode_count(void);
 int rodeo_cuda_ode_n_meas(int ode);
 int rodeo_cuda_ode_n_theta(int ode);
 /* Bit 0: a dense kernel set is compiled for this combination (any Q, R, W).  Bit 1: a
@@ -210,9 +214,15 @@ int rodeo_cuda_reset_launch_count(rodeo_problem *p);
 /* Device time (ms) of the forward and backward kernels of the most recent
  * rodeo_cuda_solve call, measured with CUDA events on its stream; synchronises. */
 int rodeo_cuda_last_kernel_ms(rodeo_problem *p, float *forward_ms, float *backward_ms);
-/* test hook: copy the first `bytes` of the handle's history workspace to a device buffer */
+/* The same summed over EVERY solve since rodeo_cuda_set_timing(p, 1) (at most 4096 chunks are kept),
+ * with the number of solves: bench.py divides by it for the per-step kernel times; synchronises. */
+int rodeo_cuda_kernel_ms_total(rodeo_problem *p, double *forward_ms, double *backward_ms, int32_t *n_solves);
+/* test hook: copy the first `bytes` of the handle's history workspace to a device buffer.  Layout
+ * hist[tile][record][element][32 systems] (csrc/kalman_common.cuh); for two-block block-diagonal priors
+ * solved by the thread-per-block kernels, system b sits at position perm16(b) (same file). */
 int rodeo_cuda_debug_copy_history(rodeo_problem *p, void *dst_device, size_t bytes, void *cuda_stream);
-/* enable (1) / disable (0) the event recording used by rodeo_cuda_last_kernel_ms */
+/* enable (1) / disable (0) the event recording used by rodeo_cuda_last_kernel_ms / _kernel_ms_total
+ * (either value restarts the accumulation) */
 int rodeo_cuda_set_timing(rodeo_problem *p, int enabled);
 
 #ifdef __cplusplus

@@ -51,8 +51,10 @@ struct rodeo_problem {
   size_t ws_limit = (size_t)48 << 30;
   int64_t launches = 0;
   bool timing = false;
-  std::vector<cudaEvent_t> ev;     // 3 per chunk of the last solve
-  int ev_chunks = 0;
+  std::vector<cudaEvent_t> ev;     // 3 per chunk, every chunk launched since timing was switched on
+  int ev_first = 0;                // first chunk of the LAST solve in ev (chunk index)
+  int ev_chunks = 0;               // chunks recorded since timing was switched on
+  int ev_solves = 0;               // solves recorded since timing was switched on
   // host-path device buffers (grow-only)
   void *hbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t hbuf_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -60,8 +62,6 @@ struct rodeo_problem {
   cudaEvent_t e_done[2] = {nullptr, nullptr}, e_copied[2] = {nullptr, nullptr};
 };
 
-static const int kOdeMeas[4] = {1, 2, 3, 5};
-static const int kOdeTheta[4] = {0, 3, 3, 6};
 
 // Q, R block diagonal with m blocks of size n/m and row a of W supported inside block a?
 static bool is_block_diagonal(const rodeo_problem *p) {
@@ -101,8 +101,9 @@ extern "C" {
 int rodeo_cuda_abi_version(void) { return RODEO_CUDA_ABI_VERSION; }
 const char *rodeo_cuda_last_error(void) { return g_err.c_str(); }
 
-int rodeo_cuda_ode_n_meas(int ode) { return (ode >= 0 && ode < 4) ? kOdeMeas[ode] : RODEO_E_INVALID; }
-int rodeo_cuda_ode_n_theta(int ode) { return (ode >= 0 && ode < 4) ? kOdeTheta[ode] : RODEO_E_INVALID; }
+int rodeo_cuda_ode_n_meas(int ode) { return ode_n_meas(ode) >= 0 ? ode_n_meas(ode) : RODEO_E_INVALID; }
+int rodeo_cuda_ode_n_theta(int ode) { return ode_n_theta(ode) >= 0 ? ode_n_theta(ode) : RODEO_E_INVALID; }
+int rodeo_cuda_ode_count(void) { return ode_count(); }
 
 // 1: a dense kernel set exists (any Q, R, W); 2: only a block-diagonal set exists (the prior
 // must be block diagonal with n_meas blocks and W row a inside block a); 3: both; 0: none.
@@ -119,9 +120,9 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) 
     return fail(RODEO_E_INVALID, "n_state, n_meas must be positive and n_eval >= 1");
   if (!d->wgt_meas || !d->wgt_state || !d->mu_state || !d->var_state)
     return fail(RODEO_E_INVALID, "wgt_meas, wgt_state, mu_state, var_state must be set");
-  if (d->ode < 0 || d->ode > 3) return fail(RODEO_E_INVALID, "unknown ode id");
+  if (ode_n_meas(d->ode) < 0) return fail(RODEO_E_INVALID, "unknown ode id");
   if (d->interrogate < 0 || d->interrogate > 2) return fail(RODEO_E_INVALID, "unknown interrogate id");
-  if (d->n_meas != kOdeMeas[d->ode]) return fail(RODEO_E_INVALID, "n_meas does not match the ode");
+  if (d->n_meas != ode_n_meas(d->ode)) return fail(RODEO_E_INVALID, "n_meas does not match the ode");
   rodeo_problem *p = new rodeo_problem();
   p->n = d->n_state;
   p->m = d->n_meas;
@@ -152,6 +153,8 @@ int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) 
 
 int rodeo_cuda_problem_destroy(rodeo_problem *p) {
   if (!p) return RODEO_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);            // a garbage-collected handle must not move the caller's current device
   cudaSetDevice(p->device);
   if (p->ws) cudaFree(p->ws);
   if (p->tab) cudaFree(p->tab);
@@ -165,6 +168,7 @@ int rodeo_cuda_problem_destroy(rodeo_problem *p) {
   }
   if (p->s_compute) cudaStreamDestroy(p->s_compute);
   if (p->s_copy) cudaStreamDestroy(p->s_copy);
+  if (prev >= 0 && prev != p->device) cudaSetDevice(prev);
   delete p;
   return RODEO_OK;
 }
@@ -344,7 +348,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
                       const double *theta, const double *z, long z_stride, double *x_out,
                       double *mu_out, double *var_out, int *status, const LoglikSpec *ll,
                       cudaStream_t stream, const BatchedPrior *bp = nullptr) {
-  const int n = p->n, nth = kOdeTheta[p->ode];
+  const int n = p->n, nth = ode_n_theta(p->ode);
   const long T1 = (long)p->N + 1;
   // per-system priors run on the dense family with the full history, never in shared-covariance mode
   const KernelSet *ks = bp ? find_kernel_set(p->ode, p->n, false) : p->ks;
@@ -375,14 +379,19 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     perm = !alt && ks->backward_perm[slot][bk];
   }
   const long n_chunks = (batch + cap - 1) / cap;
+  const int kMaxTimedChunks = 4096;       // beyond that only the last solve is kept (the ring restarts)
   if (p->timing) {
-    while ((long)p->ev.size() < 3 * n_chunks) {
+    if (p->ev_chunks + n_chunks > kMaxTimedChunks) p->ev_chunks = p->ev_solves = 0;
+    while ((long)p->ev.size() < 3 * (p->ev_chunks + n_chunks)) {
       cudaEvent_t e;
       CK(cudaEventCreate(&e));
       p->ev.push_back(e);
     }
-    p->ev_chunks = (int)n_chunks;
+    p->ev_first = p->ev_chunks;
+    p->ev_chunks += (int)n_chunks;
+    p->ev_solves += 1;
   }
+  const long ev0 = p->timing ? p->ev_first : 0;
   for (long ci = 0; ci < n_chunks; ci++) {
     const long off = ci * cap, B = std::min(cap, batch - off);
     SolveArgs a;
@@ -411,23 +420,26 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
       a.n_obs_comp = ll->n_obs_comp;
       a.loglik = ll->out + off;
     }
-    if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 0], stream));
+    if ((reinterpret_cast<uintptr_t>(a.x_out) | reinterpret_cast<uintptr_t>(a.mu_out) |
+         reinterpret_cast<uintptr_t>(a.var_out)) & 15)
+      return fail(RODEO_E_INVALID, "internal: a chunk's output array is not 16-byte aligned");
+    if (p->timing) CK(cudaEventRecord(p->ev[3 * (ev0 + ci) + 0], stream));
     if (bp) {
       BatchedPrior c{bp->W ? bp->W + off * p->m * n : nullptr, bp->Q ? bp->Q + off * n * n : nullptr,
                      bp->c ? bp->c + off * n : nullptr, bp->R ? bp->R + off * n * n : nullptr};
       CK(wide_pp ? ks->wide_pp_forward(hp, c, a, stream) : ks->pp_forward(hp, c, a, stream));
-      if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
+      if (p->timing) CK(cudaEventRecord(p->ev[3 * (ev0 + ci) + 1], stream));
       CK(wide_pp ? ks->wide_pp_backward[bk](hp, c, a, stream) : ks->pp_backward[bk](hp, c, a, stream));
     } else {
       CK(shared ? ks->sc_forward(hp, a, stream)
                 : wide ? ks->wide_forward[p->ig](hp, a, stream)
                        : (perm && ks->forward_perm[p->ig]) ? ks->forward_perm[p->ig](hp, a, stream)
                                                            : ks->forward[p->ig](hp, a, stream));
-      if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 1], stream));
+      if (p->timing) CK(cudaEventRecord(p->ev[3 * (ev0 + ci) + 1], stream));
       CK(shared ? ks->sc_backward[bk](hp, a, stream)
                 : wide ? ks->wide_backward[bk](hp, a, stream) : backward(hp, a, stream));
     }
-    if (p->timing) CK(cudaEventRecord(p->ev[3 * ci + 2], stream));
+    if (p->timing) CK(cudaEventRecord(p->ev[3 * (ev0 + ci) + 2], stream));
     p->launches += 2;
   }
   return RODEO_OK;
@@ -441,7 +453,7 @@ static int check_solve_args(rodeo_problem *p, int mode, int64_t batch, const dou
     return fail(RODEO_E_INVALID, "mode must be RODEO_MODE_MV, _SIM or _BOTH");
   if (batch < 0) return fail(RODEO_E_INVALID, "negative batch");
   if (batch > 0 && !x0) return fail(RODEO_E_INVALID, "x0 is null");
-  if (batch > 0 && kOdeTheta[p->ode] > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
+  if (batch > 0 && ode_n_theta(p->ode) > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
   if (batch > 0 && ((mode & RODEO_MODE_SIM) || p->ig == RODEO_INTERROGATE_CHKREBTII) && !z)
     return fail(RODEO_E_INVALID, "z is null but the requested mode consumes normal draws");
   if (batch > 0 && (mode & RODEO_MODE_MV) && (!mu_out || !var_out)) return fail(RODEO_E_INVALID, "mu_out / var_out is null");
@@ -484,6 +496,7 @@ int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, co
                                    const double *wgt_state_b, const double *var_state_b, double *x_out,
                                    double *mu_out, double *var_out, int32_t *status, void *cuda_stream) {
   int rc = check_solve_args(p, mode, batch, x0, theta, z, x_out, mu_out, var_out);
+  if (!rc && batch > 0) rc = check_device_alignment(x_out, mu_out, var_out);
   if (rc) return rc;
   if (batch == 0) return RODEO_OK;
   const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
@@ -505,7 +518,7 @@ int rodeo_cuda_loglik(rodeo_problem *p, int use_draw, int64_t batch, const doubl
   if (batch < 0 || n_obs_times < 0 || n_obs_comp < 0) return fail(RODEO_E_INVALID, "negative size");
   if (batch == 0) return RODEO_OK;
   if (!x0 || !loglik_out) return fail(RODEO_E_INVALID, "x0 / loglik_out is null");
-  if (kOdeTheta[p->ode] > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
+  if (ode_n_theta(p->ode) > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
   if ((use_draw || p->ig == RODEO_INTERROGATE_CHKREBTII) && !z) return fail(RODEO_E_INVALID, "z is null but draws are requested");
   if (n_obs_times * n_obs_comp > 0 && (!thin_index || !state_index || !Y)) return fail(RODEO_E_INVALID, "thin_index / state_index / Y is null");
   if (!(gamma > 0.0)) return fail(RODEO_E_INVALID, "gamma must be positive");
@@ -531,7 +544,7 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
   if (rc) return rc;
   if (batch == 0) return RODEO_OK;
   CK(cudaSetDevice(p->device));
-  const int n = p->n, nth = kOdeTheta[p->ode];
+  const int n = p->n, nth = ode_n_theta(p->ode);
   const long T1 = (long)p->N + 1;
   if (!p->s_compute) {
     CK(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
@@ -544,6 +557,10 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
   const bool mv = mode & RODEO_MODE_MV, sim = mode & RODEO_MODE_SIM;
   const bool pervar = mv && !p->shared;   // per-system variance output (general mode)
   const size_t out_per = (size_t)T1 * n * sizeof(double) * ((mv ? 1 : 0) + (pervar ? n : 0) + (sim ? 1 : 0));
+  // sub-arrays of a staging buffer start on 128-byte boundaries (the kernels store 16-byte vectors / TMA
+  // boxes relative to each array base): B * T1 * n doubles is odd when B, T1 and n are all odd
+  auto al = [](size_t doubles) { return (doubles + 15) & ~(size_t)15; };
+  const size_t out_pad = 3 * 16 * sizeof(double);
   // output staging: two buffers of at most 2 GiB each, and never more systems than a history chunk
   long hc = (long)std::max<size_t>(1, ((size_t)2 << 30) / out_per);
   hc = std::min(hc, chunk_capacity(p, (long)batch));
@@ -556,8 +573,8 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
   if (nth && (rc = ensure_buf(p, 1, (size_t)hc * nth * sizeof(double)))) return rc;
   if (need_z && (rc = ensure_buf(p, 2, (z_batch_stride ? (size_t)hc : 1) * z_elems * sizeof(double)))) return rc;
   if ((rc = ensure_buf(p, 3, (size_t)hc * sizeof(int)))) return rc;
-  if ((rc = ensure_buf(p, 4, (size_t)hc * out_per))) return rc;
-  if ((rc = ensure_buf(p, 5, (size_t)hc * out_per))) return rc;
+  if ((rc = ensure_buf(p, 4, (size_t)hc * out_per + out_pad))) return rc;
+  if ((rc = ensure_buf(p, 5, (size_t)hc * out_per + out_pad))) return rc;
   if (mv && p->shared && (rc = ensure_buf(p, 6, (size_t)T1 * n * n * sizeof(double)))) return rc;
   if (need_z && !z_batch_stride)
     CK(cudaMemcpyAsync(p->hbuf[2], z, z_elems * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
@@ -567,9 +584,10 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
     const long off = ci * hc, B = std::min(hc, (long)batch - off);
     const int slot = (int)(ci & 1);
     double *ob = (double *)p->hbuf[4 + slot];
+    const size_t vec = al((size_t)B * T1 * n), mat = al((size_t)B * T1 * n * n);
     double *d_mu = mv ? ob : nullptr;
-    double *d_var = pervar ? ob + (size_t)B * T1 * n : nullptr;
-    double *d_x = sim ? ob + (mv ? (size_t)B * T1 * n * (pervar ? 1 + n : 1) : 0) : nullptr;
+    double *d_var = pervar ? ob + vec : nullptr;
+    double *d_x = sim ? ob + (mv ? vec + (pervar ? mat : 0) : 0) : nullptr;
     if (mv && p->shared && ci == 0) d_var = (double *)p->hbuf[6];   // the single shared variance array
     // inputs of this chunk (the previous chunk's kernels are ordered before us on s_compute)
     CK(cudaMemcpyAsync(p->hbuf[0], x0 + off * n, (size_t)B * n * sizeof(double), cudaMemcpyHostToDevice, p->s_compute));
@@ -616,23 +634,42 @@ int rodeo_cuda_reset_launch_count(rodeo_problem *p) {
 int rodeo_cuda_set_timing(rodeo_problem *p, int enabled) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
   p->timing = enabled != 0;
+  p->ev_first = p->ev_chunks = p->ev_solves = 0;
+  return RODEO_OK;
+}
+// forward / backward kernel time summed over chunks [c0, c1) of the recorded events
+static int sum_kernel_ms(rodeo_problem *p, int c0, int c1, double *f, double *b) {
+  CK(cudaSetDevice(p->device));
+  *f = *b = 0.0;
+  for (int ci = c0; ci < c1; ci++) {
+    CK(cudaEventSynchronize(p->ev[3 * ci + 2]));
+    float t;
+    CK(cudaEventElapsedTime(&t, p->ev[3 * ci + 0], p->ev[3 * ci + 1]));
+    *f += t;
+    CK(cudaEventElapsedTime(&t, p->ev[3 * ci + 1], p->ev[3 * ci + 2]));
+    *b += t;
+  }
   return RODEO_OK;
 }
 int rodeo_cuda_last_kernel_ms(rodeo_problem *p, float *forward_ms, float *backward_ms) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
   if (!p->timing || p->ev_chunks == 0) return fail(RODEO_E_INVALID, "timing was not enabled for the last solve");
-  CK(cudaSetDevice(p->device));
-  float f = 0.f, b = 0.f;
-  for (int ci = 0; ci < p->ev_chunks; ci++) {
-    CK(cudaEventSynchronize(p->ev[3 * ci + 2]));
-    float t;
-    CK(cudaEventElapsedTime(&t, p->ev[3 * ci + 0], p->ev[3 * ci + 1]));
-    f += t;
-    CK(cudaEventElapsedTime(&t, p->ev[3 * ci + 1], p->ev[3 * ci + 2]));
-    b += t;
-  }
+  double f, b;
+  int rc = sum_kernel_ms(p, p->ev_first, p->ev_chunks, &f, &b);
+  if (rc) return rc;
+  if (forward_ms) *forward_ms = (float)f;
+  if (backward_ms) *backward_ms = (float)b;
+  return RODEO_OK;
+}
+int rodeo_cuda_kernel_ms_total(rodeo_problem *p, double *forward_ms, double *backward_ms, int32_t *n_solves) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (!p->timing || p->ev_chunks == 0) return fail(RODEO_E_INVALID, "no solve was timed since rodeo_cuda_set_timing");
+  double f, b;
+  int rc = sum_kernel_ms(p, 0, p->ev_chunks, &f, &b);
+  if (rc) return rc;
   if (forward_ms) *forward_ms = f;
   if (backward_ms) *backward_ms = b;
+  if (n_solves) *n_solves = p->ev_solves;
   return RODEO_OK;
 }
 

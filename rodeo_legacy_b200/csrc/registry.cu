@@ -1,6 +1,8 @@
 // registry.cu -- collects the compiled kernel sets.
 #include "registry.cuh"
 
+#include <mutex>
+
 namespace rodeo {
 
 #define RODEO_REG(name) void register_##name(KernelSet *, int *);
@@ -12,9 +14,9 @@ void attach_wide(KernelSet *, int);   // kernels_wide.cu
 
 static KernelSet g_sets[64];
 static int g_count = -1;
+static std::once_flag g_once;
 
-static void init_sets() {
-  if (g_count >= 0) return;
+static void fill_sets() {
   int c = 0;
   register_chkrebtii_dense(g_sets, &c);
   register_chkrebtii_bd(g_sets, &c);
@@ -26,6 +28,28 @@ static void init_sets() {
   register_mseir_bd(g_sets, &c);
   attach_wide(g_sets, c);
   g_count = c;
+}
+static void init_sets() { std::call_once(g_once, fill_sets); }   // handles may be created from several threads
+
+// n_meas / n_theta of a registered right-hand side, taken from its functor (ode_functors.cuh)
+int ode_count() { return 4; }
+int ode_n_meas(int ode) {
+  switch (ode) {
+    case OdeChkrebtii::id: return OdeChkrebtii::n_meas;
+    case OdeFitz::id: return OdeFitz::n_meas;
+    case OdeLorenz63::id: return OdeLorenz63::n_meas;
+    case OdeMseir::id: return OdeMseir::n_meas;
+    default: return -1;
+  }
+}
+int ode_n_theta(int ode) {
+  switch (ode) {
+    case OdeChkrebtii::id: return OdeChkrebtii::n_theta;
+    case OdeFitz::id: return OdeFitz::n_theta;
+    case OdeLorenz63::id: return OdeLorenz63::n_theta;
+    case OdeMseir::id: return OdeMseir::n_theta;
+    default: return -1;
+  }
 }
 
 const KernelSet *find_kernel_set(int ode, int n, bool blockdiag) {

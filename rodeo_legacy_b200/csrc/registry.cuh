@@ -57,6 +57,9 @@ struct KernelSet {
   int wide_hist_elems;
 };
 
+int ode_count();                 // registered right-hand sides: ids 0 .. ode_count() - 1
+int ode_n_meas(int ode);         // from the functors (ode_functors.cuh); -1 for an unknown id
+int ode_n_theta(int ode);
 const KernelSet *find_kernel_set(int ode, int n, bool blockdiag);
 int kernel_set_count();
 const KernelSet *kernel_set_at(int i);

@@ -48,7 +48,7 @@ def _ode_id(ode_fun):
         if name in ODE_FUNS:
             return ODE_FUNS[name]
         raise ValueError(f"unknown ode_fun {name!r}; registered: {register_names()}")
-    if isinstance(name, (int, np.integer)) and 0 <= int(name) <= 3:
+    if isinstance(name, (int, np.integer)) and 0 <= int(name) < _lib.load().rodeo_cuda_ode_count():
         return int(name)
     raise TypeError("rodeo.cuda runs ode_fun on the GPU: pass the name of a registered device "
                     f"functor ({register_names()}), not a Python callable")
@@ -63,6 +63,29 @@ def _copynm(dest, source, name):
         raise TypeError('{} has incorrect shape.'.format(name))
     dest[...] = source
     return source
+
+
+def _readonly(a):
+    """Property getters hand out READ-ONLY views.  The reference's getters expose its internal buffers and
+    ``kode.z_state[:] = z`` works there; here the C handle (and the cached device copy of z) hold their own
+    copies, made by the setters, so an in-place write would be silently ignored -- it raises instead:
+    assign through the property (``kode.z_state = z``)."""
+    v = a.view()
+    v.flags.writeable = False
+    return v
+
+
+def _check_out(a, shape, name):
+    """Caller-provided host output buffer: float64, C-contiguous, exactly the expected shape (the C side
+    copies raw bytes into it)."""
+    if a is None:
+        raise TypeError(f'{name} is required.')
+    if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+        raise TypeError(f'{name} must be a float64 NumPy array.')
+    if tuple(a.shape) != tuple(shape):
+        raise TypeError('{} has incorrect shape.'.format(name))
+    if not a.flags.c_contiguous or not a.flags.writeable:
+        raise TypeError(f'{name} must be C-contiguous and writeable.')
 
 
 def _ptr(t):
@@ -105,6 +128,10 @@ class KalmanODE:
             self.z_state = z_state
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         desc = _lib.ProblemDesc(n, m, self.n_eval, self._ode, self._ig, int(bool(force_dense)),
                                 self.tmin, self.tmax,
                                 self._wgt_meas.ctypes.data, self._wgt_state.ctypes.data,
@@ -135,7 +162,7 @@ class KalmanODE:
 
     @property
     def wgt_meas(self):
-        return self._wgt_meas
+        return _readonly(self._wgt_meas)
 
     @wgt_meas.setter
     def wgt_meas(self, v):
@@ -144,7 +171,7 @@ class KalmanODE:
 
     @property
     def mu_state(self):
-        return self._mu_state
+        return _readonly(self._mu_state)
 
     @mu_state.setter
     def mu_state(self, v):
@@ -153,7 +180,7 @@ class KalmanODE:
 
     @property
     def var_state(self):
-        return self._var_state
+        return _readonly(self._var_state)
 
     @var_state.setter
     def var_state(self, v):
@@ -162,7 +189,7 @@ class KalmanODE:
 
     @property
     def wgt_state(self):
-        return self._wgt_state
+        return _readonly(self._wgt_state)
 
     @wgt_state.setter
     def wgt_state(self, v):
@@ -171,7 +198,7 @@ class KalmanODE:
 
     @property
     def z_state(self):
-        return self._z_state
+        return _readonly(self._z_state)
 
     @z_state.setter
     def z_state(self, v):
@@ -251,6 +278,13 @@ class KalmanODE:
             _lib.check(self._lib.rodeo_cuda_last_kernel_ms(self._h, ctypes.byref(f), ctypes.byref(b)))
         return f.value, b.value
 
+    def kernel_ms_total(self):
+        """(forward ms, backward ms, solves) summed over every solve since ``set_timing(True)``."""
+        f, b, k = ctypes.c_double(), ctypes.c_double(), ctypes.c_int32()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rodeo_cuda_kernel_ms_total(self._h, ctypes.byref(f), ctypes.byref(b), ctypes.byref(k)))
+        return f.value, b.value, k.value
+
     # ---- argument handling --------------------------------------------------------------------
     def _prep(self, x0, W, theta, need_z):
         if W is not None:
@@ -260,6 +294,8 @@ class KalmanODE:
         if on_dev:
             if x0.dtype != torch.float64 or not x0.is_cuda:
                 raise TypeError("x0 must be a float64 CUDA tensor (or a NumPy array)")
+            if x0.device != self.device:
+                raise ValueError(f"x0 is on {x0.device} but this KalmanODE was created on {self.device}")
             single = x0.dim() == 1
             x0b = x0.reshape(-1, self.n_state).contiguous() if x0.numel() % self.n_state == 0 else None
         else:
@@ -352,6 +388,11 @@ class KalmanODE:
         else:
             if out is not None:
                 x, mu, var = out
+                if sim:
+                    _check_out(x, (B, T, n), 'x_out')
+                if mv:
+                    _check_out(mu, (B, T, n), 'mu_out')
+                    _check_out(var, vshape, 'var_out')     # shared-covariance mode: ONE (N+1, n, n) array
             else:
                 x = np.empty((B, T, n)) if sim else None
                 mu = np.empty((B, T, n)) if mv else None

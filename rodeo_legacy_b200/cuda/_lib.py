@@ -26,6 +26,7 @@ _V, _I, _L, _D, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_dou
 SYMBOLS = [
     ("rodeo_cuda_abi_version", _I, []),
     ("rodeo_cuda_last_error", ctypes.c_char_p, []),
+    ("rodeo_cuda_ode_count", _I, []),
     ("rodeo_cuda_ode_n_meas", _I, [_I]),
     ("rodeo_cuda_ode_n_theta", _I, [_I]),
     ("rodeo_cuda_supported", _I, [_I, _I, _I, _I]),
@@ -49,6 +50,8 @@ SYMBOLS = [
     ("rodeo_cuda_launch_count", _L, [_V]),
     ("rodeo_cuda_reset_launch_count", _I, [_V]),
     ("rodeo_cuda_last_kernel_ms", _I, [_V, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    ("rodeo_cuda_kernel_ms_total", _I, [_V, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                        c_int_p]),
     ("rodeo_cuda_set_timing", _I, [_V, _I]),
 ]
 

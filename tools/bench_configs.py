@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from tests import workloads as wl
+from rodeo_legacy_b200 import workloads as wl
 
 
 def timed(fn, reps):

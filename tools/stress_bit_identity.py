@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from tests import workloads as wl
+from rodeo_legacy_b200 import workloads as wl
 
 
 def check(name, maker, B, reps, mode="mv"):

@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 from rodeo_legacy_b200.dist import gather_batch, shard_range
-from tests import workloads as wl
+from rodeo_legacy_b200 import workloads as wl
 
 
 def main():
