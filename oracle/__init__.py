@@ -160,6 +160,22 @@ def solve_batch(prob, x0, theta=None, z=None, mode=MODE_MV, nthreads=0):
     return {"status": status, "x": x, "mu": mu, "var": var}
 
 
+def filter_step(prob, t, mu_filt, var_filt, theta=None):
+    """One filter step t -> t+1 (probde) from given filtered moments; var (n, n) symmetric.
+    Returns (mu_filt, var_filt) at time index t+1."""
+    n = prob.n
+    mu_in = np.ascontiguousarray(mu_filt, dtype=np.float64)
+    var_in = _f(var_filt)
+    th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    mu_out, var_out = np.zeros(n), np.zeros((n, n), order="F")
+    lib().oracle_filter_step.restype = ctypes.c_int
+    lib().oracle_filter_step(
+        ctypes.c_int(prob.ode), ctypes.c_int(n), ctypes.c_int(prob.m), ctypes.c_int(prob.N),
+        ctypes.c_double(prob.tmin), ctypes.c_double(prob.tmax), _p(prob.W), _p(prob.Q), _p(prob.c),
+        _p(prob.R), _p(th), ctypes.c_int(int(t)), _p(mu_in), _p(var_in), _p(mu_out), _p(var_out), None, None)
+    return mu_out, np.ascontiguousarray(var_out)
+
+
 def max_threads():
     return lib().oracle_max_threads()
 

@@ -24,7 +24,7 @@ def _kode_from_golden(g, name, **kw):
 
 # (case, mean tol, var tol, draw tol, horizon for the tight mean/draw check)
 GOLDEN = [("chkrebtii_n100", 1e-10, 1e-8, 1e-5, None), ("chkrebtii_n200", 1e-10, 1e-8, 1e-5, None),
-          ("fitz_n400", 1e-10, 1e-9, 1e-9, None), ("lorenz_n5000", 1e-9, 1e-7, 1e-9, 2500),
+          ("fitz_n400", 1e-10, 1e-10, 1e-9, None), ("lorenz_n5000", 1e-9, 1e-7, 1e-9, 2500),
           ("lorenz_car_n600", 1e-7, 1e-6, 1e-7, None), ("mseir_n1000", 1e-10, 1e-8, 1e-7, None)]
 
 
@@ -69,7 +69,7 @@ def test_golden_vectors_host_and_device_paths(name, mtol, vtol, xtol, hor, force
 
 @pytest.mark.parametrize("force_dense", [False, True], ids=["auto", "dense"])
 @pytest.mark.parametrize("maker,B,mtol,vtol,xtol", [
-    (wl.fitz_batch, 1500, 1e-10, 1e-9, 1e-9),
+    (wl.fitz_batch, 1500, 1e-10, 1e-10, 1e-9),
     (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7),
     (lambda B: wl.lorenz_batch(B, N=500, tmax=2.0), 130, 1e-9, 1e-7, 1e-8)])
 def test_seeded_batch_against_oracle(maker, B, mtol, vtol, xtol, force_dense):
@@ -149,10 +149,12 @@ def test_fitz_full_size_properties(force_dense):
     mu3, _ = k.solve_mv(x0d[perm], theta=thd[perm])
     assert bool((mu3 == mu[perm]).all())
     del mu3
-    pick = np.random.default_rng(0).choice(B, 48, replace=False)
+    # the oracle on 4,096 systems: the first tiles, a block in the middle, the last tiles (north-star: 1e-10)
+    pick = np.r_[0:1024, B // 2 - 17:B // 2 - 17 + 2048, B - 1024:B]
     ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], None, oracle.MODE_MV)
-    assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
-    assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-9
+    pk = torch.from_numpy(pick).cuda()
+    assert traj_err(mu[pk].cpu().numpy(), ref["mu"]).max() < 1e-10
+    assert var_err(var[pk].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-10
     if not force_dense:      # the two families agree with each other to rounding as well
         kd = wl.make_kode(w, force_dense=True)
         mud, vard = kd.solve_mv(x0d[:4096], theta=thd[:4096])
@@ -176,14 +178,20 @@ def test_wide_state_configs_at_full_size(maker, B, mode):
     z = np.asfortranarray(np.random.randn(n, w["N"]))
     k = wl.make_kode(w, z_state=z)
     x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
-    pick = [0, 7, B // 2, B - 1]
+    # oracle coverage: 256 (Lorenz63) / 512 (MSEIR) systems from the first, a middle and the last tiles
+    q = 64 if mode == "sim" else 128
+    pick = np.r_[0:q, B // 2 - 5:B // 2 - 5 + 2 * q, B - q:B]
     po = wl.make_oracle_problem(w)
     if mode == "sim":
         x = k.solve_sim(x0d, theta=thd)
         assert bool(torch.isfinite(x).all()) and int(k.status.abs().sum()) == 0
         ref = oracle.solve_batch(po, x0[pick], theta[pick], z, oracle.MODE_SIM)
-        got = x[pick].cpu().numpy()
-        assert traj_err(got[:, :2501], ref["x"][:, :2501]).max() < 1e-8
+        got = x[torch.from_numpy(pick).cuda()].cpu().numpy()
+        # Lorenz63 amplifies rounding differences at its Lyapunov rate (e^{0.9 t}: x 8,000 by t = 10): tight over
+        # the first 1,000 steps, 2e-8 at 2,500 (worst of these 256 systems: 6e-9), loose at the end of the horizon;
+        # per-step parity itself is pinned at 1e-12 by test_lorenz_one_step_consistency
+        assert traj_err(got[:, :1001], ref["x"][:, :1001]).max() < 1e-11
+        assert traj_err(got[:, :2501], ref["x"][:, :2501]).max() < 2e-8
         assert traj_err(got, ref["x"]).max() < 1e-3
         perm = torch.arange(B - 1, -1, -1, device="cuda")
         x = x[perm]
@@ -194,8 +202,10 @@ def test_wide_state_configs_at_full_size(maker, B, mode):
         for lo in range(0, B, 4096):                  # chunked compare: no 63 GB temporaries
             assert bool((var[lo:lo + 4096] == var[0:1]).all())
         ref = oracle.solve_batch(po, x0[pick], theta[pick], None, oracle.MODE_MV)
-        assert traj_err(mu[pick].cpu().numpy(), ref["mu"]).max() < 1e-10
-        assert var_err(var[pick].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
+        pk = torch.from_numpy(pick).cuda()
+        assert traj_err(mu[pk].cpu().numpy(), ref["mu"]).max() < 1e-10
+        # cond(R) ~ 1e10 at dt = 0.04: two FP64 implementations agree to 1.4e-9 here
+        assert var_err(var[pk].cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-8
 
 
 @pytest.mark.parametrize("maker,B,eps,reps", [
@@ -459,7 +469,7 @@ def test_checkpointed_history_is_bit_identical(maker, B, N, ck):
 
 
 @pytest.mark.parametrize("maker,B,mtol,vtol,xtol,dense_too", [
-    (wl.fitz_batch, 3000, 1e-10, 1e-9, 1e-9, True),
+    (wl.fitz_batch, 3000, 1e-10, 1e-10, 1e-9, True),
     (lambda B: wl.lorenz_batch(B, N=500, tmax=2.0), 130, 1e-9, 1e-7, 1e-8, False),
     (lambda B: wl.mseir_batch(B, N=200), 96, 1e-10, 1e-8, 1e-7, False),
     # n_eval + 1 even / a multiple of 4: the blocked output runs take their general path; ragged last tile
@@ -628,3 +638,169 @@ def test_batched_inference_front_end():
     assert np.all(np.linalg.eigvalsh(phi_var) > 0) and np.all(np.sqrt(np.diag(phi_var)) < 1.0)
     th = inf.theta_sample(phi_hat, phi_var, 1000, rng)
     assert th.shape == (1000, 3) and np.all(th > 0)
+
+
+def test_ragged_batch_every_system_against_oracle():
+    """A batch that is a multiple of nothing (12,345 systems: partial last warp, partial last 16-system
+    row of the granule stores, partial last 256-system block of the permuted history order): EVERY system
+    against the oracle, all three outputs, on both FitzHugh-Nagumo kernel generations."""
+    B = 12345
+    w, x0, theta = wl.fitz_batch(B, seed=11)
+    z = np.asfortranarray(np.random.default_rng(7).standard_normal((6, 400)))
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+    k = wl.make_kode(w, z_state=z)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    x, mu, var = k.solve(x0d, theta=thd)
+    assert int(k.status.abs().sum()) == 0 and not ref["status"].any()
+    assert traj_err(mu.cpu().numpy(), ref["mu"]).max() < 1e-10
+    assert traj_err(x.cpu().numpy(), ref["x"]).max() < 1e-9
+    assert var_err(var.cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < 1e-10
+    assert bool((var == var[0:1]).all()) and bool((var[:, 0] == 0).all())
+    mu2, var2 = k.solve_mv(x0d, theta=thd)
+    assert torch.equal(mu2, mu) and torch.equal(var2, var)
+    assert torch.equal(k.solve_sim(x0d, theta=thd), x)
+    # tiny batches: fewer systems than one 16-system row / one warp
+    for b in (1, 5, 17, 255, 257):
+        xs, ms, vs = k.solve(x0d[:b], theta=thd[:b])
+        assert torch.equal(ms, mu[:b]) and torch.equal(vs, var[:b]) and torch.equal(xs, x[:b]), b
+    # odd n_eval (n_eval + 1 even: every trajectory starts on a different granule phase), short grids
+    for N in (1, 2, 3, 7, 64, 399):
+        wn = dict(w, N=N, tmax=w["tmax"] * N / w["N"])
+        zn = np.asfortranarray(z[:, :N])
+        kn = wl.make_kode(wn, z_state=zn)
+        refn = oracle.solve_batch(wl.make_oracle_problem(wn), x0[:300], theta[:300], zn, oracle.MODE_BOTH)
+        xn, mn, vn = kn.solve(x0d[:300], theta=thd[:300])
+        assert traj_err(mn.cpu().numpy(), refn["mu"]).max() < 1e-10, N
+        assert traj_err(xn.cpu().numpy(), refn["x"]).max() < 1e-9, N
+        assert np.abs(vn.cpu().numpy() - refn["var"]).max() < 1e-10 * np.abs(refn["var"]).max() + 1e-300, N
+
+
+def _unpack_bd_record(rec, n, nb):
+    """(mu (n,), Sigma (n, n)) from one history record of the block-diagonal family: mu, then per block the
+    packed upper triangle, row-major (csrc/kalman_common.cuh)."""
+    p = n // nb
+    mu = rec[:n].copy()
+    S = np.zeros((n, n))
+    o = n
+    for b in range(nb):
+        for i in range(p):
+            for j in range(i, p):
+                S[b * p + i, b * p + j] = S[b * p + j, b * p + i] = rec[o]
+                o += 1
+    return mu, S
+
+
+def test_lorenz_one_step_consistency():
+    """SURVEY section 7 'hard parts': Lorenz63 is chaotic, so trajectories of two FP64 codes part at the Lyapunov
+    rate -- ONE step does not.  The filter history the GPU wrote (rodeo_cuda_debug_copy_history) is fed to the
+    oracle's one-step filter at time index t; the GPU's record for t+1 must equal the result to 1e-12."""
+    import ctypes
+    B, N = 64, 5000
+    w, x0, theta = wl.lorenz_batch(B, N=N)
+    k = wl.make_kode(w, checkpoint=1)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    mu, var = k.solve_mv(x0d, theta=thd)
+    torch.cuda.synchronize()
+    n, nb = 9, 3
+    NE = n + nb * 6
+    nbytes = (B // 32) * N * NE * 32 * 8
+    hist = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    from rodeo_legacy_b200.cuda import _lib
+    _lib.check(_lib.load().rodeo_cuda_debug_copy_history(k._h, ctypes.c_void_p(hist.data_ptr()), nbytes, None))
+    torch.cuda.synchronize()
+    h = hist.cpu().numpy().reshape(B // 32, N, NE, 32)      # [tile][record r = time N - r][element][lane]
+    po = wl.make_oracle_problem(w)
+    worst = 0.0
+    for b in (0, 31, 32, 63):
+        for t in (1, 10, 1234, 2500, 4000, 4998):
+            m0, S0 = _unpack_bd_record(h[b // 32, N - t, :, b % 32], n, nb)
+            m1, S1 = _unpack_bd_record(h[b // 32, N - (t + 1), :, b % 32], n, nb)
+            mo, So = oracle.filter_step(po, t, m0, S0, theta[b])
+            worst = max(worst, np.abs(mo - m1).max() / np.abs(m1).max(), np.abs(So - S1).max() / np.abs(S1).max())
+    assert worst < 1e-12, worst
+    # the terminal smoothed moments ARE the last filtered record
+    m_end, S_end = _unpack_bd_record(h[0, 0, :, 5], n, nb)
+    np.testing.assert_array_equal(mu[5, N].cpu().numpy(), m_end)
+    np.testing.assert_array_equal(var[5, N].cpu().numpy(), S_end)
+
+
+def test_config5_full_size_sweep():
+    """BASELINE config 5 at its full 1,048,576 theta draws on one GPU (the sharded form runs under torchrun in
+    bench.py): fused log-likelihoods, an oracle check of a strided 256-sample, determinism."""
+    total = 1 << 20
+    w = wl.fitz()
+    theta = wl.fitz_sweep_theta(total, 0, total, w)
+    x0 = np.tile(w["x0"], (total, 1))
+    k = wl.make_kode(w)
+    Y, ind, sind = wl.fitz_observations(k, w)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    ll = k.loglik(x0d, thd, Y, ind, sind, 0.2)
+    assert ll.shape == (total,) and bool(torch.isfinite(ll).all()) and int(k.status.abs().sum()) == 0
+    pick = np.linspace(0, total - 1, 256).astype(int)
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0[pick], theta[pick], None, oracle.MODE_MV)
+    want = [oracle.loglik(m, ind, sind, Y, 0.2) for m in ref["mu"]]
+    np.testing.assert_allclose(ll[torch.from_numpy(pick).cuda()].cpu().numpy(), want, rtol=1e-8)
+    assert torch.equal(k.loglik(x0d, thd, Y, ind, sind, 0.2), ll)
+    best = theta[int(ll.argmax())]
+    assert np.all(np.abs(np.log(best / w["theta0"])) < 0.25)
+
+
+def test_advice_round1_regressions():
+    """Round-1 advisor findings: (1) shared-covariance host path with odd B * (N+1) * n (Lorenz63, n = 9, odd
+    batch, even n_eval, solve()); (2) property getters are read-only views; (3) caller-provided host output
+    buffers are validated; (4) the batched-prior entry point refuses misaligned device outputs."""
+    import ctypes
+    w, x0, theta = wl.lorenz_batch(33, N=300, tmax=1.2)
+    z = np.asfortranarray(np.random.default_rng(3).standard_normal((9, 300)))
+    ks = wl.make_kode(w, z_state=z, shared_cov=True)
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+    for b in (33, 1):                                   # odd batch, and the reference's own call shape (1-D x0)
+        xa, ma, va = ks.solve(x0[:b] if b > 1 else np.asfortranarray(x0[0]), theta=theta[:b] if b > 1 else theta[0])
+        assert traj_err(ma, ref["mu"][:b] if b > 1 else ref["mu"][0]).max() < 1e-9
+        assert traj_err(xa, ref["x"][:b] if b > 1 else ref["x"][0]).max() < 1e-8
+    w15, x15, th15 = wl.mseir_batch(7, N=100)
+    z15 = np.asfortranarray(np.random.default_rng(4).standard_normal((15, 100)))
+    k15 = wl.make_kode(w15, z_state=z15, shared_cov=True)
+    r15 = oracle.solve_batch(wl.make_oracle_problem(w15), x15, th15, z15, oracle.MODE_BOTH)
+    x_, m_, v_ = k15.solve(x15, theta=th15)
+    assert traj_err(m_, r15["mu"]).max() < 1e-10 and traj_err(x_, r15["x"]).max() < 1e-7
+    # (2)
+    wf = wl.fitz()
+    k = wl.make_kode(wf)
+    for name in ("wgt_meas", "mu_state", "wgt_state", "var_state", "z_state"):
+        with pytest.raises(ValueError, match="read-only"):
+            getattr(k, name)[...] = 0.0
+    k.mu_state = np.full(6, 1e-3)                       # the setter is the way in; it reaches the device
+    mu_c, _ = k.solve_mv(wf["x0"], theta=wf["theta0"])
+    k.mu_state = np.zeros(6)
+    mu_0, _ = k.solve_mv(wf["x0"], theta=wf["theta0"])
+    assert np.abs(mu_c - mu_0).max() > 1e-6
+    # (3)
+    x0b, thb = np.tile(wf["x0"], (4, 1)), np.tile(wf["theta0"], (4, 1))
+    good_mu, good_var = np.empty((4, 401, 6)), np.empty((4, 401, 6, 6))
+    k.solve_mv_into(x0b, thb, good_mu, good_var)
+    np.testing.assert_array_equal(good_mu[0], mu_0)
+    for bad_mu, bad_var in ((np.empty((4, 401, 6), dtype=np.float32), good_var), (good_mu, np.empty((4, 401, 6, 6))[:, ::2]),
+                            (good_mu, np.empty((3, 401, 6, 6))), (np.empty((6, 401, 4)).transpose(2, 1, 0), good_var)):
+        with pytest.raises(TypeError):
+            k.solve_mv_into(x0b, thb, bad_mu, bad_var)
+    ksc = wl.make_kode(wf, shared_cov=True)
+    with pytest.raises(TypeError, match="incorrect shape"):
+        ksc.solve_mv_into(x0b, thb, good_mu, good_var)          # shared mode wants ONE (N+1, n, n) array
+    ksc.solve_mv_into(x0b, thb, good_mu, np.empty((401, 6, 6)))
+    # (4)
+    lib = _lib_load()
+    buf = torch.zeros(2 * 401 * 42 + 8, dtype=torch.float64, device="cuda")
+    x0d = torch.from_numpy(np.tile(wf["x0"], (2, 1))).cuda()
+    thd = torch.from_numpy(np.tile(wf["theta0"], (2, 1))).cuda()
+    st = torch.zeros(2, dtype=torch.int32, device="cuda")
+    mu_p, var_p = buf.data_ptr() + 8, buf.data_ptr() + 8 + 2 * 401 * 6 * 8
+    V = ctypes.c_void_p
+    rc = lib.rodeo_cuda_solve_batched_prior(k._h, 1, 2, V(x0d.data_ptr()), V(thd.data_ptr()), None, 0, None, None, None,
+                                            None, None, V(mu_p), V(var_p), V(st.data_ptr()), None)
+    assert rc == -1 and b"16-byte aligned" in lib.rodeo_cuda_last_error()
+
+
+def _lib_load():
+    from rodeo_legacy_b200.cuda import _lib
+    return _lib.load()
