@@ -273,6 +273,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the dense / shared-covariance / C5 side measurements")
+    ap.add_argument("--no-structure", action="store_true",
+                    help="general block-diagonal kernels (no upper-triangular-Q / unit-w specialisation)")
     ap.add_argument("--dense", action="store_true",
                     help="force the general dense kernel family (default: block-diagonal is auto-selected)")
     args = ap.parse_args()
@@ -312,8 +314,8 @@ def main():
 
     B = args.batch
     w, x0, theta = wl.fitz_batch(B, seed=rank)
-    k = wl.make_kode(w, force_dense=args.dense)
-    family = "/".join(k.kernel_family)
+    k = wl.make_kode(w, force_dense=args.dense, use_structure=not args.no_structure)
+    family = "/".join(k.kernel_family) + ("/structured" if k.structured else "")
     k.reserve(B)
     x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
 
@@ -535,7 +537,8 @@ def main():
         f64 = fp64_peak() if not args.no_extras else None
         bwd_s, fwd_s = bwd_ms * 1e-3, fwd_ms * 1e-3
         step_s = ms * 1e-3 / args.steps
-        kname = "kalman_backward_tpb" if family == "blockdiag/registers" else "kalman_backward_staged"
+        tpb = family.startswith("blockdiag/registers")
+        kname = "kalman_backward_tpb" if tpb else "kalman_backward_staged"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -555,7 +558,7 @@ def main():
                          "algorithmic_note": "SURVEY 8(d) bytes (the reference's four dense history arrays + the output); "
                                              "the kernel moves fewer because predicted moments are recomputed, covariances "
                                              "are stored packed per block and every second record is re-run (checkpoint 2)",
-                         "forward": {"kernel": "kalman_forward_tpb" if family == "blockdiag/registers" else "kalman_forward",
+                         "forward": {"kernel": "kalman_forward_tpb" if tpb else "kalman_forward",
                                      "kernel_ms": fwd_ms, "traffic": traffic["forward"],
                                      "achieved": traffic["forward"] / fwd_s / 1e9,
                                      "frac": traffic["forward"] / fwd_s / 1e9 / peak,

@@ -77,14 +77,31 @@ static bool is_block_diagonal(const rodeo_problem *p) {
   return true;
 }
 
+// A block-diagonal prior whose Q blocks are all upper triangular and whose W rows are the unit vector
+// e_order inside their block (ibm_init + zero_pad): the structured kernel sets skip the exact zeros.
+static bool is_structured(const rodeo_problem *p) {
+  const int n = p->n, m = p->m, bs = n / m, ord = ode_order(p->ode);
+  if (ord < 0 || ord >= bs) return false;
+  for (int b = 0; b < m; b++) {
+    for (int j = 0; j < bs; j++) {
+      for (int i = j + 1; i < bs; i++)
+        if (p->Q[(b * bs + i) + (size_t)(b * bs + j) * n] != 0.0) return false;      // strictly lower part
+      if (p->W[b + (size_t)(b * bs + j) * m] != (j == ord ? 1.0 : 0.0)) return false;
+    }
+  }
+  return true;
+}
+
 // Pick the kernel family for the current (Q, R, W): block-diagonal when the structure is
 // there (and not disabled by RODEO_FLAG_FORCE_DENSE), dense otherwise.
 static int select_kernel_set(rodeo_problem *p) {
   const KernelSet *dense = find_kernel_set(p->ode, p->n, false), *bd = find_kernel_set(p->ode, p->n, true);
   const bool structured = is_block_diagonal(p);
   const KernelSet *ks = nullptr;
-  if (bd && structured && !(p->flags & RODEO_FLAG_FORCE_DENSE)) ks = bd;
-  else if (dense) ks = dense;
+  if (bd && structured && !(p->flags & RODEO_FLAG_FORCE_DENSE)) {
+    const KernelSet *bds = find_kernel_set(p->ode, p->n, true, true);
+    ks = (bds && !(p->flags & RODEO_FLAG_NO_STRUCTURE) && is_structured(p)) ? bds : bd;
+  } else if (dense) ks = dense;
   if (!ks) {
     char buf[256];
     snprintf(buf, sizeof buf,
@@ -233,6 +250,7 @@ int rodeo_cuda_set_shared_cov(rodeo_problem *p, int enabled) {
 }
 
 int rodeo_cuda_get_shared_cov(const rodeo_problem *p) { return p ? (p->shared ? 1 : 0) : RODEO_E_INVALID; }
+int rodeo_cuda_problem_structured(const rodeo_problem *p) { return p ? (p->ks->structured ? 1 : 0) : RODEO_E_INVALID; }
 
 int rodeo_cuda_set_checkpoint(rodeo_problem *p, int interval) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");

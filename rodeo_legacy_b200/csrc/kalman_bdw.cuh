@@ -64,7 +64,8 @@ struct BdwBlock {
     const double *rmu = rec + A * p * kTile, *rS = rec + (n + A * PS) * kTile;
     const double *z = DO_SIM ? zt + A * p : nullptr;
     if (terminal) return reg::smooth_terminal<p, kTile, DO_MEAN, DO_VAR, DO_SIM>(rmu, rS, z, mus, Ss, x);
-    return reg::smooth_step<p, kTile, DO_MEAN, DO_VAR, DO_SIM>(P.Q[A], P.c + A * p, P.R[A], rmu, rS, z, mus, Ss, x);
+    return reg::smooth_step<p, kTile, DO_MEAN, DO_VAR, DO_SIM, true, Fam::kUT>(P.Q[A], P.c + A * p, P.R[A], rmu, rS, z,
+                                                                                 mus, Ss, x);
   }
 };
 

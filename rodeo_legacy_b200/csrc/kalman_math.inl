@@ -60,14 +60,20 @@ RD_UNROLL_IN
   }
 }
 
+// Structured priors (detected on the host, api.cu: is_structured).  UT: Q is upper triangular (what ibm_init
+// produces: a Toeplitz upper-triangular transition block); the terms with an exactly-zero coefficient are
+// skipped, the others are accumulated in the same order, so for finite data the results are bit-identical
+// to the general code (x * 0 = 0 and s + 0 = s exactly).  WK >= 0: w = e_WK (zero_pad puts a single 1 per
+// row of wgt_meas, at the ODE's order): products with w reduce to picking element WK.
+
 // mu_pred = Q mu + c                                         (KalmanTV.h:287-288)
-template <int n>
+template <int n, bool UT = false>
 RD_HD void predict_mean(const double *Q, const double *c, const double *mu, double *mup) {
 RD_UNROLL
   for (int i = 0; i < n; i++) {
     double s = c[i];
 RD_UNROLL_IN
-    for (int k = 0; k < n; k++) s += Q[i * n + k] * mu[k];
+    for (int k = UT ? i : 0; k < n; k++) s += Q[i * n + k] * mu[k];
     mup[i] = s;
   }
 }
@@ -75,7 +81,7 @@ RD_UNROLL_IN
 // Sp = Q S Q^T + R (packed)                                  (KalmanTV.h:290-292)
 // With KEEP_T the full product T = Q S (row-major n x n) is also returned (it is the
 // smoother's Q Sigma_f^T, KalmanTV.h:456).
-template <int n, bool KEEP_T>
+template <int n, bool KEEP_T, bool UT = false>
 RD_HD void predict_var(const double *Q, const double *R, const double *S, double *Sp, double *T) {
 RD_UNROLL
   for (int i = 0; i < n; i++) {
@@ -84,7 +90,7 @@ RD_UNROLL
     for (int k = 0; k < n; k++) {
       double s = 0.0;
 RD_UNROLL_IN
-      for (int l = 0; l < n; l++) s += Q[i * n + l] * S[sidx<n>(l, k)];
+      for (int l = UT ? i : 0; l < n; l++) s += Q[i * n + l] * S[sidx<n>(l, k)];
       Ti[k] = s;
       if (KEEP_T) T[i * n + k] = s;
     }
@@ -92,7 +98,7 @@ RD_UNROLL
     for (int j = i; j < n; j++) {
       double s = R[sidx<n>(i, j)];
 RD_UNROLL_IN
-      for (int k = 0; k < n; k++) s += Ti[k] * Q[j * n + k];
+      for (int k = UT ? j : 0; k < n; k++) s += Ti[k] * Q[j * n + k];
       Sp[sidx<n>(i, j)] = s;
     }
   }
@@ -164,22 +170,30 @@ RD_UNROLL_IN
 // The same update for ONE diagonal block with a scalar measurement  y_a = w^T x_a:
 //   A = w^T Sp; s = A w (+ A w under probde); K = A / s; mu_f = mu_p + K (y_a - w^T mu_p);
 //   Sf = Sp - A^T K.   The m x m Cholesky of the dense update degenerates to one division.
-template <int p>
+template <int p, int WK = -1>
 RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool zero_H,
                        double *dumpK = nullptr) {
   double A[p];
   double s = 0.0, e = ya;
+  if (WK >= 0) {                 // w = e_WK: A = row WK of Sp, s = Sp(WK, WK), e = y - mu_p[WK]
+    constexpr int K = WK >= 0 ? WK : 0;
 RD_UNROLL
-  for (int j = 0; j < p; j++) {
-    double v = 0.0;
+    for (int j = 0; j < p; j++) A[j] = S[sidx<p>(K, j)];
+    s = A[K];
+    e = sub_rn(ya, mu[K]);
+  } else {
+RD_UNROLL
+    for (int j = 0; j < p; j++) {
+      double v = 0.0;
 RD_UNROLL_IN
-    for (int k = 0; k < p; k++) v += w[k] * S[sidx<p>(k, j)];
-    A[j] = v;
-  }
+      for (int k = 0; k < p; k++) v += w[k] * S[sidx<p>(k, j)];
+      A[j] = v;
+    }
 RD_UNROLL
-  for (int j = 0; j < p; j++) {
-    s += A[j] * w[j];
-    e -= w[j] * mu[j];
+    for (int j = 0; j < p; j++) {
+      s += A[j] * w[j];
+      e -= w[j] * mu[j];
+    }
   }
   if (!zero_H) s = s + s;
   const int fail = (s > 0.0) ? 0 : 1;
@@ -263,7 +277,7 @@ struct RecReader<false> {
   RD_HD double operator[](int i) const { return q[i]; }
 };
 
-template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool REREAD = true>
+template <int n, int STRIDE, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool REREAD = true, bool UT = false>
 RD_HD int smooth_step(const double *Q, const double *c, const double *R, const double *rec_mu,
                       const double *rec_S, const double *zt_ptr, double *mus, double *Ss, double *x,
                       double *dumpT = nullptr, double *dumpL = nullptr) {
@@ -277,8 +291,8 @@ RD_UNROLL
 RD_UNROLL
     for (int i = 0; i < NS; i++) Sf[i] = rec_S[i * STRIDE];
     // predicted moments at t+1, recomputed exactly as the forward pass computed them
-    predict_mean<n>(Q, c, muf, mup);
-    predict_var<n, true>(Q, R, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
+    predict_mean<n, UT>(Q, c, muf, mup);
+    predict_var<n, true, UT>(Q, R, Sf, Sp, T);  // T = Q Sigma_f  (KalmanTV.h:456)
   }
   if (DO_VAR) {                              // D = Sigma_s(t+1) - Sigma_p(t+1)  (:460)
 RD_UNROLL
@@ -327,7 +341,7 @@ RD_UNROLL
       for (int j = 0; j < n; j++) {
         double s = 0.0;
 RD_UNROLL_IN
-        for (int l = 0; l < n; l++) s += Q[k * n + l] * Sf[sidx<n>(l, j)];
+        for (int l = UT ? k : 0; l < n; l++) s += Q[k * n + l] * Sf[sidx<n>(l, j)];
         Tk[j] = s;
       }
 RD_UNROLL

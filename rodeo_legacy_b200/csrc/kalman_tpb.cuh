@@ -343,8 +343,8 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
         // re-run the filter t0 -> t0 + 1 (BdFam::step, this block's share; the right-hand side needs every
         // block's predicted first component: one shuffle per block)
         double fm[p], fS[PS];
-        reg::predict_mean<p>(bp.Q(), bp.c(), cm, fm);
-        reg::predict_var<p, false>(bp.Q(), bp.R(), cS, fS, nullptr);
+        reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), cm, fm);
+        reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), cS, fS, nullptr);
         double X[n], y[Fam::m];
 #pragma unroll
         for (int e = 0; e < n; e++) X[e] = 0.0;
@@ -355,16 +355,16 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
         double ya = y[0];
 #pragma unroll
         for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
-        reg::update_block<p>(bp.w(), fm, fS, ya, false);
+        reg::update_block<p, Fam::kWK>(bp.w(), fm, fS, ya, false);
         const int t = t0 + 1;
-        const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false>(
+        const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false, Fam::kUT>(
             bp.Q(), bp.c(), bp.R(), fm, fS, DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
         if (f && !fail) fail = f;
         emit(t, mus, Ss, x);
       }
     }
     if (base >= 1) {
-      const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false>(
+      const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false, Fam::kUT>(
           bp.Q(), bp.c(), bp.R(), cm, cS, DO_SIM ? zb + (long)(base - 1) * n : nullptr, mus, Ss, x);
       if (f && !fail) fail = f;
       emit(base, mus, Ss, x);
@@ -442,8 +442,8 @@ kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
   int until = back % ck;       // steps until the next stored record
   for (int t = 0; t < N; t++, back--) {
     double mup[p], Sp[PS];
-    reg::predict_mean<p>(bp.Q(), bp.c(), mu, mup);
-    reg::predict_var<p, false>(bp.Q(), bp.R(), S, Sp, nullptr);
+    reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), mu, mup);
+    reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), S, Sp, nullptr);
     double X[n], y[Fam::m], lead = mup[0];
     int f = 0;
     if (IG == IG_CHKREBTII) {   // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
@@ -464,7 +464,7 @@ kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
     double ya = y[0];
 #pragma unroll
     for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
-    const int f2 = reg::update_block<p>(bp.w(), mup, Sp, ya, IG == IG_SCHOBERT);
+    const int f2 = reg::update_block<p, Fam::kWK>(bp.w(), mup, Sp, ya, IG == IG_SCHOBERT);
     if ((f | f2) && t_fail == 0x7fffffff) t_fail = t;
 #pragma unroll
     for (int e = 0; e < p; e++) mu[e] = mup[e];

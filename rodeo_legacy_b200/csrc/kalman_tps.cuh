@@ -81,16 +81,16 @@ namespace rodeo {
 // Family selector: Fam<UNROLL, BD, Ode, K> is the dense family with n_state = K (BD = false)
 // or the block-diagonal family with block size K (BD = true), in the register (UNROLL) or
 // rolled loop policy.
-template <bool UNROLL, bool BD, class Ode, int K>
+template <bool UNROLL, bool BD, class Ode, int K, bool ST = false>
 struct FamSel;
 template <class Ode, int K>
-struct FamSel<true, false, Ode, K> { using type = reg::DenseFam<Ode, K>; };
+struct FamSel<true, false, Ode, K, false> { using type = reg::DenseFam<Ode, K>; };
+template <class Ode, int K, bool ST>
+struct FamSel<true, true, Ode, K, ST> { using type = reg::BdFam<Ode, K, ST>; };
 template <class Ode, int K>
-struct FamSel<true, true, Ode, K> { using type = reg::BdFam<Ode, K>; };
+struct FamSel<false, false, Ode, K, false> { using type = loc::DenseFam<Ode, K>; };
 template <class Ode, int K>
-struct FamSel<false, false, Ode, K> { using type = loc::DenseFam<Ode, K>; };
-template <class Ode, int K>
-struct FamSel<false, true, Ode, K> { using type = loc::BdFam<Ode, K>; };
+struct FamSel<false, true, Ode, K, false> { using type = loc::BdFam<Ode, K>; };
 
 template <bool UNROLL>
 struct Bodies;

@@ -63,9 +63,15 @@ RD_UNROLL
   RD_HD static double var_at(const double *Ss, int i, int j) { return Ss[sidx<n>(i, j)]; }
 };
 
-template <class Ode_, int p_>
+// ST ("structured"): every block's Q is upper triangular and w = e_{Ode::order} (ibm_init + zero_pad priors of
+// a first/second-order ODE: every BASELINE config); see kalman_math.inl.  Selected on the host; same results.
+template <class Ode_, int p_, bool ST_ = false>
 struct BdFam {
   using Ode = Ode_;
+  static constexpr bool kUT = ST_;
+  static constexpr int kWK = ST_ ? Ode_::order : -1;
+  using General = BdFam<Ode_, p_, false>;        // the same family without the specialisation (same results)
+  static_assert(!ST_ || Ode_::order < p_, "the unit entry of w must lie inside the block");
   static constexpr int p = p_, nb = Ode::n_meas, n = p_ * Ode_::n_meas, m = Ode::n_meas;
   static constexpr int PS = Sym<p_>::size, NS = Ode_::n_meas * Sym<p_>::size, NE = n + NS;
   static constexpr bool kBlockDiag = true;
@@ -78,8 +84,8 @@ struct BdFam {
     int fail = 0;
 RD_UNROLL
     for (int blk = 0; blk < nb; blk++) {
-      predict_mean<p>(P.Q[blk], P.c + blk * p, mu + blk * p, mup + blk * p);
-      predict_var<p, false>(P.Q[blk], P.R[blk], S + blk * PS, Sp + blk * PS, nullptr);
+      predict_mean<p, kUT>(P.Q[blk], P.c + blk * p, mu + blk * p, mup + blk * p);
+      predict_var<p, false, kUT>(P.Q[blk], P.R[blk], S + blk * PS, Sp + blk * PS, nullptr);
     }
     const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / P.n_eval;
     if (IG == IG_CHKREBTII) {  // chol of a block-diagonal matrix is the blocks' chol
@@ -100,7 +106,7 @@ RD_UNROLL
     }
 RD_UNROLL
     for (int blk = 0; blk < nb; blk++) {
-      int f = update_block<p>(P.w[blk], mup + blk * p, Sp + blk * PS, y[blk], IG == IG_SCHOBERT);
+      int f = update_block<p, kWK>(P.w[blk], mup + blk * p, Sp + blk * PS, y[blk], IG == IG_SCHOBERT);
       if (f && !fail) fail = blk + 1;
     }
 RD_UNROLL
@@ -129,7 +135,7 @@ RD_UNROLL
     int fail = 0;
 RD_UNROLL
     for (int blk = 0; blk < nb; blk++) {
-      int f = smooth_step<p, STRIDE, DO_MEAN, DO_VAR, DO_SIM>(
+      int f = smooth_step<p, STRIDE, DO_MEAN, DO_VAR, DO_SIM, true, kUT>(
           P.Q[blk], P.c + blk * p, P.R[blk], rec + blk * p * STRIDE, rec + (n + blk * PS) * STRIDE,
           DO_SIM ? zt + blk * p : nullptr, mus + blk * p, Ss + blk * PS, x + blk * p);
       if (f && !fail) fail = blk * p + f;

@@ -144,13 +144,20 @@ void fill_backward(KernelSet &k) {
     // two diagonal blocks (FitzHugh-Nagumo): one thread per block, history prefetched into registers,
     // outputs as whole 256-byte-aligned granules through TMA tensor stores (kalman_tpb.cuh); these
     // launchers need the history in the permuted order (backward_perm -> SolveArgs::perm16)
-    k.backward[CKI][BK_MV] = launch_backward_tpb<Fam, CK, true, true, false>;
-    k.backward[CKI][BK_SIM] = launch_backward_tpb<Fam, CK, false, false, true>;
-    k.backward[CKI][BK_BOTH] = launch_backward_tpb<Fam, CK, true, true, true>;
+    // The smoothers that write per-step outputs are HBM-bound: the structured arithmetic buys them nothing and
+    // measured 3 % slower (FN solve_mv 2.03 -> 2.10 ms: same register cap, one spill), so the structured sets
+    // reuse the general family's instantiation there (bit-identical results; also halves the build).  The
+    // FP64-bound kernels (forward filters, log-likelihood smoothers) do use the specialisation.
+    using FamB = typename Fam::General;
+    k.backward[CKI][BK_MV] = launch_backward_tpb<FamB, CK, true, true, false>;
+    k.backward[CKI][BK_SIM] = launch_backward_tpb<FamB, CK, false, false, true>;
+    k.backward[CKI][BK_BOTH] = launch_backward_tpb<FamB, CK, true, true, true>;
     k.backward_perm[CKI][BK_MV] = k.backward_perm[CKI][BK_SIM] = k.backward_perm[CKI][BK_BOTH] = true;
-    k.backward_alt[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
-    k.backward_alt[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
-    k.backward_alt[CKI][BK_BOTH] = launch_backward_staged<Fam, CK, true, true, true>;
+    if constexpr (!Fam::kUT) {   // the round-1 smoother, kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
+      k.backward_alt[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
+      k.backward_alt[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
+      k.backward_alt[CKI][BK_BOTH] = launch_backward_staged<Fam, CK, true, true, true>;
+    }
   } else if constexpr (UNROLL) {  // registers: history and outputs staged through shared memory
     k.backward[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
     k.backward[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
@@ -170,10 +177,11 @@ void fill_backward(KernelSet &k) {
 }
 
 // K = n_state for the dense family, block size p for the block-diagonal family.
-template <class Ode, int K, bool BD, bool UNROLL>
+template <class Ode, int K, bool BD, bool UNROLL, bool ST = false>
 KernelSet make_kernel_set(const char *name) {
-  using Fam = typename FamSel<UNROLL, BD, Ode, K>::type;
+  using Fam = typename FamSel<UNROLL, BD, Ode, K, ST>::type;
   KernelSet k;
+  k.structured = ST;
   k.ode = Ode::id;
   k.n = Fam::n;
   k.m = Ode::n_meas;

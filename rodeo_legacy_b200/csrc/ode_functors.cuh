@@ -11,7 +11,7 @@
 namespace rodeo {
 
 struct OdeChkrebtii {
-  static constexpr int id = 0, n_meas = 1, n_theta = 0;
+  static constexpr int id = 0, n_meas = 1, n_theta = 0, order = 2;   // x'' = ...: W picks the 2nd derivative
   template <int n>
   RD_HD static void eval(const double *X, double t, const double *, double *out) {
     out[0] = sin(2 * t) - X[0];
@@ -19,7 +19,7 @@ struct OdeChkrebtii {
 };
 
 struct OdeFitz {
-  static constexpr int id = 1, n_meas = 2, n_theta = 3;
+  static constexpr int id = 1, n_meas = 2, n_theta = 3, order = 1;
   template <int n>
   RD_HD static void eval(const double *X, double t, const double *th, double *out) {
     constexpr int p = n / 2;
@@ -31,7 +31,7 @@ struct OdeFitz {
 };
 
 struct OdeLorenz63 {
-  static constexpr int id = 2, n_meas = 3, n_theta = 3;
+  static constexpr int id = 2, n_meas = 3, n_theta = 3, order = 1;
   template <int n>
   RD_HD static void eval(const double *X, double t, const double *th, double *out) {
     constexpr int p = n / 3;
@@ -44,7 +44,7 @@ struct OdeLorenz63 {
 };
 
 struct OdeMseir {
-  static constexpr int id = 3, n_meas = 5, n_theta = 6;
+  static constexpr int id = 3, n_meas = 5, n_theta = 6, order = 1;
   template <int n>
   RD_HD static void eval(const double *X, double t, const double *th, double *out) {
     constexpr int p = n / 5;

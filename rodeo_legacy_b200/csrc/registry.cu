@@ -8,6 +8,7 @@ namespace rodeo {
 #define RODEO_REG(name) void register_##name(KernelSet *, int *);
 RODEO_REG(chkrebtii_dense) RODEO_REG(chkrebtii_bd) RODEO_REG(fitz_dense) RODEO_REG(fitz_bd)
 RODEO_REG(lorenz_dense) RODEO_REG(lorenz_bd) RODEO_REG(mseir_dense) RODEO_REG(mseir_bd)
+RODEO_REG(chkrebtii_bds) RODEO_REG(fitz_bds) RODEO_REG(lorenz_bds) RODEO_REG(mseir_bds)
 #undef RODEO_REG
 
 void attach_wide(KernelSet *, int);   // kernels_wide.cu
@@ -26,6 +27,10 @@ static void fill_sets() {
   register_lorenz_bd(g_sets, &c);
   register_mseir_dense(g_sets, &c);
   register_mseir_bd(g_sets, &c);
+  register_chkrebtii_bds(g_sets, &c);
+  register_fitz_bds(g_sets, &c);
+  register_lorenz_bds(g_sets, &c);
+  register_mseir_bds(g_sets, &c);
   attach_wide(g_sets, c);
   g_count = c;
 }
@@ -42,6 +47,15 @@ int ode_n_meas(int ode) {
     default: return -1;
   }
 }
+int ode_order(int ode) {
+  switch (ode) {
+    case OdeChkrebtii::id: return OdeChkrebtii::order;
+    case OdeFitz::id: return OdeFitz::order;
+    case OdeLorenz63::id: return OdeLorenz63::order;
+    case OdeMseir::id: return OdeMseir::order;
+    default: return -1;
+  }
+}
 int ode_n_theta(int ode) {
   switch (ode) {
     case OdeChkrebtii::id: return OdeChkrebtii::n_theta;
@@ -52,10 +66,12 @@ int ode_n_theta(int ode) {
   }
 }
 
-const KernelSet *find_kernel_set(int ode, int n, bool blockdiag) {
+const KernelSet *find_kernel_set(int ode, int n, bool blockdiag, bool structured) {
   init_sets();
   for (int i = 0; i < g_count; i++)
-    if (g_sets[i].ode == ode && g_sets[i].n == n && g_sets[i].blockdiag == blockdiag) return &g_sets[i];
+    if (g_sets[i].ode == ode && g_sets[i].n == n && g_sets[i].blockdiag == blockdiag &&
+        g_sets[i].structured == structured)
+      return &g_sets[i];
   return nullptr;
 }
 int kernel_set_count() {

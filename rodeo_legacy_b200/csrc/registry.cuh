@@ -30,6 +30,7 @@ struct KernelSet {
   int ode, n, m;
   bool blockdiag;                 // block-diagonal family (needs structured Q, R, W) or dense
   bool registers;                 // fully unrolled register kernels (else rolled / local memory)
+  bool structured;                // block-diagonal family specialised for upper-triangular Q blocks and w = e_order
   const char *name;
   launch_fn forward[3];           // by interrogation variant
   launch_fn forward_perm[3];      // forward pass that writes the permuted history order (nullptr: forward[] honours perm16)
@@ -60,7 +61,8 @@ struct KernelSet {
 int ode_count();                 // registered right-hand sides: ids 0 .. ode_count() - 1
 int ode_n_meas(int ode);         // from the functors (ode_functors.cuh); -1 for an unknown id
 int ode_n_theta(int ode);
-const KernelSet *find_kernel_set(int ode, int n, bool blockdiag);
+int ode_order(int ode);          // order of the ODE: the derivative zero_pad's wgt_meas picks in every block
+const KernelSet *find_kernel_set(int ode, int n, bool blockdiag, bool structured = false);
 int kernel_set_count();
 const KernelSet *kernel_set_at(int i);
 

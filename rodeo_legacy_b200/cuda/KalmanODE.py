@@ -99,7 +99,7 @@ def _ptr(t):
 class KalmanODE:
     def __init__(self, W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state,
                  z_state=None, interrogate="probde", device=None, force_dense=False, checkpoint=0,
-                 shared_cov=False):
+                 shared_cov=False, use_structure=True):
         self._lib = _lib.load()                      # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
@@ -132,7 +132,8 @@ class KalmanODE:
             raise ValueError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        desc = _lib.ProblemDesc(n, m, self.n_eval, self._ode, self._ig, int(bool(force_dense)),
+        desc = _lib.ProblemDesc(n, m, self.n_eval, self._ode, self._ig,
+                                int(bool(force_dense)) | (0 if use_structure else 2),
                                 self.tmin, self.tmax,
                                 self._wgt_meas.ctypes.data, self._wgt_state.ctypes.data,
                                 self._mu_state.ctypes.data, self._var_state.ctypes.data)
@@ -235,6 +236,13 @@ class KalmanODE:
         bd, rg, _ = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _lib.check(self._lib.rodeo_cuda_problem_info(self._h, ctypes.byref(bd), ctypes.byref(rg), ctypes.byref(_)))
         return ("blockdiag" if bd.value else "dense", ("rolled", "registers", "wide")[rg.value])
+
+    @property
+    def structured(self):
+        """True when the block-diagonal kernels specialised for ibm_init / zero_pad priors are in use (every Q
+        block upper triangular, every W row a unit vector): they skip the exactly-zero terms, same bits.
+        ``use_structure=False`` keeps the general block-diagonal kernels."""
+        return bool(self._lib.rodeo_cuda_problem_structured(self._h))
 
     @property
     def shared_cov(self):

@@ -34,6 +34,7 @@ SYMBOLS = [
     ("rodeo_cuda_problem_destroy", _I, [_V]),
     ("rodeo_cuda_problem_set", _I, [_V, _I, _V]),
     ("rodeo_cuda_problem_info", _I, [_V, c_int_p, c_int_p, c_int_p]),
+    ("rodeo_cuda_problem_structured", _I, [_V]),
     ("rodeo_cuda_history_bytes_per_system", _Z, [_V]),
     ("rodeo_cuda_set_workspace_limit", _I, [_V, _Z]),
     ("rodeo_cuda_set_checkpoint", _I, [_V, _I]),

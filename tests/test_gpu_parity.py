@@ -804,3 +804,49 @@ def test_advice_round1_regressions():
 def _lib_load():
     from rodeo_legacy_b200.cuda import _lib
     return _lib.load()
+
+
+@pytest.mark.parametrize("maker,B", [
+    (wl.fitz_batch, 2000), (lambda B: wl.lorenz_batch(B, N=400, tmax=1.6), 130), (lambda B: wl.mseir_batch(B, N=150), 70),
+    (lambda B: (wl.chkrebtii(150), np.tile(wl.chkrebtii(150)["x0"], (B, 1)) * (1 + 1e-3 * np.arange(B)[:, None]), None), 40)])
+def test_structured_prior_kernels_are_bit_identical(maker, B):
+    """ibm_init + zero_pad priors (upper-triangular Q blocks, unit-vector W rows) select the structured
+    block-diagonal kernels, which skip the exactly-zero terms: the outputs must equal the general block-diagonal
+    kernels' bit for bit (solve, loglik, checkpoint 1 and auto), and a CAR prior (dense Q blocks) must not select
+    them."""
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(9).standard_normal((n, w["N"])))
+    x0d = torch.from_numpy(x0).cuda()
+    thd = None if theta is None else torch.from_numpy(theta).cuda()
+    for ck in (0, 1):
+        ks = wl.make_kode(w, z_state=z, checkpoint=ck)
+        kg = wl.make_kode(w, z_state=z, checkpoint=ck, use_structure=False)
+        assert ks.structured and not kg.structured and ks.kernel_family == kg.kernel_family == ("blockdiag", "registers")
+        for a, b in zip(ks.solve(x0d, theta=thd), kg.solve(x0d, theta=thd)):
+            assert torch.equal(a, b)
+        for a, b in zip(ks.solve_mv(x0d, theta=thd), kg.solve_mv(x0d, theta=thd)):
+            assert torch.equal(a, b)
+        assert torch.equal(ks.status, kg.status)
+        if n == 6:
+            ind = np.arange(10, w["N"] + 1, 10)
+            Y = np.random.default_rng(1).standard_normal((len(ind), 2))
+            for draw in (False, True):
+                assert torch.equal(ks.loglik(x0d, thd, Y, ind, [0, 3], 0.3, use_draw=draw),
+                                   kg.loglik(x0d, thd, Y, ind, [0, 3], 0.3, use_draw=draw))
+    # a W row that is not the unit vector, or a Q block with a non-zero below the diagonal: general kernels
+    w2 = dict(w)
+    w2["W"] = np.asfortranarray(np.asarray(w["W"]) * 2.0)
+    assert not wl.make_kode(w2, z_state=z).structured
+    w3 = dict(w)
+    Q3 = np.array(w["Q"], order="F")
+    Q3[1, 0] = 1e-6
+    w3["Q"] = Q3
+    k3 = wl.make_kode(w3, z_state=z)
+    assert not k3.structured and k3.kernel_family[0] == "blockdiag"
+
+
+def test_structured_flag_on_car_prior():
+    g = load_golden("lorenz_car_n600")
+    k = _kode_from_golden(g, "lorenz_car_n600", z_state=np.asfortranarray(g["z"]))
+    assert k.kernel_family[0] == "blockdiag" and not k.structured
