@@ -283,6 +283,12 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    # stdout carries exactly ONE line (the JSON): anything libraries print there (NCCL's version banner, ...)
+    # goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -578,7 +584,8 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "status_nonzero": status_bad,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
