@@ -220,15 +220,16 @@ int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t 
   return RODEO_OK;
 }
 
-// checkpoint interval actually used: the requested one where a kernel exists for it
-static int effective_ck(const rodeo_problem *p) {
+// checkpoint interval actually used by entry point `bk`: the requested one where a kernel exists for it
+static int effective_ck(const rodeo_problem *p, int bk = BK_MV) {
   // auto: interval 2 for the block-diagonal family (measured on B200: FN solve_mv 3.28 -> 2.85 ms,
   // log-likelihood sweep 2.88 -> 2.30 ms; interval 4 is slower again), 1 for the dense family
-  // (its filter step is FP64-bound: re-running it took the backward kernel from 3.4 to 5.9 ms)
+  // (its filter step is FP64-bound: re-running it took the backward kernel from 3.4 to 5.9 ms).
+  // Families with >= 3 blocks have checkpointed kernels for solve_sim only (kalman_tpx.cuh).
   const int want = p->ck == 0 ? (p->ks->blockdiag ? 2 : 1) : p->ck;
   if (want == 1 || p->ig != RODEO_INTERROGATE_PROBDE) return 1;
   const int slot = ck_slot(want);
-  return (slot >= 0 && p->ks->backward[slot][BK_MV]) ? want : 1;
+  return (slot >= 0 && p->ks->backward[slot][bk]) ? want : 1;
 }
 
 size_t rodeo_cuda_history_bytes_per_system(const rodeo_problem *p) {
@@ -372,10 +373,12 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   const KernelSet *ks = bp ? find_kernel_set(p->ode, p->n, false) : p->ks;
   const bool shared = p->shared && !bp;
   const bool wide = !bp && wide_path(p) && p->ks->wide_backward[bk] != nullptr;
-  const int ck = bp ? 1 : effective_ck(p), slot = ck_slot(ck);
+  const int ck = bp ? 1 : effective_ck(p, bk), slot = ck_slot(ck);
   const bool wide_pp = bp && ks->wide_pp_forward != nullptr;   // dense wide-state kernels, per-system priors
+  // history bytes per system of THIS entry point (rodeo_cuda_history_bytes_per_system is the largest over them)
   const size_t per_system = bp ? (size_t)p->N * (wide_pp ? ks->wide_hist_elems : ks->hist_elems) * sizeof(double)
-                               : rodeo_cuda_history_bytes_per_system(p);
+                               : (shared || wide) ? rodeo_cuda_history_bytes_per_system(p)
+                                                  : (size_t)n_records(p->N, ck) * ks->hist_elems * sizeof(double);
   long cap = (long)(p->ws_limit / per_system) / 1024 * 1024;
   if (cap < 1024) cap = 1024;
   cap = std::min(cap, round_up(batch, 256));   // whole 256-system blocks: the permuted history order pads to them

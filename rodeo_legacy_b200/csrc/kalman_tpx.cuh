@@ -1,0 +1,302 @@
+// kalman_tpx.cuh -- draw-only backward kernel (solve_sim) of the block-diagonal family with >= 3 blocks:
+// one THREAD PER DIAGONAL BLOCK, U systems per lane, checkpointed history.  Written for BASELINE config 3
+// (Lorenz63, 16,384 x0, n_eval 5000, solve_sim), the config furthest from its bytes in round 1:
+//   * 16,384 systems x 3 blocks are 49,152 independent 5,000-step chains = 10.4 warps per SM: the step is bound by
+//     the LATENCY of one block step (two 3 x 3 Cholesky factorisations in sequence), not by throughput.  Each
+//     lane therefore runs the blocks of U = 2 different systems interleaved (independent instruction streams:
+//     the compiler overlaps their dependency chains), which halves the latency per system.
+//   * the warp-per-block kernel (kalman_bdw.cuh) needs the full history because re-running the filter means a
+//     CTA barrier per step; here the blocks of a system sit in one warp and exchange the m predicted values the
+//     right-hand side needs with shuffles, so checkpoint interval 2 works: half the history traffic
+//     (Lorenz63: 17.7 -> 8.9 GB written and read).
+//   * draws leave through a per-system FIFO in shared memory as whole 256-byte-aligned granules, one
+//     cp.async.bulk per granule issued by the lane of block 0 (72-byte runs: a granule every 3.6 steps per
+//     system, so the per-lane issue loop that was too slow for 288-byte variance runs is cheap here).
+// Lane = blk * SPW + s, SPW = 32 / n_blocks systems per warp and slot; warp w owns systems
+// [w * SPW * U, (w + 1) * SPW * U), system of (slot u, lane s) = w * SPW * U + u * SPW + s.  History in the plain
+// (unpermuted) tile order.  Warps never synchronise with each other.
+#pragma once
+#include <cstdint>
+
+#include "kalman_tpb.cuh"
+
+namespace rodeo {
+
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem),
+               "r"(bytes)
+               : "memory");
+}
+
+// FIFO of one output stream (W doubles per system and step) of ONE system: the image of the not-yet-stored
+// bytes of its trajectory, addressed by global byte offset modulo the FIFO size.
+template <int W>
+struct OutFifo {
+  static constexpr int RUN = W * 8;                                     // bytes per step
+  static constexpr int SLACK = kGranule - cgcd(RUN, kGranule);          // most bytes left pending after an emission
+  static constexpr int CB = (SLACK + RUN + 15) / 16 * 16;               // FIFO bytes
+  static constexpr bool kEven = (W % 2 == 0);                           // every run boundary is 16-byte aligned
+  uint32_t base;   // shared-memory address of this system's FIFO (16-byte aligned)
+  int off;         // (global byte offset of the current run) mod CB
+  int pend;        // bytes at and above the current run that are in the FIFO but not yet stored
+  __device__ __forceinline__ void init(uint32_t smem_base, long g_top) {
+    base = smem_base;
+    off = (int)((g_top * RUN) % CB);   // g_top = global run index one past the trajectory's last run
+    pend = 0;
+  }
+  __device__ __forceinline__ void advance() {   // to the next (lower) run: once per time index, before put
+    off -= RUN;
+    if (off < 0) off += CB;
+    pend += RUN;
+  }
+  template <int CNT>
+  __device__ __forceinline__ void put_at(int e0, const double *v) const {   // doubles e0 .. e0+CNT-1 of the run
+    int o = off + 8 * e0;
+    if (o >= CB) o -= CB;
+    const int room = CB - o;
+#pragma unroll
+    for (int i = 0; i < CNT; i++) {
+      const int d = 8 * i >= room ? 8 * i - CB : 8 * i;
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + (uint32_t)(o + d)), "d"(v[i]) : "memory");
+    }
+  }
+  // bytes [gs, gs + len) of the array (inside one granule) from FIFO offset so
+  __device__ __forceinline__ void copy_out(char *out, long gs, int so, int len) const {
+    if constexpr (!kEven) {   // run boundaries are only 8-byte aligned: ragged edges by plain stores
+      if (gs & 8) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)so));
+        *reinterpret_cast<double *>(out + gs) = v;
+        gs += 8;
+        so += 8;
+        if (so >= CB) so -= CB;
+        len -= 8;
+      }
+      if (len & 8) {
+        int st = so + len - 8;
+        if (st >= CB) st -= CB;
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)st));
+        *reinterpret_cast<double *>(out + gs + len - 8) = v;
+        len -= 8;
+      }
+      if (len <= 0) return;
+    }
+    const int l1 = len < CB - so ? len : CB - so;
+    bulk_s2g(out + gs, base + (uint32_t)so, (uint32_t)l1);
+    if (l1 < len) bulk_s2g(out + gs + l1, base, (uint32_t)(len - l1));
+  }
+  // After the current run (global run index g, time index t) is in the FIFO: store every granule it
+  // completed (everything at t = 0).  Called by ONE lane of the system; the caller commits the group.
+  __device__ __forceinline__ void emit(char *out, long g, int t) {
+    const long a = g * RUN;
+    const int d = (t == 0) ? 0 : (int)((kGranule - (a & (kGranule - 1))) & (kGranule - 1));   // up to the next boundary
+    if (pend > d) {
+      long gs = a + d;
+      int so = off + d;
+      if (so >= CB) so -= CB;
+      int len = pend - d;
+      while (len > 0) {
+        const int room = kGranule - (int)(gs & (kGranule - 1));
+        const int l = len < room ? len : room;
+        copy_out(out, gs, so, l);
+        gs += l;
+        so += l;
+        if (so >= CB) so -= CB;
+        len -= l;
+      }
+      pend = d;
+    }
+  }
+};
+
+template <class Fam, int CK, int U>
+struct TpxLayout {
+  static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
+  static constexpr int SPW = 32 / nb, LANES = SPW * nb;
+  using Fifo = OutFifo<n>;
+  // per-system stride: an odd number of 16-byte chunks (FIFO rows of different systems start in different banks)
+  static constexpr int SYS_BYTES = (Fifo::CB / 16) % 2 == 1 ? Fifo::CB : Fifo::CB + 16;
+  static constexpr int WARPS = 2, THREADS = WARPS * 32;
+  static constexpr size_t smem_bytes = (size_t)WARPS * U * SPW * SYS_BYTES;
+  static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
+};
+
+template <class Fam, int CK, int U, bool UNIFORM>
+__global__ void __launch_bounds__(TpxLayout<Fam, CK, U>::THREADS)
+kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+  using L = TpxLayout<Fam, CK, U>;
+  using Ode = typename Fam::Ode;
+  constexpr int p = L::p, nb = L::nb, n = L::n, PS = L::PS, NE = Fam::NE, SPW = L::SPW;
+  constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
+  constexpr unsigned kFull = 0xffffffffu;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long wg = (long)blockIdx.x * L::WARPS + warp;
+  const long b_first = wg * SPW * U;
+  if (b_first >= a.B) return;                              // warp-uniform; warps are independent
+  const bool lane_on = lane < L::LANES;
+  const int blk = lane_on ? lane / SPW : 0, s = lane_on ? lane % SPW : 0;
+  const int N = P.n_eval, R = n_records(N, CK);
+  const long T1 = (long)N + 1;
+  const BlockPrior<Fam, UNIFORM> bp(P, blk);
+
+  long b[U], bs[U], g[U];
+  bool valid[U];
+  typename L::Fifo fx[U];
+  const double *hb[U], *zb[U];
+  double th[U][NT], x0b[U][p];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    b[u] = b_first + u * SPW + s;
+    valid[u] = lane_on && b[u] < a.B;
+    bs[u] = b[u] < a.B ? b[u] : b_first;                   // a safe system for the loads of idle lanes
+    g[u] = (bs[u] + 1) * T1;
+    fx[u].init(smem_u32(smem_raw) + (uint32_t)(((warp * U + u) * SPW + s) * L::SYS_BYTES), g[u]);
+    hb[u] = a.hist + hist_offset(bs[u], 0, R, NE);
+    zb[u] = a.z + bs[u] * a.z_stride + blk * p;
+#pragma unroll
+    for (int e = 0; e < p; e++) x0b[u][e] = ld_once(a.x0 + bs[u] * n + blk * p + e);
+#pragma unroll
+    for (int e = 0; e < NT; e++) th[u][e] = (Ode::n_theta > 0 && CK > 1) ? ld_once(a.theta + bs[u] * Ode::n_theta + e) : 0.0;
+  }
+  auto load_rec = [&](int u, int r, double *mu, double *S) {
+    const double *h = hb[u] + (size_t)r * NE * kTile;
+#pragma unroll
+    for (int e = 0; e < p; e++) mu[e] = ld_stream(h + (blk * p + e) * kTile);
+#pragma unroll
+    for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
+  };
+  // store the draws of time index t (both slots), then the granules they completed
+  auto emit = [&](int t, double (*x)[p]) {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this lane's earlier stores have left the FIFOs
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      g[u] -= 1;
+      fx[u].advance();
+      fx[u].template put_at<p>(blk * p, x[u]);
+    }
+    fence_proxy_async();   // the rows (generic proxy) become visible to the bulk copies (async proxy) ...
+    __syncwarp();          // ... of every lane of a system, before the lane of block 0 issues the stores
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (valid[u] && blk == 0) fx[u].emit(reinterpret_cast<char *>(a.x_out), g[u], t);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  };
+  auto z_at = [&](int u, int t, double *zt) {   // z[:, t-1], this block's rows
+#pragma unroll
+    for (int e = 0; e < p; e++) zt[e] = __ldg(zb[u] + (long)(t - 1) * n + e);
+  };
+
+  double x[U][p], cm[U][p], cS[U][PS], nm[U][p], nS[U][PS], mus_unused[p], Ss_unused[PS];
+  int fail[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) fail[u] = 0;
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    load_rec(u, 0, cm[u], cS[u]);
+    if (R > 1) load_rec(u, 1, nm[u], nS[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {   // terminal time index N = record 0
+    double zt[p];
+    z_at(u, N, zt);
+    const int f = reg::smooth_terminal<p, 1, false, false, true>(cm[u], cS[u], zt, mus_unused, Ss_unused, x[u]);
+    if (f && !fail[u]) fail[u] = f;
+  }
+  emit(N, x);
+  int r = 1;
+  for (int t_hi = N; t_hi > 1;) {   // this group draws time indices t_hi-1 .. max(t_hi-CK, 1)
+    const int base = t_hi - CK;
+    if (base >= 1) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int e = 0; e < p; e++) cm[u][e] = nm[u][e];
+#pragma unroll
+        for (int e = 0; e < PS; e++) cS[u][e] = nS[u][e];
+        if (r + 1 < R) load_rec(u, r + 1, nm[u], nS[u]);            // one group ahead
+      }
+    }
+    if (CK == 2) {
+      const int t0 = base >= 1 ? base : 0;
+      if (base < 1) {   // the known initial state (KalmanODE.pyx:293-297)
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+          for (int e = 0; e < p; e++) cm[u][e] = x0b[u][e];
+#pragma unroll
+          for (int e = 0; e < PS; e++) cS[u][e] = 0.0;
+        }
+      }
+      if (t_hi - 1 > t0) {
+        // re-run the filter t0 -> t0 + 1 (BdFam::step, this block's share; the right-hand side needs every
+        // block's predicted first component: one shuffle per block), then draw time index t0 + 1
+        const int t = t0 + 1;
+        const double tt = P.tmin + (P.tmax - P.tmin) * (t0 + 1) / P.n_eval;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          double fm[p], fS[PS], zt[p];
+          z_at(u, t, zt);
+          reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), cm[u], fm);
+          reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), cS[u], fS, nullptr);
+          double X[n], y[Fam::m];
+#pragma unroll
+          for (int e = 0; e < n; e++) X[e] = 0.0;
+#pragma unroll
+          for (int k = 0; k < nb; k++) X[k * p] = __shfl_sync(kFull, fm[0], k * SPW + s);
+          Ode::template eval<n>(X, tt, th[u], y);
+          double ya = y[0];
+#pragma unroll
+          for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
+          reg::update_block<p, Fam::kWK>(bp.w(), fm, fS, ya, false);
+          const int f = reg::smooth_step<p, 1, false, false, true, false, Fam::kUT>(
+              bp.Q(), bp.c(), bp.R(), fm, fS, zt, mus_unused, Ss_unused, x[u]);
+          if (f && !fail[u]) fail[u] = f;
+        }
+        emit(t, x);
+      }
+    }
+    if (base >= 1) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        double zt[p];
+        z_at(u, base, zt);
+        const int f = reg::smooth_step<p, 1, false, false, true, false, Fam::kUT>(
+            bp.Q(), bp.c(), bp.R(), cm[u], cS[u], zt, mus_unused, Ss_unused, x[u]);
+        if (f && !fail[u]) fail[u] = f;
+      }
+      emit(base, x);
+    }
+    t_hi = base >= 1 ? base : 1;
+    r++;
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++)   // time index 0: the initial state is known (KalmanODE.pyx:409)
+#pragma unroll
+    for (int e = 0; e < p; e++) x[u][e] = x0b[u][e];
+  emit(0, x);
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int u = 0; u < U; u++)
+    if (valid[u] && a.status && fail[u]) atomicCAS(a.status + b[u], 0, blk * p + fail[u]);
+}
+
+template <class Fam, int CK, int U>
+cudaError_t launch_backward_tpx(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  using L = TpxLayout<Fam, CK, U>;
+  if (a.perm16) return cudaErrorInvalidValue;
+  const typename Fam::PriorT P = make_prior<Fam>(h);
+  const bool uni = blocks_uniform<Fam>(P);
+  auto kern = uni ? kalman_backward_tpx<Fam, CK, U, true> : kalman_backward_tpx<Fam, CK, U, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
+  if (e != cudaSuccess) return e;
+  const long per_warp = (long)L::SPW * U;
+  const long n_warps = (a.B + per_warp - 1) / per_warp;
+  const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
+  kern<<<grid, L::THREADS, L::smem_bytes, s>>>(P, a);
+  return cudaGetLastError();
+}
+
+}  // namespace rodeo

@@ -52,6 +52,7 @@ inline typename Fam::PriorT make_prior(const HostPrior &h) {
 #include "kalman_bdw.cuh"
 #include "kalman_sc.cuh"
 #include "kalman_tpb.cuh"
+#include "kalman_tpx.cuh"
 namespace rodeo {
 
 template <class Fam, bool UNROLL, int IG>
@@ -133,10 +134,16 @@ void fill_backward(KernelSet &k) {
     // block-diagonal with >= 3 blocks: one warp per diagonal block, CTA per tile (measured:
     // 2.1x on MSEIR, 1.9x on Lorenz63 over thread-per-system; 8 % slower at 2 blocks).
     // Full history only (checkpoint interval 1): see kalman_bdw.cuh.
+    // Draw-only smoothing (solve_sim): one thread per block, two systems per lane, checkpoint interval 1 or 2
+    // (kalman_tpx.cuh).  Intervals > 1 exist for that entry point only; the API picks the interval per entry point.
     if constexpr (CK == 1) {
       k.backward[CKI][BK_MV] = launch_backward_bdw<Fam, true, true, false>;
-      k.backward[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
+      k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 1, 2>;
+      k.backward_alt[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
       k.backward[CKI][BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
+    } else if constexpr (CK == 2) {
+      k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 2, 2>;
+      return;   // the other entry points of this family keep the full history
     } else {
       return;   // leaves this slot empty: the API falls back to interval 1 for this family
     }

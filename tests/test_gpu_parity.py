@@ -850,3 +850,37 @@ def test_structured_flag_on_car_prior():
     g = load_golden("lorenz_car_n600")
     k = _kode_from_golden(g, "lorenz_car_n600", z_state=np.asfortranarray(g["z"]))
     assert k.kernel_family[0] == "blockdiag" and not k.structured
+
+
+@pytest.mark.parametrize("maker,B,N", [
+    (lambda B: wl.lorenz_batch(B, N=301, tmax=1.2), 107, 301), (lambda B: wl.lorenz_batch(B, N=300, tmax=1.2), 20, 300),
+    (lambda B: wl.lorenz_batch(B, N=2, tmax=0.01), 41, 2), (lambda B: wl.lorenz_batch(B, N=1, tmax=0.01), 9, 1),
+    (lambda B: wl.mseir_batch(B, N=150), 64, 150), (lambda B: wl.mseir_batch(B, N=77), 13, 77)])
+def test_draw_only_smoother_for_three_or_more_blocks(maker, B, N):
+    """solve_sim on priors with >= 3 blocks runs on the thread-per-block, two-systems-per-lane kernel
+    (kalman_tpx.cuh) with checkpoint interval 2 by default: against the oracle, bit-identical to the full
+    history (checkpoint=1), to the draws of solve() (warp-per-block kernel) and to the host path; shared and
+    per-system z; batches that fill no warp."""
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    rng = np.random.default_rng(10)
+    z = np.asfortranarray(rng.standard_normal((n, N)))
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    k2, k1 = wl.make_kode(w, z_state=z), wl.make_kode(w, z_state=z, checkpoint=1)
+    x2 = k2.solve_sim(x0d, theta=thd)
+    x1 = k1.solve_sim(x0d, theta=thd)
+    assert torch.equal(x1, x2) and int(k2.status.abs().sum()) == 0
+    xb, _, _ = k2.solve(x0d, theta=thd)
+    assert torch.equal(xb, x2)
+    np.testing.assert_array_equal(k2.solve_sim(x0, theta=theta), x2.cpu().numpy())
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_SIM)
+    assert traj_err(x2.cpu().numpy(), ref["x"]).max() < (1e-8 if n == 9 else 1e-7)
+    assert torch.equal(x2[:, 0], x0d)
+    # general (unstructured) kernels give the same bits
+    assert torch.equal(wl.make_kode(w, z_state=z, use_structure=False).solve_sim(x0d, theta=thd), x2)
+    # per-system draws
+    zb = rng.standard_normal((B, n, N))
+    kz = wl.make_kode(w, z_state=zb)
+    xz = kz.solve_sim(x0d, theta=thd)
+    refz = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, zb, oracle.MODE_SIM)
+    assert traj_err(xz.cpu().numpy(), refz["x"]).max() < (1e-8 if n == 9 else 1e-7)
