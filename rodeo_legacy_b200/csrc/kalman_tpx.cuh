@@ -30,11 +30,12 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint
 
 // FIFO of one output stream (W doubles per system and step) of ONE system: the image of the not-yet-stored
 // bytes of its trajectory, addressed by global byte offset modulo the FIFO size.
-template <int W>
+// EK = steps between emissions: the FIFO holds what an emission can leave pending plus EK runs.
+template <int W, int EK = 1>
 struct OutFifo {
   static constexpr int RUN = W * 8;                                     // bytes per step
   static constexpr int SLACK = kGranule - cgcd(RUN, kGranule);          // most bytes left pending after an emission
-  static constexpr int CB = (SLACK + RUN + 15) / 16 * 16;               // FIFO bytes
+  static constexpr int CB = (SLACK + EK * RUN + 15) / 16 * 16;          // FIFO bytes
   static constexpr bool kEven = (W % 2 == 0);                           // every run boundary is 16-byte aligned
   uint32_t base;   // shared-memory address of this system's FIFO (16-byte aligned)
   int off;         // (global byte offset of the current run) mod CB
@@ -114,16 +115,23 @@ template <class Fam, int CK, int U>
 struct TpxLayout {
   static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
   static constexpr int SPW = 32 / nb, LANES = SPW * nb;
-  using Fifo = OutFifo<n>;
+  // Draws are 8 n bytes per step (Lorenz63: 72): a granule completes every 256 / (8 n) steps per system.  The
+  // emission round (proxy fence, warp barriers, per-lane bulk-copy issue loop) runs every EK steps instead of
+  // every step: ncu showed it was ~40 % of the kernel's instructions at EK = 1.
+  static constexpr int EK = 4;
+  using Fifo = OutFifo<n, EK>;
   // per-system stride: an odd number of 16-byte chunks (FIFO rows of different systems start in different banks)
   static constexpr int SYS_BYTES = (Fifo::CB / 16) % 2 == 1 ? Fifo::CB : Fifo::CB + 16;
   static constexpr int WARPS = 2, THREADS = WARPS * 32;
+  // U = 1: 12 resident warps per SM (<= 170 registers) hold a whole 16,384-system Lorenz63 batch (11.1 warps per
+  // SM) in ONE wave; at the 190 registers ptxas would take, 10 fit and the launch needs two
+  static constexpr int MINB = U == 1 ? 6 : 1;
   static constexpr size_t smem_bytes = (size_t)WARPS * U * SPW * SYS_BYTES;
   static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
 };
 
 template <class Fam, int CK, int U, bool UNIFORM>
-__global__ void __launch_bounds__(TpxLayout<Fam, CK, U>::THREADS)
+__global__ void __launch_bounds__(TpxLayout<Fam, CK, U>::THREADS, TpxLayout<Fam, CK, U>::MINB)
 kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
   using L = TpxLayout<Fam, CK, U>;
   using Ode = typename Fam::Ode;
@@ -167,22 +175,31 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
   };
-  // store the draws of time index t (both slots), then the granules they completed
+  // park the draws of time index t in the FIFOs; every EK steps (and at t = 0) store the granules they completed
+  int since = 0;
+  bool reads_pending = false;
   auto emit = [&](int t, double (*x)[p]) {
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // this lane's earlier stores have left the FIFOs
-    __syncwarp();
+    if (reads_pending) {   // the bulk copies of the last emission round have left the FIFOs
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      reads_pending = false;
+    }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       g[u] -= 1;
       fx[u].advance();
       fx[u].template put_at<p>(blk * p, x[u]);
     }
-    fence_proxy_async();   // the rows (generic proxy) become visible to the bulk copies (async proxy) ...
-    __syncwarp();          // ... of every lane of a system, before the lane of block 0 issues the stores
+    if (++since == L::EK || t == 0) {
+      since = 0;
+      fence_proxy_async();   // the rows (generic proxy) become visible to the bulk copies (async proxy) ...
+      __syncwarp();          // ... of every lane of a system, before the lane of block 0 issues the stores
 #pragma unroll
-    for (int u = 0; u < U; u++)
-      if (valid[u] && blk == 0) fx[u].emit(reinterpret_cast<char *>(a.x_out), g[u], t);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      for (int u = 0; u < U; u++)
+        if (valid[u] && blk == 0) fx[u].emit(reinterpret_cast<char *>(a.x_out), g[u], t);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      reads_pending = true;
+    }
   };
   auto z_at = [&](int u, int t, double *zt) {   // z[:, t-1], this block's rows
 #pragma unroll

@@ -127,6 +127,9 @@ cudaError_t launch_backward_pp(const HostPrior &h, const BatchedPrior &bp, const
 // backward launchers of one family for checkpoint interval CK (slot CKI of the table)
 template <class Fam, class Ode, bool BD, bool UNROLL, int CK, int CKI>
 void fill_backward(KernelSet &k) {
+#ifndef RODEO_TPX_U
+#define RODEO_TPX_U 1      // systems per lane of the draw-only thread-per-block smoother (kalman_tpx.cuh)
+#endif
 #ifndef RODEO_BDW_MIN_BLOCKS
 #define RODEO_BDW_MIN_BLOCKS 3
 #endif
@@ -138,11 +141,11 @@ void fill_backward(KernelSet &k) {
     // (kalman_tpx.cuh).  Intervals > 1 exist for that entry point only; the API picks the interval per entry point.
     if constexpr (CK == 1) {
       k.backward[CKI][BK_MV] = launch_backward_bdw<Fam, true, true, false>;
-      k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 1, 2>;
+      k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 1, RODEO_TPX_U>;
       k.backward_alt[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
       k.backward[CKI][BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
     } else if constexpr (CK == 2) {
-      k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 2, 2>;
+      k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 2, RODEO_TPX_U>;
       return;   // the other entry points of this family keep the full history
     } else {
       return;   // leaves this slot empty: the API falls back to interval 1 for this family
