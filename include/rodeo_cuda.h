@@ -187,14 +187,32 @@ int rodeo_cuda_solve(rodeo_problem *p, int mode, int64_t batch, const double *x0
 /* Per-system priors (e.g. a sweep over the prior scale sigma).  As rodeo_cuda_solve,
  * but every system may bring its own wgt_meas (m x n), mu_state (n), wgt_state (n x n),
  * var_state (n x n): device arrays, batch-major, each system column-major like the constructor's
- * arrays.  A NULL array means "the handle's shared value for every system".  Runs on the dense
- * kernel family with the full history (each thread keeps its prior in registers / local memory
- * instead of the constant bank); probde interrogation only. */
+ * arrays.  A NULL array means "the handle's shared value for every system".  When the handle's prior and every
+ * system's arrays are block diagonal (two equal blocks: the FitzHugh-Nagumo family) the thread-per-block kernels
+ * run with a per-lane prior (checkpoint 2, granule stores); otherwise the dense kernel family with the full
+ * history (each thread keeps its prior in registers / local memory instead of the constant bank).  probde
+ * interrogation only.  Synchronises `cuda_stream` once (structure check). */
 int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, const double *x0,
                                    const double *theta, const double *z, int64_t z_batch_stride,
                                    const double *wgt_meas_b, const double *mu_state_b,
                                    const double *wgt_state_b, const double *var_state_b, double *x_out,
                                    double *mu_out, double *var_out, int32_t *status, void *cuda_stream);
+
+/* 1 when the most recent rodeo_cuda_solve_batched_prior call ran on the block-diagonal thread-per-block kernels:
+ * the handle's prior and EVERY system's own arrays are block diagonal with n_meas equal blocks and row a of W
+ * inside block a (checked on the device per call; e.g. a sweep over the IBM scale sigma).  0: dense family. */
+int rodeo_cuda_last_batched_prior_blockdiag(const rodeo_problem *p);
+
+/* rodeo_cuda_loglik with per-system priors (a sigma-tuning likelihood sweep without materialising trajectories):
+ * the batched arrays as in rodeo_cuda_solve_batched_prior, the observation arguments as in rodeo_cuda_loglik.
+ * Dense kernel family, probde interrogation. */
+int rodeo_cuda_loglik_batched_prior(rodeo_problem *p, int use_draw, int64_t batch, const double *x0,
+                                    const double *theta, const double *z, int64_t z_batch_stride,
+                                    const double *wgt_meas_b, const double *mu_state_b,
+                                    const double *wgt_state_b, const double *var_state_b,
+                                    const int32_t *thin_index, int32_t n_obs_times, const int32_t *state_index,
+                                    int32_t n_obs_comp, const double *Y, double gamma, double *loglik_out,
+                                    int32_t *status, void *cuda_stream);
 
 /* Host-pointer entry point (the call a NumPy user of the reference makes): copies the
  * inputs to the device, solves in chunks with copy/compute overlap, copies the results

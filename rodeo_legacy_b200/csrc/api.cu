@@ -38,6 +38,8 @@ struct rodeo_problem {
   std::vector<double> W, Q, c, R;  // column-major host copies
   const KernelSet *ks;
   int flags = 0;
+  int *bd_flag_dev = nullptr;      // device flag of the batched-prior structure check
+  bool last_pp_bd = false;         // the last batched-prior solve ran on the block-diagonal kernels
   int ck = 0;                      // requested checkpoint interval of the filter history (0 = auto)
   // shared-covariance mode (kalman_sc.inl): tables cached per (prior, N), rebuilt after problem_set
   bool shared = false;
@@ -176,6 +178,7 @@ int rodeo_cuda_problem_destroy(rodeo_problem *p) {
   if (p->ws) cudaFree(p->ws);
   if (p->tab) cudaFree(p->tab);
   if (p->tab_fail_dev) cudaFree(p->tab_fail_dev);
+  if (p->bd_flag_dev) cudaFree(p->bd_flag_dev);
   for (int i = 0; i < 8; i++)
     if (p->hbuf[i]) cudaFree(p->hbuf[i]);
   for (auto e : p->ev) cudaEventDestroy(e);
@@ -362,21 +365,43 @@ static bool prefer_staged_backward() {
   return v;
 }
 
+// Per-system priors: is EVERY system's prior block diagonal with m blocks of size n / m and row a of W inside block a?
+// One thread per system; flag = 1 on the first violation.
+__global__ void check_batched_blockdiag(BatchedPrior bp, long B, int n, int m, int *flag) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int bs = n / m;
+  bool bad = false;
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++)
+      if (i / bs != j / bs) {
+        if (bp.Q && bp.Q[b * n * n + i + (long)j * n] != 0.0) bad = true;
+        if (bp.R && bp.R[b * n * n + i + (long)j * n] != 0.0) bad = true;
+      }
+  if (bp.W)
+    for (int j = 0; j < n; j++)
+      for (int a = 0; a < m; a++)
+        if (j / bs != a && bp.W[b * m * n + a + (long)j * m] != 0.0) bad = true;
+  if (bad) *flag = 1;
+}
+
 // One pass over `batch` systems in chunks: forward kernel then backward kernel per chunk.
 static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const double *x0,
                       const double *theta, const double *z, long z_stride, double *x_out,
                       double *mu_out, double *var_out, int *status, const LoglikSpec *ll,
-                      cudaStream_t stream, const BatchedPrior *bp = nullptr) {
+                      cudaStream_t stream, const BatchedPrior *bp = nullptr, bool bp_bd = false) {
   const int n = p->n, nth = ode_n_theta(p->ode);
   const long T1 = (long)p->N + 1;
-  // per-system priors run on the dense family with the full history, never in shared-covariance mode
-  const KernelSet *ks = bp ? find_kernel_set(p->ode, p->n, false) : p->ks;
+  // per-system priors: block-diagonal thread-per-block kernels (checkpoint 2, permuted history) when every
+  // system's prior has the structure (bp_bd), else the dense family with the full history; never shared-covariance
+  const KernelSet *ks = (bp && !bp_bd) ? find_kernel_set(p->ode, p->n, false) : p->ks;
   const bool shared = p->shared && !bp;
   const bool wide = !bp && wide_path(p) && p->ks->wide_backward[bk] != nullptr;
-  const int ck = bp ? 1 : effective_ck(p, bk), slot = ck_slot(ck);
-  const bool wide_pp = bp && ks->wide_pp_forward != nullptr;   // dense wide-state kernels, per-system priors
+  const int ck = bp ? (bp_bd ? 2 : 1) : effective_ck(p, bk), slot = ck_slot(ck);
+  const bool wide_pp = bp && !bp_bd && ks->wide_pp_forward != nullptr;   // dense wide-state kernels, per-system priors
   // history bytes per system of THIS entry point (rodeo_cuda_history_bytes_per_system is the largest over them)
-  const size_t per_system = bp ? (size_t)p->N * (wide_pp ? ks->wide_hist_elems : ks->hist_elems) * sizeof(double)
+  const size_t per_system = bp_bd ? (size_t)n_records(p->N, ck) * ks->hist_elems * sizeof(double)
+                            : bp ? (size_t)p->N * (wide_pp ? ks->wide_hist_elems : ks->hist_elems) * sizeof(double)
                                : (shared || wide) ? rodeo_cuda_history_bytes_per_system(p)
                                                   : (size_t)n_records(p->N, ck) * ks->hist_elems * sizeof(double);
   long cap = (long)(p->ws_limit / per_system) / 1024 * 1024;
@@ -393,7 +418,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   }
   // which smoother runs: the current kernel, or the previous generation on request (A/B measurements)
   launch_fn backward = nullptr;
-  bool perm = false;
+  bool perm = bp_bd;
   if (!bp && !shared && !wide) {
     const bool alt = prefer_staged_backward() && ks->backward_alt[slot][bk];
     backward = alt ? ks->backward_alt[slot][bk] : ks->backward[slot][bk];
@@ -448,9 +473,11 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     if (bp) {
       BatchedPrior c{bp->W ? bp->W + off * p->m * n : nullptr, bp->Q ? bp->Q + off * n * n : nullptr,
                      bp->c ? bp->c + off * n : nullptr, bp->R ? bp->R + off * n * n : nullptr};
-      CK(wide_pp ? ks->wide_pp_forward(hp, c, a, stream) : ks->pp_forward(hp, c, a, stream));
+      CK(bp_bd ? ks->pp_bd_forward(hp, c, a, stream)
+               : wide_pp ? ks->wide_pp_forward(hp, c, a, stream) : ks->pp_forward(hp, c, a, stream));
       if (p->timing) CK(cudaEventRecord(p->ev[3 * (ev0 + ci) + 1], stream));
-      CK(wide_pp ? ks->wide_pp_backward[bk](hp, c, a, stream) : ks->pp_backward[bk](hp, c, a, stream));
+      CK(bp_bd ? ks->pp_bd_backward[bk](hp, c, a, stream)
+               : wide_pp ? ks->wide_pp_backward[bk](hp, c, a, stream) : ks->pp_backward[bk](hp, c, a, stream));
     } else {
       CK(shared ? ks->sc_forward(hp, a, stream)
                 : wide ? ks->wide_forward[p->ig](hp, a, stream)
@@ -489,6 +516,24 @@ static int check_device_alignment(const double *x_out, const double *mu_out, con
   return RODEO_OK;
 }
 
+// Can the per-system priors of this call run on the block-diagonal thread-per-block kernels?  The handle's own
+// prior must have selected a block-diagonal set that carries them, and every system's arrays must have the
+// structure (checked on the device; one 4-byte read back -- this entry point synchronises the stream once).
+static int batched_prior_is_blockdiag(rodeo_problem *p, const BatchedPrior &bp, long batch, cudaStream_t stream,
+                                      bool *out) {
+  *out = false;
+  if (!p->ks->blockdiag || !p->ks->pp_bd_forward || (p->flags & RODEO_FLAG_FORCE_DENSE)) return RODEO_OK;
+  if (!p->bd_flag_dev) CK(cudaMalloc((void **)&p->bd_flag_dev, sizeof(int)));
+  CK(cudaMemsetAsync(p->bd_flag_dev, 0, sizeof(int), stream));
+  check_batched_blockdiag<<<(unsigned)((batch + 127) / 128), 128, 0, stream>>>(bp, batch, p->n, p->m, p->bd_flag_dev);
+  CK(cudaGetLastError());
+  int flag = 1;
+  CK(cudaMemcpyAsync(&flag, p->bd_flag_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  *out = flag == 0;
+  return RODEO_OK;
+}
+
 extern "C" {
 
 int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch) {
@@ -520,14 +565,60 @@ int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, co
   if (!rc && batch > 0) rc = check_device_alignment(x_out, mu_out, var_out);
   if (rc) return rc;
   if (batch == 0) return RODEO_OK;
-  const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
-  if (!dense || !dense->pp_forward || p->ig != RODEO_INTERROGATE_PROBDE)
-    return fail(RODEO_E_UNSUPPORTED, "per-system priors need a dense kernel set and the probde interrogation");
+  if (p->ig != RODEO_INTERROGATE_PROBDE)
+    return fail(RODEO_E_UNSUPPORTED, "per-system priors need the probde interrogation");
   CK(cudaSetDevice(p->device));
   BatchedPrior bp{wgt_meas_b, wgt_state_b, mu_state_b, var_state_b};
   BackwardKind bk = mode == RODEO_MODE_MV ? BK_MV : mode == RODEO_MODE_SIM ? BK_SIM : BK_BOTH;
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  bool bd = false;
+  rc = batched_prior_is_blockdiag(p, bp, (long)batch, stream, &bd);
+  if (rc) return rc;
+  p->last_pp_bd = bd;
+  if (!bd) {
+    const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
+    if (!dense || !dense->pp_forward)
+      return fail(RODEO_E_UNSUPPORTED, "per-system priors that are not block diagonal need a dense kernel set");
+  }
   return run_chunks(p, bk, (long)batch, x0, theta, z, (long)z_batch_stride, x_out, mu_out, var_out, status,
-                    nullptr, (cudaStream_t)cuda_stream, &bp);
+                    nullptr, stream, &bp, bd);
+}
+
+int rodeo_cuda_last_batched_prior_blockdiag(const rodeo_problem *p) { return p ? (p->last_pp_bd ? 1 : 0) : RODEO_E_INVALID; }
+
+int rodeo_cuda_loglik_batched_prior(rodeo_problem *p, int use_draw, int64_t batch, const double *x0,
+                                    const double *theta, const double *z, int64_t z_batch_stride,
+                                    const double *wgt_meas_b, const double *mu_state_b,
+                                    const double *wgt_state_b, const double *var_state_b,
+                                    const int32_t *thin_index, int32_t n_obs_times, const int32_t *state_index,
+                                    int32_t n_obs_comp, const double *Y, double gamma, double *loglik_out,
+                                    int32_t *status, void *cuda_stream) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (batch < 0 || n_obs_times < 0 || n_obs_comp < 0) return fail(RODEO_E_INVALID, "negative size");
+  if (batch == 0) return RODEO_OK;
+  if (!x0 || !loglik_out) return fail(RODEO_E_INVALID, "x0 / loglik_out is null");
+  if (ode_n_theta(p->ode) > 0 && !theta) return fail(RODEO_E_INVALID, "theta is null but the RHS has parameters");
+  if (use_draw && !z) return fail(RODEO_E_INVALID, "z is null but draws are requested");
+  if (n_obs_times * n_obs_comp > 0 && (!thin_index || !state_index || !Y)) return fail(RODEO_E_INVALID, "thin_index / state_index / Y is null");
+  if (!(gamma > 0.0)) return fail(RODEO_E_INVALID, "gamma must be positive");
+  if (p->ig != RODEO_INTERROGATE_PROBDE)
+    return fail(RODEO_E_UNSUPPORTED, "per-system priors need the probde interrogation");
+  const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
+  const BackwardKind bk = use_draw ? BK_LL_DRAW : BK_LL_MEAN;
+  if (!dense || !dense->pp_forward || !(dense->wide_pp_forward ? dense->wide_pp_backward[bk] : dense->pp_backward[bk]))
+    return fail(RODEO_E_UNSUPPORTED, "log-likelihood with per-system priors needs a dense kernel set");
+  CK(cudaSetDevice(p->device));
+  BatchedPrior bp{wgt_meas_b, wgt_state_b, mu_state_b, var_state_b};
+  LoglikSpec ll;
+  ll.thin_index = thin_index;
+  ll.state_index = state_index;
+  ll.Y = Y;
+  ll.gamma = gamma;
+  ll.n_obs_times = n_obs_times;
+  ll.n_obs_comp = n_obs_comp;
+  ll.out = loglik_out;
+  return run_chunks(p, bk, (long)batch, x0, theta, z, (long)z_batch_stride, nullptr, nullptr, nullptr, status, &ll,
+                    (cudaStream_t)cuda_stream, &bp, false);
 }
 
 int rodeo_cuda_loglik(rodeo_problem *p, int use_draw, int64_t batch, const double *x0, const double *theta,

@@ -32,6 +32,7 @@
 // Warps never synchronise with each other.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 #include "kalman_staged.cuh"
 
@@ -205,12 +206,42 @@ struct BlockPrior<Fam, false> {
       c_[i] = P.c[blk * p + i];
     }
   }
+  // per-system priors (rodeo_cuda_solve_batched_prior): overlay system b's own block of every array that is
+  // given (device arrays, batch-major, each system column-major like the constructor's; nullptr = shared value)
+  __device__ __forceinline__ void overlay(const BatchedPrior &bq, long b, int blk) {
+    constexpr int n = Fam::n, m = Fam::m;
+    if (bq.Q) {
+      const double *q = bq.Q + b * n * n;
+#pragma unroll
+      for (int i = 0; i < p; i++)
+#pragma unroll
+        for (int j = 0; j < p; j++) q_[i * p + j] = q[(blk * p + i) + (blk * p + j) * n];
+    }
+    if (bq.R) {
+      const double *r = bq.R + b * n * n;
+#pragma unroll
+      for (int i = 0; i < p; i++)
+#pragma unroll
+        for (int j = i; j < p; j++) r_[sidx<p>(i, j)] = r[(blk * p + i) + (blk * p + j) * n];
+    }
+    if (bq.W) {
+      const double *w = bq.W + b * m * n;
+#pragma unroll
+      for (int i = 0; i < p; i++) w_[i] = w[blk + (blk * p + i) * m];
+    }
+    if (bq.c) {
+#pragma unroll
+      for (int i = 0; i < p; i++) c_[i] = bq.c[b * n + blk * p + i];
+    }
+  }
   __device__ __forceinline__ const double *Q() const { return q_; }
   __device__ __forceinline__ const double *R() const { return r_; }
   __device__ __forceinline__ const double *w() const { return w_; }
   __device__ __forceinline__ const double *c() const { return c_; }
 };
 
+// PM, the prior mode of the thread-per-block kernels: 0 = every block has the same Q, R, w, c (immediate
+// constant-bank operands), 1 = per-lane register copies of the lane's block, 2 = per-SYSTEM priors overlaid on them
 __device__ __forceinline__ double ld_once(const double *p) {
   double v;   // volatile: loaded where it is written and kept (never re-loaded inside the time loop)
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -222,13 +253,13 @@ __device__ __forceinline__ double ld_stream(const double *p) {
   return v;
 }
 
-template <class Fam, int CK, bool UNIFORM, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, int PM, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
 __global__ void __launch_bounds__(TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::THREADS)
 #ifdef RODEO_TPB_MAXNREG
 __maxnreg__(RODEO_TPB_MAXNREG)
 #endif
 kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
-                    const __grid_constant__ GranuleMaps maps) {
+                    const __grid_constant__ GranuleMaps maps, const __grid_constant__ BatchedPrior bpr) {
   using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
   using Ode = typename Fam::Ode;
   constexpr int p = L::p, nb = L::nb, n = L::n, PS = L::PS, NE = Fam::NE;
@@ -247,7 +278,8 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
   const long upos = 256 * q + 16 * j + i;                  // its position in the (permuted) history
   const int N = P.n_eval, R = n_records(N, CK);
   const long T1 = (long)N + 1;
-  const BlockPrior<Fam, UNIFORM> bp(P, blk);
+  BlockPrior<Fam, PM == 0> bp(P, blk);
+  if constexpr (PM == 2) bp.overlay(bpr, bs, blk);
 
   // ---- output streams -------------------------------------------------------------------------------
   const uint32_t tile = ((smem_u32(smem_raw) + 1023u) & ~1023u) + (uint32_t)warp * L::WARP_BYTES;
@@ -408,9 +440,10 @@ inline bool blocks_uniform(const typename Fam::PriorT &P) {
 // each, and the filtered records go to the permuted history position 256 q + 16 j + i: a half-warp stores
 // 128 contiguous bytes per element row.  Half the dependent FP64 chain per step and twice the warps of the
 // thread-per-system kernel (which stays for the unpermuted order).
-template <class Fam, int IG, bool UNIFORM>
+template <class Fam, int IG, int PM>
 __global__ void __launch_bounds__(128)
-kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
+kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a,
+                   const __grid_constant__ BatchedPrior bpr) {
   using Ode = typename Fam::Ode;
   constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS, NE = Fam::NE;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
@@ -426,7 +459,8 @@ kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
   const bool valid = b < a.B;
   const long bs = valid ? b : 256 * q + j;
   const long upos = 256 * q + 16 * j + i;
-  const BlockPrior<Fam, UNIFORM> bp(P, blk);
+  BlockPrior<Fam, PM == 0> bp(P, blk);
+  if constexpr (PM == 2) bp.overlay(bpr, bs, blk);
   const int N = P.n_eval, ck = a.ck, R = n_records(N, ck);
   double mu[p], S[PS], th[NT];
 #pragma unroll
@@ -499,8 +533,46 @@ cudaError_t launch_forward_tpb(const HostPrior &h, const SolveArgs &a, cudaStrea
   const typename Fam::PriorT P = make_prior<Fam>(h);
   const long n_warps = (a.B + 255) / 256 * 16;
   const unsigned grid = (unsigned)((n_warps + 3) / 4);
-  if (blocks_uniform<Fam>(P)) kalman_forward_tpb<Fam, IG, true><<<grid, 128, 0, s>>>(P, a);
-  else kalman_forward_tpb<Fam, IG, false><<<grid, 128, 0, s>>>(P, a);
+  const BatchedPrior none{nullptr, nullptr, nullptr, nullptr};
+  if (blocks_uniform<Fam>(P)) kalman_forward_tpb<Fam, IG, 0><<<grid, 128, 0, s>>>(P, a, none);
+  else kalman_forward_tpb<Fam, IG, 1><<<grid, 128, 0, s>>>(P, a, none);
+  return cudaGetLastError();
+}
+
+// per-system priors (block-diagonal for every system: checked by the caller), probde interrogation
+template <class Fam>
+cudaError_t launch_forward_tpb_pp(const HostPrior &h, const BatchedPrior &bq, const SolveArgs &a, cudaStream_t s) {
+  if (!a.perm16) return cudaErrorInvalidValue;
+  const typename Fam::PriorT P = make_prior<Fam>(h);
+  const long n_warps = (a.B + 255) / 256 * 16;
+  kalman_forward_tpb<Fam, IG_PROBDE, 2><<<(unsigned)((n_warps + 3) / 4), 128, 0, s>>>(P, a, bq);
+  return cudaGetLastError();
+}
+
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+cudaError_t launch_backward_tpb_mode(const typename Fam::PriorT &P, int pm, const BatchedPrior *bq, const SolveArgs &a,
+                                     cudaStream_t s) {
+  using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
+  auto kern = pm == 0 ? kalman_backward_tpb<Fam, CK, 0, DO_MEAN, DO_VAR, DO_SIM>
+              : pm == 1 ? kalman_backward_tpb<Fam, CK, 1, DO_MEAN, DO_VAR, DO_SIM>
+                        : kalman_backward_tpb<Fam, CK, 2, DO_MEAN, DO_VAR, DO_SIM>;
+  // measurement knob: extra dynamic shared memory per CTA lowers the resident CTAs per SM without a rebuild
+  static const size_t pad = [] {
+    const char *v = getenv("RODEO_TPB_SMEM_PAD");
+    return v ? (size_t)atol(v) : (size_t)0;
+  }();
+  const size_t smem = L::smem_bytes + pad;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  GranuleMaps maps;
+  constexpr int n = Fam::n;
+  if ((e = encode_granule_map(&maps.mu, DO_MEAN ? a.mu_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
+  if ((e = encode_granule_map(&maps.x, DO_SIM ? a.x_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
+  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
+  const long n_warps = (a.B + 255) / 256 * 16;
+  const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
+  const BatchedPrior none{nullptr, nullptr, nullptr, nullptr};
+  kern<<<grid, L::THREADS, smem, s>>>(P, a, maps, bq ? *bq : none);
   return cudaGetLastError();
 }
 
@@ -511,20 +583,14 @@ cudaError_t launch_backward_tpb(const HostPrior &h, const SolveArgs &a, cudaStre
   if (!a.perm16) return cudaErrorInvalidValue;
   if ((double)16 * a.n_steps * Fam::n * Fam::n * 8 >= 2147483648.0) return cudaErrorInvalidValue;   // 32-bit row coordinates
   const typename Fam::PriorT P = make_prior<Fam>(h);
-  const bool uni = blocks_uniform<Fam>(P);
-  auto kern = uni ? kalman_backward_tpb<Fam, CK, true, DO_MEAN, DO_VAR, DO_SIM>
-                  : kalman_backward_tpb<Fam, CK, false, DO_MEAN, DO_VAR, DO_SIM>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
-  if (e != cudaSuccess) return e;
-  GranuleMaps maps;
-  constexpr int n = Fam::n;
-  if ((e = encode_granule_map(&maps.mu, DO_MEAN ? a.mu_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
-  if ((e = encode_granule_map(&maps.x, DO_SIM ? a.x_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
-  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
-  const long n_warps = (a.B + 255) / 256 * 16;
-  const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
-  kern<<<grid, L::THREADS, L::smem_bytes, s>>>(P, a, maps);
-  return cudaGetLastError();
+  return launch_backward_tpb_mode<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>(P, blocks_uniform<Fam>(P) ? 0 : 1, nullptr, a, s);
+}
+
+template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+cudaError_t launch_backward_tpb_pp(const HostPrior &h, const BatchedPrior &bq, const SolveArgs &a, cudaStream_t s) {
+  if (!a.perm16) return cudaErrorInvalidValue;
+  if ((double)16 * a.n_steps * Fam::n * Fam::n * 8 >= 2147483648.0) return cudaErrorInvalidValue;
+  return launch_backward_tpb_mode<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>(make_prior<Fam>(h), 2, &bq, a, s);
 }
 
 }  // namespace rodeo

@@ -225,6 +225,15 @@ KernelSet make_kernel_set(const char *name) {
   for (int b = 0; b < BK_COUNT; b++) k.sc_backward[b] = nullptr;
   k.pp_forward = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.pp_backward[b] = nullptr;
+  k.pp_bd_forward = nullptr;
+  for (int b = 0; b < BK_COUNT; b++) k.pp_bd_backward[b] = nullptr;
+  if constexpr (UNROLL && BD && Ode::n_meas == 2) {   // per-system priors that are block diagonal per system
+    using FamG = typename Fam::General;
+    k.pp_bd_forward = launch_forward_tpb_pp<FamG>;
+    k.pp_bd_backward[BK_MV] = launch_backward_tpb_pp<FamG, 2, true, true, false>;
+    k.pp_bd_backward[BK_SIM] = launch_backward_tpb_pp<FamG, 2, false, false, true>;
+    k.pp_bd_backward[BK_BOTH] = launch_backward_tpb_pp<FamG, 2, true, true, true>;
+  }
   k.wide_forward[0] = k.wide_forward[1] = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.wide_backward[b] = nullptr;
   k.wide_pp_forward = nullptr;

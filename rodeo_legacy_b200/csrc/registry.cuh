@@ -48,6 +48,10 @@ struct KernelSet {
   // per-system priors (dense family, probde interrogation); nullptr when not compiled
   launch_pp_fn pp_forward;
   launch_pp_fn pp_backward[BK_COUNT];
+  // ... for two-block block-diagonal sets when every system's prior is block diagonal too: the thread-per-block
+  // kernels with a per-lane prior (checkpoint 2, permuted history order); nullptr when not compiled
+  launch_pp_fn pp_bd_forward;
+  launch_pp_fn pp_bd_backward[BK_COUNT];
   // dense wide-state kernels (kalman_dw.cuh: half a warp per system); nullptr / 0 when not compiled.
   // Used for every entry point under the probde and schobert interrogations; they keep
   // their own history layout (wide_hist_elems doubles per system per step, full history).

@@ -238,6 +238,12 @@ class KalmanODE:
         return ("blockdiag" if bd.value else "dense", ("rolled", "registers", "wide")[rg.value])
 
     @property
+    def last_batched_prior_blockdiag(self):
+        """True when the last ``solve*(..., priors=...)`` call ran on the block-diagonal thread-per-block kernels
+        (every system's own prior block diagonal), False when it used the dense family."""
+        return bool(self._lib.rodeo_cuda_last_batched_prior_blockdiag(self._h))
+
+    @property
     def structured(self):
         """True when the block-diagonal kernels specialised for ibm_init / zero_pad priors are in use (every Q
         block upper triangular, every W row a unit vector): they skip the exactly-zero terms, same bits.
@@ -465,7 +471,7 @@ class KalmanODE:
         self._run(MODE_MV, x0, None, theta, out=(None, mu_out, var_out))
 
     # ---- fused thinning + Gaussian log-likelihood (examples/inference.py:54-56, 66-94) ------
-    def loglik(self, x0, theta, Y, thin_index, state_ind, gamma, use_draw=False):
+    def loglik(self, x0, theta, Y, thin_index, state_ind, gamma, use_draw=False, priors=None):
         """One log-likelihood per system, no per-step output materialised.
 
         sum_d sum_k log N(Y[d, k]; X[thin_index[d], state_ind[k]], sd=gamma) with X the
@@ -499,10 +505,18 @@ class KalmanODE:
         status = torch.zeros(B, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            _lib.check(self._lib.rodeo_cuda_loglik(
-                self._h, int(bool(use_draw)), B, _ptr(x0b), _ptr(th), _ptr(z), z_stride,
-                _ptr(d_thin), len(thin), _ptr(d_si), len(si), _ptr(d_Y), float(gamma),
-                _ptr(out), _ptr(status), stream))
+            if priors is None:
+                _lib.check(self._lib.rodeo_cuda_loglik(
+                    self._h, int(bool(use_draw)), B, _ptr(x0b), _ptr(th), _ptr(z), z_stride,
+                    _ptr(d_thin), len(thin), _ptr(d_si), len(si), _ptr(d_Y), float(gamma),
+                    _ptr(out), _ptr(status), stream))
+            else:       # one prior per system (e.g. a likelihood sweep over the IBM scale sigma)
+                bp = self._batched_prior(priors, B, dev)
+                _lib.check(self._lib.rodeo_cuda_loglik_batched_prior(
+                    self._h, int(bool(use_draw)), B, _ptr(x0b), _ptr(th), _ptr(z), z_stride,
+                    _ptr(bp["wgt_meas"]), _ptr(bp["mu_state"]), _ptr(bp["wgt_state"]), _ptr(bp["var_state"]),
+                    _ptr(d_thin), len(thin), _ptr(d_si), len(si), _ptr(d_Y), float(gamma),
+                    _ptr(out), _ptr(status), stream))
         self.status = status if on_dev else status.cpu().numpy()
         res = out if on_dev else out.cpu().numpy()
         return res[0] if single else res

@@ -44,6 +44,9 @@ SYMBOLS = [
     ("rodeo_cuda_reserve", _I, [_V, _L]),
     ("rodeo_cuda_solve", _I, [_V, _I, _L, _V, _V, _V, _L, _V, _V, _V, _V, _V]),
     ("rodeo_cuda_solve_batched_prior", _I, [_V, _I, _L, _V, _V, _V, _L, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
+    ("rodeo_cuda_last_batched_prior_blockdiag", _I, [_V]),
+    ("rodeo_cuda_loglik_batched_prior", _I, [_V, _I, _L, _V, _V, _V, _L, _V, _V, _V, _V, _V, ctypes.c_int32, _V,
+                                             ctypes.c_int32, _V, _D, _V, _V, _V]),
     ("rodeo_cuda_solve_host", _I, [_V, _I, _L, _V, _V, _V, _L, _V, _V, _V, _V]),
     ("rodeo_cuda_loglik", _I, [_V, _I, _L, _V, _V, _V, _L, _V, ctypes.c_int32, _V, ctypes.c_int32,
                                _V, _D, _V, _V, _V]),

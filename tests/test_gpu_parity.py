@@ -884,3 +884,61 @@ def test_draw_only_smoother_for_three_or_more_blocks(maker, B, N):
     xz = kz.solve_sim(x0d, theta=thd)
     refz = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, zb, oracle.MODE_SIM)
     assert traj_err(xz.cpu().numpy(), refz["x"]).max() < (1e-8 if n == 9 else 1e-7)
+
+
+def test_per_system_blockdiag_priors_and_sigma_sweep_likelihood():
+    """SURVEY section 8(f) #4's motivating use: a sweep over the IBM scale sigma.  Every system has its own (block
+    diagonal) R and c: the thread-per-block kernels run with a per-lane prior (checkpoint 2, granule stores);
+    rodeo_cuda_loglik_batched_prior gives the likelihood of each sigma without materialising trajectories."""
+    from rodeo_legacy_b200 import ibm_init, indep_init
+    B = 333                                           # ragged: partial 16-system row, partial 256 block
+    w, x0, theta = wl.fitz_batch(B, seed=6)
+    n, N = 6, w["N"]
+    rng = np.random.default_rng(3)
+    sig = 0.02 + 0.3 * rng.random((B, 2))
+    R = np.empty((B, n, n)); c = np.zeros((B, n))
+    for b in range(B):
+        R[b] = indep_init(ibm_init(40.0 / N, [3, 3], list(sig[b])), [3, 3])["var_state"]
+        if b % 4 == 0:
+            c[b] = 1e-4 * rng.standard_normal(n)
+    z = np.asfortranarray(rng.standard_normal((n, N)))
+    k = wl.make_kode(w, z_state=z)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    pri = dict(var_state=R, mu_state=c)
+    x, mu, var = k.solve(x0d, theta=thd, priors=pri)
+    assert k.last_batched_prior_blockdiag and int(k.status.abs().sum()) == 0
+    pick = list(range(0, B, 7)) + [B - 1]
+    for b in pick:
+        po = oracle.Problem("fitz", w["W"], w["tmin"], w["tmax"], N, w["Q"], c[b], R[b])
+        ref = oracle.solve(po, x0[b], theta[b], z, oracle.MODE_BOTH)
+        assert traj_err(mu[b].cpu().numpy(), ref["mu"]).max() < 1e-10
+        assert var_err(var[b].cpu().numpy()[1:], ref["var"][1:]).max() < 1e-9
+        assert traj_err(x[b].cpu().numpy(), ref["x"]).max() < 1e-8
+    # the three entry points agree bit for bit; NumPy in -> NumPy out
+    mu2, var2 = k.solve_mv(x0d, theta=thd, priors=pri)
+    assert torch.equal(mu2, mu) and torch.equal(var2, var)
+    assert torch.equal(k.solve_sim(x0d, theta=thd, priors=pri), x)
+    mu_h, _ = k.solve_mv(x0, theta=theta, priors=pri)
+    np.testing.assert_array_equal(mu_h, mu.cpu().numpy())
+    # repeating the shared prior per system reproduces the shared-prior solve exactly (same kernels, same bits)
+    mu_s, var_s = k.solve_mv(x0d, theta=thd)
+    mu_r, var_r = k.solve_mv(x0d, theta=thd, priors=dict(var_state=np.tile(np.asarray(w["R"]), (B, 1, 1))))
+    assert k.last_batched_prior_blockdiag
+    assert torch.equal(mu_r, mu_s) and torch.equal(var_r, var_s)
+    # a prior that couples the blocks for ONE system sends the call to the dense family
+    R2 = R.copy()
+    R2[200, 0, 3] = R2[200, 3, 0] = 1e-12
+    mu_d, _ = k.solve_mv(x0d, theta=thd, priors=dict(var_state=R2, mu_state=c))
+    assert not k.last_batched_prior_blockdiag
+    assert float((mu_d[:200] - mu[:200]).abs().max()) < 1e-9 * float(mu.abs().max())
+    # likelihood of each sigma: rodeo_cuda_loglik_batched_prior against the oracle's solve + loglik
+    g = load_golden("fitz_n400")
+    ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
+    for draw, key in ((False, "mu"), (True, "x")):
+        ll = k.loglik(x0d, thd, Y, ind, [0, 3], gam, use_draw=draw, priors=pri).cpu().numpy()
+        for b in pick[::5]:
+            po = oracle.Problem("fitz", w["W"], w["tmin"], w["tmax"], N, w["Q"], c[b], R[b])
+            ref = oracle.solve(po, x0[b], theta[b], z, oracle.MODE_BOTH)
+            assert np.isclose(ll[b], oracle.loglik(ref[key], ind, [0, 3], Y, gam), rtol=1e-8)
+    ll_np = k.loglik(x0, theta, Y, ind, [0, 3], gam, priors=pri)
+    assert isinstance(ll_np, np.ndarray) and ll_np.shape == (B,)

@@ -56,6 +56,10 @@ def main():
             fn = lambda: k.solve_mv(x0d, theta=thd)
         elif mode == "sim":
             fn = lambda: k.solve_sim(x0d, theta=thd)
+        elif mode == "mv_pp":       # every system its own var_state (a sweep over the prior scale sigma)
+            scale = torch.linspace(0.5, 2.0, B, dtype=torch.float64, device="cuda")
+            Rb = torch.from_numpy(np.ascontiguousarray(w["R"])).cuda()[None] * scale[:, None, None] ** 2
+            fn = lambda: k.solve_mv(x0d, theta=thd, priors=dict(var_state=Rb))
         else:
             ind = np.arange(w["N"] // 40, w["N"] + 1, w["N"] // 40)
             Y = np.zeros((len(ind), 2))
@@ -77,6 +81,7 @@ def main():
         ("C3 lorenz63 solve_sim", wl.lorenz_batch, 16384, "sim", hist(9) + 8 * 9),
         ("C4 mseir solve_mv", wl.mseir_batch, 32768, "mv", hist(15) + 8 * (15 + 225)),
         ("C5 fitz loglik (per GPU of 8)", wl.fitz_batch, 131072, "ll", hist(6)),
+        ("C2pp fitz solve_mv, per-system var_state", wl.fitz_batch, 65536, "mv_pp", hist(6) + 8 * (6 + 36)),
     ]
     for c in cfgs:
         if sel is None or any(s in c[0] for s in sel):
