@@ -26,7 +26,8 @@ NVCC_FLAGS = [
   + ([f"-DRODEO_STAGED_WARPS={os.environ['RODEO_STAGED_WARPS']}"] if os.environ.get("RODEO_STAGED_WARPS") else []) \
   + ([f"-DRODEO_TPB_WARPS={os.environ['RODEO_TPB_WARPS']}"] if os.environ.get("RODEO_TPB_WARPS") else []) \
   + ([f"-DRODEO_TPB_MAXNREG={os.environ['RODEO_TPB_MAXNREG']}"] if os.environ.get("RODEO_TPB_MAXNREG") else []) \
-  + ([f"-DRODEO_TPX_U={os.environ['RODEO_TPX_U']}"] if os.environ.get("RODEO_TPX_U") else [])
+  + ([f"-DRODEO_TPX_U={os.environ['RODEO_TPX_U']}"] if os.environ.get("RODEO_TPX_U") else []) \
+  + ([f"-DRODEO_TPB_GVAR={os.environ['RODEO_TPB_GVAR']}"] if os.environ.get("RODEO_TPB_GVAR") else [])
 
 
 def nvcc():

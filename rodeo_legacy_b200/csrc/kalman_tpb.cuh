@@ -75,13 +75,16 @@ struct GranuleMaps {
 
 // One output stream (W doubles per system and step) of one warp.  All members are warp-uniform except
 // tile_i / i7s / out_i (the lane's system).
-template <int W>
+// G = granule bytes (a power of two >= 256 with 16 * RUN * T1 a multiple of G for every T1: 256 always works for
+// even W; 512 when 16 * RUN is a multiple of 512, e.g. the 288-byte variance runs of n_state 6).
+template <int W, int G = kGranule>
 struct GranuleStream {
   static constexpr int RUN = W * 8;                                  // bytes per system and step
-  static constexpr int SLACK = kGranule - cgcd(RUN, kGranule);       // most bytes left pending after an emission
-  static constexpr int NSLOT = (SLACK + RUN + kGranule - 1) / kGranule;
-  static constexpr int UNITS = 2 * NSLOT;                            // 128-byte units per system in the slots
-  static constexpr int BYTES = NSLOT * kSlotBytes;
+  static_assert(G >= 256 && (G & (G - 1)) == 0 && (16 * W * 8) % G == 0, "granule size");
+  static constexpr int SLACK = G - cgcd(RUN, G);       // most bytes left pending after an emission
+  static constexpr int NSLOT = (SLACK + RUN + G - 1) / G;
+  static constexpr int UNITS = NSLOT * (G / 128);                    // 128-byte units per system in the slots
+  static constexpr int BYTES = NSLOT * 16 * G;
   static_assert(W % 2 == 0, "granule stores need 16-byte run boundaries (even n_state)");
   // row coordinates are 32-bit: the launcher checks 16 * T1 * RUN < 2^31
   int x;           // offset of the current run inside the 16-system row (bytes): (j * T1 + t) * RUN
@@ -94,7 +97,7 @@ struct GranuleStream {
   __device__ __forceinline__ void init(uint32_t tile_, int i, double *out, long k_row, int j, long T1) {
     x_end = (int)((j + 1) * T1 * RUN);
     x = x_end;
-    Fx = (x_end + kGranule - 1) & ~(kGranule - 1);
+    Fx = (x_end + G - 1) & ~(G - 1);
     tile = tile_;
     tile_i = tile + (uint32_t)i * 128u;
     i7s = (uint32_t)(i & 7) << 4;
@@ -134,24 +137,24 @@ struct GranuleStream {
   //   tail_row: this lane's system sits in the last, incomplete row: it stores whole granules itself too
   __device__ __forceinline__ void emit(const CUtensorMap *map, int t, int row0, bool full_row, bool lane0, bool mine,
                                        bool tail_row) {
-    const int c = (t == 0) ? x : (x + kGranule - 1) & ~(kGranule - 1);
-    for (int g0 = (c + kGranule - 1) & ~(kGranule - 1); g0 < Fx; g0 += kGranule) {
-      if (g0 + kGranule > x_end) {                     // the top granule is shared with the next trajectory
+    const int c = (t == 0) ? x : (x + G - 1) & ~(G - 1);
+    for (int g0 = (c + G - 1) & ~(G - 1); g0 < Fx; g0 += G) {
+      if (g0 + G > x_end) {                     // the top granule is shared with the next trajectory
         if (mine) copy_lsu(g0, x_end);
       } else {
         if (full_row && lane0) {
-          const uint32_t src = tile + ((((uint32_t)g0 >> 8) % NSLOT) << 12);
-          tma_store_3d_s(map, src, 0, g0 >> 7, row0);
-          tma_store_3d_s(map, src + 2048u, 0, (g0 >> 7) + 1, row0);
+          const uint32_t src = tile + (((uint32_t)g0 / G) % NSLOT) * (16u * G);
+#pragma unroll
+          for (int h = 0; h < G / 128; h++) tma_store_3d_s(map, src + 2048u * h, 0, (g0 >> 7) + h, row0);
         }
-        if (mine && tail_row) copy_lsu(g0, g0 + kGranule);
+        if (mine && tail_row) copy_lsu(g0, g0 + G);
       }
     }
-    if (t == 0 && (c & (kGranule - 1))) {              // the bottom granule is shared with the previous trajectory
-      const int top = (c + kGranule - 1) & ~(kGranule - 1);
+    if (t == 0 && (c & (G - 1))) {              // the bottom granule is shared with the previous trajectory
+      const int top = (c + G - 1) & ~(G - 1);
       if (mine) copy_lsu(c, top < x_end ? top : x_end);
     }
-    Fx = (c + kGranule - 1) & ~(kGranule - 1);
+    Fx = (c + G - 1) & ~(G - 1);
   }
 };
 
@@ -160,8 +163,13 @@ struct TpbLayout {
   static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
   static_assert(nb == 2, "thread-per-block smoother: two diagonal blocks (16 systems x 2 blocks per warp)");
   static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
+#ifndef RODEO_TPB_GVAR
+#define RODEO_TPB_GVAR 256
+#endif
+  // variance granules of RODEO_TPB_GVAR bytes where the run length allows it (see GranuleStream), else 256
+  static constexpr int GVAR = (16 * n * n * 8) % RODEO_TPB_GVAR == 0 ? RODEO_TPB_GVAR : kGranule;
   using SVec = GranuleStream<n>;
-  using SVar = GranuleStream<n * n>;
+  using SVar = GranuleStream<n * n, GVAR>;
   static constexpr int OFF_MEAN = 0;
   static constexpr int OFF_X = OFF_MEAN + (DO_MEAN ? SVec::BYTES : 0);
   static constexpr int OFF_VAR = OFF_X + (DO_SIM ? SVec::BYTES : 0);
@@ -175,7 +183,11 @@ struct TpbLayout {
   static constexpr int WARPS = RODEO_TPB_WARPS;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int MINB = RODEO_TPB_MINB;
-  static constexpr size_t smem_bytes = (size_t)WARPS * WARP_BYTES + 1024;      // + alignment slack (1024-byte swizzle atoms)
+  static constexpr size_t smem_need = (size_t)WARPS * WARP_BYTES + 1024;       // + alignment slack (1024-byte swizzle atoms)
+  // The kernel is HBM-bound and runs best with FEWER resident warps (measured, FN solve_mv, 65,536 systems:
+  // 12 warps per SM 2.05 ms, 10: 2.00, 8: 1.99, 6: 1.98, 4: 2.40): with 4,096 equal-length warps the last,
+  // partially filled wave is a smaller share of the launch.  Requesting 55 KB per CTA caps it at 4 CTAs = 8 warps.
+  static constexpr size_t smem_bytes = smem_need > 55 * 1024 ? smem_need : 55 * 1024;
 };
 
 // The prior of the lane's block: immediate constant-bank operands when every block has the same Q, R, w, c
