@@ -527,6 +527,38 @@ def main():
                            "h2d_bytes_per_step": B * (N_STATE + 3) * 8, "d2h_bytes_per_step": B * 12,
                            "host_buffers": "pageable NumPy arrays", "checksum": float(np.sum(lln))}}
             del kz, xs
+            # opt-in compact variance layouts (rodeo_cuda_set_var_layout): the same solve_mv, fewer output bytes
+            for lay, vw in (("blocks", 2 * 9), ("diag", 6)):
+                kl = wl.make_kode(w, var_layout=lay)
+                pin = lambda *s_: torch.empty(s_, dtype=torch.float64, pin_memory=True)
+                x0p, thp = pin(B, N_STATE), pin(B, 3)
+                x0p.copy_(torch.from_numpy(x0))
+                thp.copy_(torch.from_numpy(theta))
+                mup = pin(B, N_EVAL + 1, N_STATE)
+                varp = pin(B, N_EVAL + 1, 2, 3, 3) if lay == "blocks" else pin(B, N_EVAL + 1, N_STATE)
+                kl.solve_mv_into(x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy())
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    kl.solve_mv_into(x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy())
+                el_l = (time.perf_counter() - t0) / args.e2e_steps
+                for _ in range(3):
+                    kl.solve_mv(x0d, theta=thd)
+                torch.cuda.synchronize()
+                l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0.record()
+                for _ in range(10):
+                    kl.solve_mv(x0d, theta=thd)
+                l1.record()
+                torch.cuda.synchronize()
+                e2e_other["solve_mv_var_" + lay] = {
+                    "value": B / el_l, "unit": UNIT, "ms_per_step": 1e3 * el_l,
+                    "h2d_bytes_per_step": B * (N_STATE + 3) * 8,
+                    "d2h_bytes_per_step": B * (N_EVAL + 1) * (N_STATE + vw) * 8 + B * 4,
+                    "host_buffers": "pinned", "device_resident_value": B * 10 / (l0.elapsed_time(l1) * 1e-3),
+                    "note": "opt-in output layout, never the headline: var = " +
+                            ("the two (3, 3) diagonal blocks" if lay == "blocks" else "the marginal variances") +
+                            " of the reference's (6, 6) matrix, same numbers"}
+                del kl, mup, varp
 
     # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None

@@ -169,6 +169,19 @@ int rodeo_cuda_get_checkpoint(const rodeo_problem *p);
  * families without it (rolled dense n > 6) and for the chkrebtii interrogation. */
 int rodeo_cuda_set_shared_cov(rodeo_problem *p, int enabled);
 int rodeo_cuda_get_shared_cov(const rodeo_problem *p);
+/* Layout of `var_out` (opt-in; the default RODEO_VAR_FULL is the reference's (n_state, n_state) matrix per
+ * system and time index).  For block-diagonal priors 2/3 (FitzHugh-Nagumo) to 4/5 (MSEIR) of that matrix are
+ * structural zeros and it is 82 % of the bytes a solve_mv writes and returns:
+ *   RODEO_VAR_BLOCKS  var_out (B, n_eval+1, n_meas, p, p): the diagonal blocks only, block a = Sigma[a*p:(a+1)*p, a*p:(a+1)*p]
+ *   RODEO_VAR_DIAG    var_out (B, n_eval+1, n_state): the marginal variances only
+ * Same numbers as the corresponding entries of the full output, bit for bit.  Available for block-diagonal priors
+ * with two blocks (the thread-per-block kernels) in general mode; RODEO_E_UNSUPPORTED otherwise.  It applies to
+ * rodeo_cuda_solve / rodeo_cuda_solve_host (not to the batched-prior entry point, nor to shared-covariance mode). */
+enum { RODEO_VAR_FULL = 0, RODEO_VAR_BLOCKS = 1, RODEO_VAR_DIAG = 2 };
+int rodeo_cuda_set_var_layout(rodeo_problem *p, int layout);
+int rodeo_cuda_get_var_layout(const rodeo_problem *p);
+/* doubles of var_out per (system, time index) in the current layout: n*n, n_meas*p*p or n */
+int rodeo_cuda_var_doubles_per_step(const rodeo_problem *p);
 /* Pre-allocate the workspace for batches up to max_batch (otherwise grown on demand). */
 int rodeo_cuda_reserve(rodeo_problem *p, int64_t max_batch);
 

@@ -41,6 +41,7 @@ struct rodeo_problem {
   int *bd_flag_dev = nullptr;      // device flag of the batched-prior structure check
   bool last_pp_bd = false;         // the last batched-prior solve ran on the block-diagonal kernels
   int ck = 0;                      // requested checkpoint interval of the filter history (0 = auto)
+  int var_layout = 0;              // RODEO_VAR_FULL / _BLOCKS / _DIAG
   // shared-covariance mode (kalman_sc.inl): tables cached per (prior, N), rebuilt after problem_set
   bool shared = false;
   double *tab = nullptr;
@@ -205,7 +206,14 @@ int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *v) {
   p->tab_valid = false;          // the covariance tables depend on Q, R, W
   int rc = select_kernel_set(p); // the structure (hence the kernel family) may have changed
   if (rc == RODEO_OK && p->shared && !p->ks->sc_forward) p->shared = false;
+  if (rc == RODEO_OK && p->var_layout && !p->ks->backward_vl[p->var_layout - 1][0]) p->var_layout = RODEO_VAR_FULL;
   return rc;
+}
+
+// doubles per (system, time index) of var_out in the current layout
+static int var_width(const rodeo_problem *p) {
+  const int n = p->n, m = p->m;
+  return p->var_layout == RODEO_VAR_BLOCKS ? m * (n / m) * (n / m) : p->var_layout == RODEO_VAR_DIAG ? n : n * n;
 }
 
 // dense wide-state kernels (kalman_dw.cuh) serve the plain solves of the sets that carry them
@@ -255,6 +263,20 @@ int rodeo_cuda_set_shared_cov(rodeo_problem *p, int enabled) {
 
 int rodeo_cuda_get_shared_cov(const rodeo_problem *p) { return p ? (p->shared ? 1 : 0) : RODEO_E_INVALID; }
 int rodeo_cuda_problem_structured(const rodeo_problem *p) { return p ? (p->ks->structured ? 1 : 0) : RODEO_E_INVALID; }
+
+int rodeo_cuda_set_var_layout(rodeo_problem *p, int layout) {
+  if (!p) return fail(RODEO_E_INVALID, "null problem");
+  if (layout != RODEO_VAR_FULL && layout != RODEO_VAR_BLOCKS && layout != RODEO_VAR_DIAG)
+    return fail(RODEO_E_INVALID, "unknown variance layout");
+  if (layout != RODEO_VAR_FULL && (!p->ks->backward_vl[layout - 1][0] || p->ig != RODEO_INTERROGATE_PROBDE))
+    return fail(RODEO_E_UNSUPPORTED,
+                "compact variance layouts need a block-diagonal prior with two blocks (the thread-per-block "
+                "kernels) and the probde interrogation");
+  p->var_layout = layout;
+  return RODEO_OK;
+}
+int rodeo_cuda_get_var_layout(const rodeo_problem *p) { return p ? p->var_layout : RODEO_E_INVALID; }
+int rodeo_cuda_var_doubles_per_step(const rodeo_problem *p) { return p ? var_width(p) : RODEO_E_INVALID; }
 
 int rodeo_cuda_set_checkpoint(rodeo_problem *p, int interval) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
@@ -397,7 +419,12 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   const KernelSet *ks = (bp && !bp_bd) ? find_kernel_set(p->ode, p->n, false) : p->ks;
   const bool shared = p->shared && !bp;
   const bool wide = !bp && wide_path(p) && p->ks->wide_backward[bk] != nullptr;
-  const int ck = bp ? (bp_bd ? 2 : 1) : effective_ck(p, bk), slot = ck_slot(ck);
+  // a compact variance layout runs on its own kernels (checkpoint 2) for solve_mv / solve
+  const bool vl = p->var_layout != RODEO_VAR_FULL && !bp && (bk == BK_MV || bk == BK_BOTH);
+  if (vl && (p->shared || !p->ks->backward_vl[p->var_layout - 1][0]))
+    return fail(RODEO_E_UNSUPPORTED, "the variance layout is not available in this mode (shared covariance / kernel family)");
+  const int ck = vl ? 2 : bp ? (bp_bd ? 2 : 1) : effective_ck(p, bk), slot = ck_slot(ck);
+  const int vw = (bp || p->shared) ? n * n : var_width(p);
   const bool wide_pp = bp && !bp_bd && ks->wide_pp_forward != nullptr;   // dense wide-state kernels, per-system priors
   // history bytes per system of THIS entry point (rodeo_cuda_history_bytes_per_system is the largest over them)
   const size_t per_system = bp_bd ? (size_t)n_records(p->N, ck) * ks->hist_elems * sizeof(double)
@@ -419,7 +446,10 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   // which smoother runs: the current kernel, or the previous generation on request (A/B measurements)
   launch_fn backward = nullptr;
   bool perm = bp_bd;
-  if (!bp && !shared && !wide) {
+  if (vl) {
+    backward = ks->backward_vl[p->var_layout - 1][bk == BK_BOTH ? 1 : 0];
+    perm = true;
+  } else if (!bp && !shared && !wide) {
     const bool alt = prefer_staged_backward() && ks->backward_alt[slot][bk];
     backward = alt ? ks->backward_alt[slot][bk] : ks->backward[slot][bk];
     perm = !alt && ks->backward_perm[slot][bk];
@@ -453,7 +483,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
     a.n_steps = p->N + 1;
     a.x_out = x_out ? x_out + off * T1 * n : nullptr;
     a.mu_out = mu_out ? mu_out + off * T1 * n : nullptr;
-    a.var_out = (var_out && !shared) ? var_out + off * T1 * n * n : nullptr;
+    a.var_out = (var_out && !shared) ? var_out + off * T1 * vw : nullptr;
     a.tab = shared ? p->tab : nullptr;
     a.tab_fail = shared ? p->tab_fail : 0;
     a.status = status ? status + off : nullptr;
@@ -668,7 +698,8 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
   }
   const bool mv = mode & RODEO_MODE_MV, sim = mode & RODEO_MODE_SIM;
   const bool pervar = mv && !p->shared;   // per-system variance output (general mode)
-  const size_t out_per = (size_t)T1 * n * sizeof(double) * ((mv ? 1 : 0) + (pervar ? n : 0) + (sim ? 1 : 0));
+  const int vw = var_width(p);                // doubles of variance per (system, time index) in the current layout
+  const size_t out_per = (size_t)T1 * sizeof(double) * ((mv ? n : 0) + (pervar ? vw : 0) + (sim ? n : 0));
   // sub-arrays of a staging buffer start on 128-byte boundaries (the kernels store 16-byte vectors / TMA
   // boxes relative to each array base): B * T1 * n doubles is odd when B, T1 and n are all odd
   auto al = [](size_t doubles) { return (doubles + 15) & ~(size_t)15; };
@@ -696,7 +727,7 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
     const long off = ci * hc, B = std::min(hc, (long)batch - off);
     const int slot = (int)(ci & 1);
     double *ob = (double *)p->hbuf[4 + slot];
-    const size_t vec = al((size_t)B * T1 * n), mat = al((size_t)B * T1 * n * n);
+    const size_t vec = al((size_t)B * T1 * n), mat = al((size_t)B * T1 * vw);
     double *d_mu = mv ? ob : nullptr;
     double *d_var = pervar ? ob + vec : nullptr;
     double *d_x = sim ? ob + (mv ? vec + (pervar ? mat : 0) : 0) : nullptr;
@@ -717,7 +748,7 @@ int rodeo_cuda_solve_host(rodeo_problem *p, int mode, int64_t batch, const doubl
     if (mv) {
       CK(cudaMemcpyAsync(mu_out + off * T1 * n, d_mu, (size_t)B * T1 * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
       if (pervar)
-        CK(cudaMemcpyAsync(var_out + off * T1 * n * n, d_var, (size_t)B * T1 * n * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
+        CK(cudaMemcpyAsync(var_out + off * T1 * vw, d_var, (size_t)B * T1 * vw * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
       else if (ci == 0)
         CK(cudaMemcpyAsync(var_out, d_var, (size_t)T1 * n * n * sizeof(double), cudaMemcpyDeviceToHost, p->s_copy));
     }

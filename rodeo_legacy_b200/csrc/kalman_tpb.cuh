@@ -158,7 +158,9 @@ struct GranuleStream {
   }
 };
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+// DO_VAR: 0 no variance output, 1 the reference's full (n, n) matrices, 2 the n_meas diagonal (p, p) blocks only
+// (RODEO_VAR_BLOCKS), 3 the marginal variances only (RODEO_VAR_DIAG) -- rodeo_cuda_set_var_layout
+template <class Fam, int CK, bool DO_MEAN, int DO_VAR, bool DO_SIM>
 struct TpbLayout {
   static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
   static_assert(nb == 2, "thread-per-block smoother: two diagonal blocks (16 systems x 2 blocks per warp)");
@@ -168,8 +170,9 @@ struct TpbLayout {
 #endif
   // variance granules of RODEO_TPB_GVAR bytes where the run length allows it (see GranuleStream), else 256
   static constexpr int GVAR = (16 * n * n * 8) % RODEO_TPB_GVAR == 0 ? RODEO_TPB_GVAR : kGranule;
+  static constexpr int WV = DO_VAR == 2 ? nb * p * p : DO_VAR == 3 ? n : n * n;   // variance doubles per system and step
   using SVec = GranuleStream<n>;
-  using SVar = GranuleStream<n * n, GVAR>;
+  using SVar = GranuleStream<WV, DO_VAR == 1 ? GVAR : kGranule>;
   static constexpr int OFF_MEAN = 0;
   static constexpr int OFF_X = OFF_MEAN + (DO_MEAN ? SVec::BYTES : 0);
   static constexpr int OFF_VAR = OFF_X + (DO_SIM ? SVec::BYTES : 0);
@@ -265,7 +268,7 @@ __device__ __forceinline__ double ld_stream(const double *p) {
   return v;
 }
 
-template <class Fam, int CK, int PM, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, int PM, bool DO_MEAN, int DO_VAR, bool DO_SIM>
 __global__ void __launch_bounds__(TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::THREADS)
 #ifdef RODEO_TPB_MAXNREG
 __maxnreg__(RODEO_TPB_MAXNREG)
@@ -319,13 +322,28 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
     }
     if (DO_VAR) {
       sv.advance();
-      // rows blk*p .. blk*p+p-1 of the n x n matrix (the reference's var[t][j][i]; symmetric), zeros outside the block
+      if constexpr (DO_VAR == 1) {
+        // rows blk*p .. blk*p+p-1 of the n x n matrix (the reference's var[t][j][i]; symmetric), zeros outside the block
 #pragma unroll
-      for (int jj = 0; jj < p; jj++) {
-        double row[n];
+        for (int jj = 0; jj < p; jj++) {
+          double row[n];
 #pragma unroll
-        for (int c = 0; c < n; c++) row[c] = (blk == c / p) ? Ss[sidx<p>(c % p, jj)] : 0.0;
-        sv.template put_pairs<n>((blk * p + jj) * n * 8, row);
+          for (int c = 0; c < n; c++) row[c] = (blk == c / p) ? Ss[sidx<p>(c % p, jj)] : 0.0;
+          sv.template put_pairs<n>((blk * p + jj) * n * 8, row);
+        }
+      } else if constexpr (DO_VAR == 2) {   // this block's p x p matrix, var[t][blk][jj][ii]
+        double bv[p * p];
+#pragma unroll
+        for (int jj = 0; jj < p; jj++)
+#pragma unroll
+          for (int ii = 0; ii < p; ii++) bv[jj * p + ii] = Ss[sidx<p>(ii, jj)];
+        if constexpr ((p * p) % 2 == 0) sv.template put_pairs<p * p>(blk * p * p * 8, bv);
+        else sv.template put_singles<p * p>(blk * p * p * 8, bv);
+      } else {                              // marginal variances of this block's components
+        double dv[p];
+#pragma unroll
+        for (int ii = 0; ii < p; ii++) dv[ii] = Ss[sidx<p>(ii, ii)];
+        sv.template put_singles<p>(blk * p * 8, dv);
       }
     }
     fence_proxy_async();   // the rows (generic proxy) become visible to the tensor stores (async proxy) ...
@@ -362,7 +380,7 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
   load_rec(0, cm, cS);
   if (R > 1) load_rec(1, nm, nS);
   {  // terminal time index N = record 0
-    fail = reg::smooth_terminal<p, 1, DO_MEAN, DO_VAR, DO_SIM>(cm, cS, DO_SIM ? zb + (long)(N - 1) * n : nullptr, mus, Ss, x);
+    fail = reg::smooth_terminal<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM>(cm, cS, DO_SIM ? zb + (long)(N - 1) * n : nullptr, mus, Ss, x);
     emit(N, mus, Ss, x);
   }
   int r = 1;
@@ -401,14 +419,14 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
         for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
         reg::update_block<p, Fam::kWK>(bp.w(), fm, fS, ya, false);
         const int t = t0 + 1;
-        const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false, Fam::kUT>(
+        const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
             bp.Q(), bp.c(), bp.R(), fm, fS, DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
         if (f && !fail) fail = f;
         emit(t, mus, Ss, x);
       }
     }
     if (base >= 1) {
-      const int f = reg::smooth_step<p, 1, DO_MEAN, DO_VAR, DO_SIM, false, Fam::kUT>(
+      const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
           bp.Q(), bp.c(), bp.R(), cm, cS, DO_SIM ? zb + (long)(base - 1) * n : nullptr, mus, Ss, x);
       if (f && !fail) fail = f;
       emit(base, mus, Ss, x);
@@ -561,7 +579,7 @@ cudaError_t launch_forward_tpb_pp(const HostPrior &h, const BatchedPrior &bq, co
   return cudaGetLastError();
 }
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, bool DO_MEAN, int DO_VAR, bool DO_SIM>
 cudaError_t launch_backward_tpb_mode(const typename Fam::PriorT &P, int pm, const BatchedPrior *bq, const SolveArgs &a,
                                      cudaStream_t s) {
   using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
@@ -580,7 +598,7 @@ cudaError_t launch_backward_tpb_mode(const typename Fam::PriorT &P, int pm, cons
   constexpr int n = Fam::n;
   if ((e = encode_granule_map(&maps.mu, DO_MEAN ? a.mu_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
   if ((e = encode_granule_map(&maps.x, DO_SIM ? a.x_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
-  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, n * n, a.n_steps, a.B)) != cudaSuccess) return e;
+  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, L::WV, a.n_steps, a.B)) != cudaSuccess) return e;
   const long n_warps = (a.B + 255) / 256 * 16;
   const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
   const BatchedPrior none{nullptr, nullptr, nullptr, nullptr};
@@ -589,7 +607,7 @@ cudaError_t launch_backward_tpb_mode(const typename Fam::PriorT &P, int pm, cons
 }
 
 // Needs SolveArgs::perm16 = 1 (the forward pass wrote the history in the permuted order).
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, bool DO_MEAN, int DO_VAR, bool DO_SIM>
 cudaError_t launch_backward_tpb(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
   using L = TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>;
   if (!a.perm16) return cudaErrorInvalidValue;
@@ -598,7 +616,7 @@ cudaError_t launch_backward_tpb(const HostPrior &h, const SolveArgs &a, cudaStre
   return launch_backward_tpb_mode<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>(P, blocks_uniform<Fam>(P) ? 0 : 1, nullptr, a, s);
 }
 
-template <class Fam, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, int CK, bool DO_MEAN, int DO_VAR, bool DO_SIM>
 cudaError_t launch_backward_tpb_pp(const HostPrior &h, const BatchedPrior &bq, const SolveArgs &a, cudaStream_t s) {
   if (!a.perm16) return cudaErrorInvalidValue;
   if ((double)16 * a.n_steps * Fam::n * Fam::n * 8 >= 2147483648.0) return cudaErrorInvalidValue;

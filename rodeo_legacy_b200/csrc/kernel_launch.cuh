@@ -163,6 +163,12 @@ void fill_backward(KernelSet &k) {
     k.backward[CKI][BK_SIM] = launch_backward_tpb<FamB, CK, false, false, true>;
     k.backward[CKI][BK_BOTH] = launch_backward_tpb<FamB, CK, true, true, true>;
     k.backward_perm[CKI][BK_MV] = k.backward_perm[CKI][BK_SIM] = k.backward_perm[CKI][BK_BOTH] = true;
+    if constexpr (CK == 2) {   // compact variance layouts: diagonal blocks only / marginal variances only
+      k.backward_vl[0][0] = launch_backward_tpb<FamB, 2, true, 2, false>;
+      k.backward_vl[0][1] = launch_backward_tpb<FamB, 2, true, 2, true>;
+      k.backward_vl[1][0] = launch_backward_tpb<FamB, 2, true, 3, false>;
+      k.backward_vl[1][1] = launch_backward_tpb<FamB, 2, true, 3, true>;
+    }
     if constexpr (!Fam::kUT) {   // the round-1 smoother, kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
       k.backward_alt[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
       k.backward_alt[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
@@ -212,6 +218,7 @@ KernelSet make_kernel_set(const char *name) {
       k.backward[c][b] = k.backward_alt[c][b] = nullptr;
       k.backward_perm[c][b] = false;
     }
+  k.backward_vl[0][0] = k.backward_vl[0][1] = k.backward_vl[1][0] = k.backward_vl[1][1] = nullptr;
   fill_backward<Fam, Ode, BD, UNROLL, 1, 0>(k);
   if constexpr (UNROLL) {  // checkpointed history for the register families only
     fill_backward<Fam, Ode, BD, UNROLL, 2, 1>(k);

@@ -37,7 +37,10 @@ struct KernelSet {
   launch_fn backward[kNumCk][BK_COUNT];  // by checkpoint slot and BackwardKind (nullptr: not compiled)
   // the previous generation of a kernel where one is kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
   launch_fn backward_alt[kNumCk][BK_COUNT];
-  bool backward_perm[kNumCk][BK_COUNT];  // backward[][] wants the history in the permuted order (SolveArgs::perm16)
+  bool backward_perm[kNumCk][BK_COUNT];
+  // compact variance layouts (rodeo_cuda_set_var_layout): [layout - 1][0 = solve_mv, 1 = solve], checkpoint 2,
+  // permuted history; nullptr when not compiled for this set
+  launch_fn backward_vl[2][2];  // backward[][] wants the history in the permuted order (SolveArgs::perm16)
   int hist_elems;                 // doubles of history per system per step
   // shared-covariance mode (kalman_sc.cuh); all nullptr when not compiled for this set
   cudaError_t (*sc_tables)(const HostPrior &, int zero_H, double *tab, int *fail_out, cudaStream_t);

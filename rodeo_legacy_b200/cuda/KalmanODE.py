@@ -34,6 +34,8 @@ _ALIASES = {"lorenz": "lorenz63", "fitzhugh_nagumo": "fitz", "fitzhugh-nagumo": 
 _INTERROGATE = {"probde": 0, "schobert": 1, "chkrebtii": 2}
 MODE_MV, MODE_SIM, MODE_BOTH = 1, 2, 3
 _FIELDS = {"wgt_meas": 0, "mu_state": 1, "wgt_state": 2, "var_state": 3}
+_VAR_LAYOUTS = {"full": 0, "blocks": 1, "diag": 2}
+_VAR_LAYOUTS_INV = {v: k for k, v in _VAR_LAYOUTS.items()}
 
 
 def register_names():
@@ -99,7 +101,7 @@ def _ptr(t):
 class KalmanODE:
     def __init__(self, W, tmin, tmax, n_eval, ode_fun, mu_state, wgt_state, var_state,
                  z_state=None, interrogate="probde", device=None, force_dense=False, checkpoint=0,
-                 shared_cov=False, use_structure=True):
+                 shared_cov=False, use_structure=True, var_layout="full"):
         self._lib = _lib.load()                      # raises if the CUDA library is missing
         if not torch.cuda.is_available():
             raise RuntimeError("rodeo.cuda needs a CUDA device; there is no CPU fallback")
@@ -145,6 +147,8 @@ class KalmanODE:
             self.checkpoint = checkpoint
         if shared_cov:
             self.shared_cov = True
+        if var_layout != "full":
+            self.var_layout = var_layout
         self._z_dev = None          # cached device copy of the shared z
         self._ll_cache = {}
 
@@ -236,6 +240,27 @@ class KalmanODE:
         bd, rg, _ = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _lib.check(self._lib.rodeo_cuda_problem_info(self._h, ctypes.byref(bd), ctypes.byref(rg), ctypes.byref(_)))
         return ("blockdiag" if bd.value else "dense", ("rolled", "registers", "wide")[rg.value])
+
+    @property
+    def var_layout(self):
+        """Layout of the returned variance: ``"full"`` (default, the reference's (n, n) matrices), ``"blocks"``
+        ((n_meas, p, p): the diagonal blocks only) or ``"diag"`` ((n,): marginal variances).  The compact layouts
+        are opt-in for block-diagonal priors with two blocks; they hold the same numbers as the corresponding
+        entries of the full output and cut the bytes written and copied to the host (FitzHugh-Nagumo solve_mv:
+        336 -> 192 / 96 bytes per system and step).  Not applied to ``priors=`` calls or shared-covariance mode."""
+        return _VAR_LAYOUTS_INV[int(self._lib.rodeo_cuda_get_var_layout(self._h))]
+
+    @var_layout.setter
+    def var_layout(self, name):
+        if name not in _VAR_LAYOUTS:
+            raise ValueError(f"var_layout must be one of {sorted(_VAR_LAYOUTS)}")
+        _lib.check(self._lib.rodeo_cuda_set_var_layout(self._h, _VAR_LAYOUTS[name]))
+
+    def _var_shape(self, B):
+        n, m, T = self.n_state, self.n_meas, self.n_steps
+        lay = self.var_layout
+        p = n // m
+        return (B, T, m, p, p) if lay == "blocks" else (B, T, n) if lay == "diag" else (B, T, n, n)
 
     @property
     def last_batched_prior_blockdiag(self):
@@ -386,7 +411,7 @@ class KalmanODE:
         n, T = self.n_state, self.n_steps
         mv, sim = bool(mode & MODE_MV), bool(mode & MODE_SIM)
         shared = self.shared_cov
-        vshape = (T, n, n) if shared else (B, T, n, n)     # shared: ONE array for the batch
+        vshape = (T, n, n) if shared else self._var_shape(B)     # shared: ONE array for the batch
         if on_dev:
             dev = x0b.device
             mk = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)

@@ -39,6 +39,9 @@ SYMBOLS = [
     ("rodeo_cuda_set_workspace_limit", _I, [_V, _Z]),
     ("rodeo_cuda_set_checkpoint", _I, [_V, _I]),
     ("rodeo_cuda_get_checkpoint", _I, [_V]),
+    ("rodeo_cuda_set_var_layout", _I, [_V, _I]),
+    ("rodeo_cuda_get_var_layout", _I, [_V]),
+    ("rodeo_cuda_var_doubles_per_step", _I, [_V]),
     ("rodeo_cuda_set_shared_cov", _I, [_V, _I]),
     ("rodeo_cuda_get_shared_cov", _I, [_V]),
     ("rodeo_cuda_reserve", _I, [_V, _L]),

@@ -942,3 +942,55 @@ def test_per_system_blockdiag_priors_and_sigma_sweep_likelihood():
             assert np.isclose(ll[b], oracle.loglik(ref[key], ind, [0, 3], Y, gam), rtol=1e-8)
     ll_np = k.loglik(x0, theta, Y, ind, [0, 3], gam, priors=pri)
     assert isinstance(ll_np, np.ndarray) and ll_np.shape == (B,)
+
+
+@pytest.mark.parametrize("B,N", [(3000, 400), (77, 33), (1, 2)])
+def test_compact_variance_layouts(B, N):
+    """var_layout="blocks" / "diag" (opt-in): the diagonal (p, p) blocks / the marginal variances of the reference's
+    (n, n) output, bit for bit, through the device and the host entry points, solve_mv and solve; means and draws
+    unchanged; against the oracle's full matrices."""
+    w, x0, theta = wl.fitz_batch(B, seed=12)
+    if N != w["N"]:
+        w = dict(w, N=N, tmax=w["tmax"] * N / w["N"])
+    z = np.asfortranarray(np.random.default_rng(2).standard_normal((6, N)))
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    kf = wl.make_kode(w, z_state=z)
+    xf, muf, varf = kf.solve(x0d, theta=thd)
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, None, oracle.MODE_MV)
+    blocks_of = lambda v: torch.stack([v[..., 0:3, 0:3], v[..., 3:6, 3:6]], dim=-3)
+    for lay in ("blocks", "diag"):
+        k = wl.make_kode(w, z_state=z, var_layout=lay)
+        assert k.var_layout == lay
+        want = blocks_of(varf) if lay == "blocks" else torch.diagonal(varf, dim1=-2, dim2=-1)
+        mu, var = k.solve_mv(x0d, theta=thd)
+        assert var.shape == ((B, N + 1, 2, 3, 3) if lay == "blocks" else (B, N + 1, 6))
+        assert torch.equal(mu, muf) and torch.equal(var, want.contiguous())
+        x, mu2, var2 = k.solve(x0d, theta=thd)
+        assert torch.equal(x, xf) and torch.equal(mu2, muf) and torch.equal(var2, var)
+        assert torch.equal(k.solve_sim(x0d, theta=thd), xf)
+        muh, varh = k.solve_mv(x0, theta=theta)                      # host buffers: fewer bytes cross PCIe
+        np.testing.assert_array_equal(varh, var.cpu().numpy())
+        np.testing.assert_array_equal(muh, muf.cpu().numpy())
+        ro = ref["var"]
+        wo = (np.stack([ro[..., 0:3, 0:3], ro[..., 3:6, 3:6]], axis=-3) if lay == "blocks"
+              else np.diagonal(ro, axis1=-2, axis2=-1))
+        got = var.cpu().numpy()
+        assert np.abs(got - wo).max() <= 1e-10 * np.abs(wo).max()
+        # 1-D x0: the reference's single-solve shapes
+        m1, v1 = k.solve_mv(np.asfortranarray(x0[0]), theta=theta[0])
+        assert v1.shape == ((N + 1, 2, 3, 3) if lay == "blocks" else (N + 1, 6))
+    kf.var_layout = "diag"                                           # settable after construction, and back
+    assert kf.solve_mv(x0d, theta=thd)[1].shape == (B, N + 1, 6)
+    kf.var_layout = "full"
+    assert torch.equal(kf.solve_mv(x0d, theta=thd)[1], varf)
+    with pytest.raises(ValueError):
+        kf.var_layout = "upper"
+    # families without the thread-per-block kernels refuse instead of silently returning the full layout
+    wL, _, _ = wl.lorenz_batch(4, N=50, tmax=0.2)
+    with pytest.raises(NotImplementedError):
+        wl.make_kode(wL, var_layout="blocks")
+    with pytest.raises(NotImplementedError):
+        wl.make_kode(w, force_dense=True, var_layout="diag")
+    ks = wl.make_kode(w, shared_cov=True, var_layout="blocks")
+    with pytest.raises(NotImplementedError):
+        ks.solve_mv(x0d, theta=thd)
