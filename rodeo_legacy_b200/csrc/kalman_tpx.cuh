@@ -300,6 +300,11 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
     if (valid[u] && a.status && fail[u]) atomicCAS(a.status + b[u], 0, blk * p + fail[u]);
 }
 
+// A thread-per-block FORWARD filter for >= 3 blocks was measured and dropped: with 10 systems per warp its history
+// stores are 80-byte pieces (partial 32-byte sectors: Lorenz63 3.9 ms vs 1.9 ms for the thread-per-system kernel,
+// MSEIR 7.6 vs 2.0 ms), with 8 systems per warp (aligned 64-byte pieces) still 2.08 vs 1.88 ms -- the forward pass is
+// bound by how its history rows reach DRAM, and one thread per system writes whole 256-byte rows per instruction.
+
 template <class Fam, int CK, int U>
 cudaError_t launch_backward_tpx(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
   using L = TpxLayout<Fam, CK, U>;
