@@ -22,10 +22,11 @@
 //     registers one group (CK steps) ahead (half-warp = 128 contiguous bytes per element row); no ring.
 //   * checkpoint interval CK in {1, 2}: for CK = 2 the filter is re-run from the checkpoint for one step in
 //     registers (same routines as the forward pass: bit-identical moments).
-//   * outputs: per output array the warp keeps NSLOT granule slots in shared memory, a slot being two TMA box
-//     images {16 doubles, 1, 16 systems} (2 x 2 KB, 128-byte swizzle: lane i's 16-byte chunk c sits at chunk
-//     c ^ (i & 7), which makes the row writes bank-conflict free).  A slot holds granule (x >> 8) % NSLOT of
-//     every system, x = byte offset inside the 16-system row.  Every lane writes its block's rows of the
+//   * outputs: per output array the warp keeps NSLOT granule slots in shared memory, a slot being ONE TMA box
+//     image {16 doubles, 2, 16 systems} (4 KB: [system][half][128 bytes], 128-byte swizzle: chunk c of 128-byte
+//     row r = 2 i + half sits at chunk c ^ (r & 7), a 2-way bank conflict on the per-lane row writes, which is
+//     cheap; one store per whole granule is what the memory system wants).  A slot holds granule (x >> 8) % NSLOT
+//     of every system, x = byte offset inside the 16-system row.  Every lane writes its block's rows of the
 //     step's run (structural zeros included); when the run completes a granule, lane 0 issues one tensor
 //     store.  Trajectory ends (partial granules) and the systems of a last incomplete 16-system row are
 //     stored with plain 16-byte stores.
@@ -44,9 +45,12 @@ constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 
 // Tensor map of one output array for the granule stores: W doubles per (system, time index).
 // Byte address = k * PITCH + x with k = system / 16 and x the offset inside the 16-system row,
-// PITCH = 16 * T1 * W * 8.  Dimensions {16 doubles, x / 128, k < B / 16}, box {16, 1, 16}: half a granule of
-// 16 systems, [system][128 bytes] in shared memory (two stores per granule).
-inline cudaError_t encode_granule_map(CUtensorMap *m, double *base, int W, long T1, long B) {
+// PITCH = 16 * T1 * W * 8.  Dimensions {16 doubles, x / 128, k < B / 16}, box {16, G / 128, 16}: one whole granule
+// of 16 systems per store, [system][G / 128][128 bytes] in shared memory.  ONE store per granule matters: with two
+// 128-byte-wide boxes per 256-byte granule the halves of a granule reach L2 / DRAM separated in time and the
+// memory system runs at the 128-byte-granule rate (write_pattern3: 4.6 vs 5.75 TB/s) -- measured in the kernel:
+// 1.97 ms with box {16, 1, 16}, see NOTES_r02.md for the one-store figure.
+inline cudaError_t encode_granule_map(CUtensorMap *m, double *base, int W, long T1, long B, int G = kGranule) {
   memset(m, 0, sizeof *m);
   if (!base || B < 16) return cudaSuccess;     // no complete 16-system row: only plain stores are used
   encode_tiled_fn enc = tensor_map_encoder();
@@ -54,7 +58,7 @@ inline cudaError_t encode_granule_map(CUtensorMap *m, double *base, int W, long 
   const cuuint64_t pitch = (cuuint64_t)16 * T1 * W * 8;
   const cuuint64_t dims[3] = {16, pitch / 128, (cuuint64_t)(B / 16)};
   const cuuint64_t strides[2] = {128, pitch};
-  const cuuint32_t box[3] = {16, 1, 16};
+  const cuuint32_t box[3] = {16, (cuuint32_t)(G / 128), 16};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -80,6 +84,7 @@ struct GranuleMaps {
 template <int W, int G = kGranule>
 struct GranuleStream {
   static constexpr int RUN = W * 8;                                  // bytes per system and step
+  static constexpr int kG = G;
   static_assert(G >= 256 && (G & (G - 1)) == 0 && (16 * W * 8) % G == 0, "granule size");
   static constexpr int SLACK = G - cgcd(RUN, G);       // most bytes left pending after an emission
   static constexpr int NSLOT = (SLACK + RUN + G - 1) / G;
@@ -91,23 +96,27 @@ struct GranuleStream {
   int Fx;          // everything at or above Fx (a granule boundary) is stored or not ours
   int x_end;       // end of this warp's trajectories inside the row: (j + 1) * T1 * RUN
   uint32_t tile;   // shared address of the slots (1024-byte aligned)
-  uint32_t tile_i; // tile + i * 128
-  uint32_t i7s;    // (i & 7) << 4: the swizzle of this lane's row
+  uint32_t tile_i; // tile + i * G: this lane's system inside a slot
+  uint32_t r0;     // i * (G / 128): index of this lane's first 128-byte row inside a slot (the swizzle key)
   char *out_i;     // array + (system / 16) * PITCH: this lane's row base in global memory
   __device__ __forceinline__ void init(uint32_t tile_, int i, double *out, long k_row, int j, long T1) {
     x_end = (int)((j + 1) * T1 * RUN);
     x = x_end;
     Fx = (x_end + G - 1) & ~(G - 1);
     tile = tile_;
-    tile_i = tile + (uint32_t)i * 128u;
-    i7s = (uint32_t)(i & 7) << 4;
+    tile_i = tile + (uint32_t)i * (uint32_t)G;
+    r0 = (uint32_t)i * (uint32_t)(G / 128);
     out_i = reinterpret_cast<char *>(out) + k_row * (16 * T1 * RUN);
   }
   __device__ __forceinline__ void advance() { x -= RUN; }
   // shared address of byte xx (a multiple of 8) of this lane's system
   __device__ __forceinline__ uint32_t phys(int xx) const {
     const uint32_t u = (uint32_t)xx;
-    return tile_i + (((u >> 7) % UNITS) << 11) + (((u & 0x70u) ^ i7s) | (u & 8u));
+    // slot image = the TMA box {16 doubles, G / 128, 16 systems} with the 128-byte swizzle: 128-byte row
+    // r = i * (G / 128) + hh of the slot, its 16-byte chunk c stored at chunk c ^ (r & 7)
+    const uint32_t unit = (u >> 7) % UNITS, hh = unit % (G / 128), slot = unit / (G / 128);
+    const uint32_t swz = ((r0 + hh) & 7u) << 4;
+    return tile_i + slot * (16u * G) + hh * 128u + (((u & 0x70u) ^ swz) | (u & 8u));
   }
   // CNT doubles of the current run starting at byte offset rb (lane dependent) of the run
   template <int CNT>
@@ -143,9 +152,7 @@ struct GranuleStream {
         if (mine) copy_lsu(g0, x_end);
       } else {
         if (full_row && lane0) {
-          const uint32_t src = tile + (((uint32_t)g0 / G) % NSLOT) * (16u * G);
-#pragma unroll
-          for (int h = 0; h < G / 128; h++) tma_store_3d_s(map, src + 2048u * h, 0, (g0 >> 7) + h, row0);
+          tma_store_3d_s(map, tile + (((uint32_t)g0 / G) % NSLOT) * (16u * G), 0, g0 >> 7, row0);
         }
         if (mine && tail_row) copy_lsu(g0, g0 + G);
       }
@@ -164,7 +171,7 @@ template <class Fam, int CK, bool DO_MEAN, int DO_VAR, bool DO_SIM>
 struct TpbLayout {
   static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
   static_assert(nb == 2, "thread-per-block smoother: two diagonal blocks (16 systems x 2 blocks per warp)");
-  static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
+  static_assert(CK == 1 || CK == 2 || CK == 4, "thread-per-block smoother: checkpoint interval 1, 2 or 4");
 #ifndef RODEO_TPB_GVAR
 #define RODEO_TPB_GVAR 256
 #endif
@@ -393,7 +400,7 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
       for (int e = 0; e < PS; e++) cS[e] = nS[e];
       if (r + 1 < R) load_rec(r + 1, nm, nS);            // one group ahead
     }
-    if (CK == 2) {
+    if constexpr (CK > 1) {
       const int t0 = base >= 1 ? base : 0;
       if (base < 1) {   // the known initial state (KalmanODE.pyx:293-297)
 #pragma unroll
@@ -401,28 +408,39 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
         for (int e = 0; e < PS; e++) cS[e] = 0.0;
       }
-      if (t_hi - 1 > t0) {
-        // re-run the filter t0 -> t0 + 1 (BdFam::step, this block's share; the right-hand side needs every
-        // block's predicted first component: one shuffle per block)
-        double fm[p], fS[PS];
-        reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), cm, fm);
-        reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), cS, fS, nullptr);
-        double X[n], y[Fam::m];
+      const int nfwd = t_hi - 1 - t0;   // time indices t0+1 .. t_hi-1 are re-run from the checkpoint (0 .. CK-1 of them)
+      // re-run the filter (BdFam::step, this block's share; the right-hand side needs every block's predicted
+      // first component: one shuffle per block), keeping the CK-1 intermediate filtered states in registers
+      double sm_[CK - 1][p], sS_[CK - 1][PS];
 #pragma unroll
-        for (int e = 0; e < n; e++) X[e] = 0.0;
+      for (int jf = 0; jf < CK - 1; jf++) {
+        if (jf < nfwd) {
+          const double *pm = jf == 0 ? cm : sm_[jf == 0 ? 0 : jf - 1];
+          const double *pS = jf == 0 ? cS : sS_[jf == 0 ? 0 : jf - 1];
+          reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), pm, sm_[jf]);
+          reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), pS, sS_[jf], nullptr);
+          double X[n], y[Fam::m];
 #pragma unroll
-        for (int k = 0; k < nb; k++) X[k * p] = __shfl_sync(kFull, fm[0], k * 16 + i);
-        const double tt = P.tmin + (P.tmax - P.tmin) * (t0 + 1) / P.n_eval;
-        Ode::template eval<n>(X, tt, th, y);
-        double ya = y[0];
+          for (int e = 0; e < n; e++) X[e] = 0.0;
 #pragma unroll
-        for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
-        reg::update_block<p, Fam::kWK>(bp.w(), fm, fS, ya, false);
-        const int t = t0 + 1;
-        const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
-            bp.Q(), bp.c(), bp.R(), fm, fS, DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
-        if (f && !fail) fail = f;
-        emit(t, mus, Ss, x);
+          for (int k = 0; k < nb; k++) X[k * p] = __shfl_sync(kFull, sm_[jf][0], k * 16 + i);
+          const double tt = P.tmin + (P.tmax - P.tmin) * (t0 + jf + 1) / P.n_eval;
+          Ode::template eval<n>(X, tt, th, y);
+          double ya = y[0];
+#pragma unroll
+          for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
+          reg::update_block<p, Fam::kWK>(bp.w(), sm_[jf], sS_[jf], ya, false);
+        }
+      }
+#pragma unroll
+      for (int jf = CK - 2; jf >= 0; jf--) {
+        if (jf < nfwd) {
+          const int t = t0 + jf + 1;
+          const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
+              bp.Q(), bp.c(), bp.R(), sm_[jf], sS_[jf], DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
+          if (f && !fail) fail = f;
+          emit(t, mus, Ss, x);
+        }
       }
     }
     if (base >= 1) {
@@ -598,7 +616,7 @@ cudaError_t launch_backward_tpb_mode(const typename Fam::PriorT &P, int pm, cons
   constexpr int n = Fam::n;
   if ((e = encode_granule_map(&maps.mu, DO_MEAN ? a.mu_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
   if ((e = encode_granule_map(&maps.x, DO_SIM ? a.x_out : nullptr, n, a.n_steps, a.B)) != cudaSuccess) return e;
-  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, L::WV, a.n_steps, a.B)) != cudaSuccess) return e;
+  if ((e = encode_granule_map(&maps.var, DO_VAR ? a.var_out : nullptr, L::WV, a.n_steps, a.B, L::SVar::kG)) != cudaSuccess) return e;
   const long n_warps = (a.B + 255) / 256 * 16;
   const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
   const BatchedPrior none{nullptr, nullptr, nullptr, nullptr};

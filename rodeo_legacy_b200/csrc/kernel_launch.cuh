@@ -150,7 +150,7 @@ void fill_backward(KernelSet &k) {
     } else {
       return;   // leaves this slot empty: the API falls back to interval 1 for this family
     }
-  } else if constexpr (UNROLL && BD && Ode::n_meas == 2 && (CK == 1 || CK == 2)) {
+  } else if constexpr (UNROLL && BD && Ode::n_meas == 2) {
     // two diagonal blocks (FitzHugh-Nagumo): one thread per block, history prefetched into registers,
     // outputs as whole 256-byte-aligned granules through TMA tensor stores (kalman_tpb.cuh); these
     // launchers need the history in the permuted order (backward_perm -> SolveArgs::perm16)
