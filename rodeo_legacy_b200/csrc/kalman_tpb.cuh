@@ -275,7 +275,9 @@ __device__ __forceinline__ double ld_stream(const double *p) {
   return v;
 }
 
-template <class Fam, int CK, int PM, bool DO_MEAN, int DO_VAR, bool DO_SIM>
+// LL: no per-step output; the thinned Gaussian log-likelihood of the smoothed mean (DO_MEAN) or of the draw (DO_SIM)
+// is accumulated per system (examples/inference.py:54-56, 66-94) -- no shared memory, no stores but one double.
+template <class Fam, int CK, int PM, bool DO_MEAN, int DO_VAR, bool DO_SIM, bool LL = false>
 __global__ void __launch_bounds__(TpbLayout<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>::THREADS)
 #ifdef RODEO_TPB_MAXNREG
 __maxnreg__(RODEO_TPB_MAXNREG)
@@ -312,11 +314,27 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
   const bool mine = valid && blk == 0, lane0 = lane == 0;
   typename L::SVec sm, sx;
   typename L::SVar sv;
-  if (DO_MEAN) sm.init(tile + L::OFF_MEAN, i, a.mu_out, k_row, j, T1);
-  if (DO_SIM) sx.init(tile + L::OFF_X, i, a.x_out, k_row, j, T1);
-  if (DO_VAR) sv.init(tile + L::OFF_VAR, i, a.var_out, k_row, j, T1);
+  if (!LL && DO_MEAN) sm.init(tile + L::OFF_MEAN, i, a.mu_out, k_row, j, T1);
+  if (!LL && DO_SIM) sx.init(tile + L::OFF_X, i, a.x_out, k_row, j, T1);
+  if (!LL && DO_VAR) sv.init(tile + L::OFF_VAR, i, a.var_out, k_row, j, T1);
+  double lp = 0.0;                 // (LL) this system's log-likelihood so far
+  int d_obs = a.n_obs_times - 1;   // (LL) next observation time, walking backwards
 
   auto emit = [&](int t, const double *mus, const double *Ss, const double *x) {
+    if constexpr (LL) {
+      // At an observed time index the lanes of a system pool the state vector and add the terms in the order of
+      // the thread-per-system kernels (LoglikEmitter, kalman_staged.cuh), so the sums are bit-identical to theirs.
+      while (d_obs >= 0 && a.thin_index[d_obs] == t) {       // warp-uniform
+        double X[n];
+#pragma unroll
+        for (int k = 0; k < nb; k++)
+#pragma unroll
+          for (int e = 0; e < p; e++) X[k * p + e] = __shfl_sync(kFull, DO_SIM ? x[e] : mus[e], k * 16 + i);
+        lp += reg::loglik_terms<n>(a, d_obs, X);
+        d_obs--;
+      }
+      return;
+    }
     if (lane0) tma_wait_read();   // the earlier tensor stores have left the slots
     __syncwarp();
     if (DO_MEAN) {
@@ -463,7 +481,13 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
     for (int e = 0; e < PS; e++) Ss[e] = 0.0;
     emit(0, mus, Ss, x);
   }
-  if (lane0) tma_wait_all();
+  if constexpr (LL) {
+    // constant of the normal density: -(log sqrt(2 pi) + log gamma) per observation (as LoglikEmitter::finish)
+    const double cst = -0.91893853320467274178 - log(a.gamma);
+    if (valid && blk == 0) a.loglik[b] = lp + cst * (double)(a.n_obs_times * a.n_obs_comp);
+  } else {
+    if (lane0) tma_wait_all();
+  }
   if (valid && a.status && fail) atomicCAS(a.status + b, 0, blk * p + fail);
 }
 
@@ -632,6 +656,22 @@ cudaError_t launch_backward_tpb(const HostPrior &h, const SolveArgs &a, cudaStre
   if ((double)16 * a.n_steps * Fam::n * Fam::n * 8 >= 2147483648.0) return cudaErrorInvalidValue;   // 32-bit row coordinates
   const typename Fam::PriorT P = make_prior<Fam>(h);
   return launch_backward_tpb_mode<Fam, CK, DO_MEAN, DO_VAR, DO_SIM>(P, blocks_uniform<Fam>(P) ? 0 : 1, nullptr, a, s);
+}
+
+// log-likelihood smoother (DRAW: of the draw, else of the mean): FP64-bound, no shared memory, full occupancy
+template <class Fam, int CK, bool DRAW>
+cudaError_t launch_backward_tpb_ll(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  using L = TpbLayout<Fam, CK, !DRAW, 0, DRAW>;
+  if (!a.perm16) return cudaErrorInvalidValue;
+  const typename Fam::PriorT P = make_prior<Fam>(h);
+  const long n_warps = (a.B + 255) / 256 * 16;
+  const unsigned grid = (unsigned)((n_warps + L::WARPS - 1) / L::WARPS);
+  GranuleMaps maps;
+  memset(&maps, 0, sizeof maps);
+  const BatchedPrior none{nullptr, nullptr, nullptr, nullptr};
+  if (blocks_uniform<Fam>(P)) kalman_backward_tpb<Fam, CK, 0, !DRAW, 0, DRAW, true><<<grid, L::THREADS, 0, s>>>(P, a, maps, none);
+  else kalman_backward_tpb<Fam, CK, 1, !DRAW, 0, DRAW, true><<<grid, L::THREADS, 0, s>>>(P, a, maps, none);
+  return cudaGetLastError();
 }
 
 template <class Fam, int CK, bool DO_MEAN, int DO_VAR, bool DO_SIM>

@@ -183,7 +183,15 @@ void fill_backward(KernelSet &k) {
     k.backward[CKI][BK_SIM] = launch_backward<Fam, UNROLL, CK, false, false, true, false>;
     k.backward[CKI][BK_BOTH] = launch_backward<Fam, UNROLL, CK, true, true, true, false>;
   }
-  if constexpr (UNROLL) {   // register families: history through the TMA ring, nothing staged out
+  if constexpr (UNROLL && BD && Ode::n_meas == 2 && CK == 2) {
+    // two blocks, the auto interval: thread-per-block log-likelihood smoother (kalman_tpb.cuh), structured
+    // arithmetic where the set has it (the kernel is FP64-bound); same sums, bit for bit, as the staged kernels
+    k.backward[CKI][BK_LL_MEAN] = launch_backward_tpb_ll<Fam, CK, false>;
+    k.backward[CKI][BK_LL_DRAW] = launch_backward_tpb_ll<Fam, CK, true>;
+    k.backward_perm[CKI][BK_LL_MEAN] = k.backward_perm[CKI][BK_LL_DRAW] = true;
+    k.backward_alt[CKI][BK_LL_MEAN] = launch_backward_staged<Fam, CK, true, false, false, true>;
+    k.backward_alt[CKI][BK_LL_DRAW] = launch_backward_staged<Fam, CK, false, false, true, true>;
+  } else if constexpr (UNROLL) {   // register families: history through the TMA ring, nothing staged out
     k.backward[CKI][BK_LL_MEAN] = launch_backward_staged<Fam, CK, true, false, false, true>;
     k.backward[CKI][BK_LL_DRAW] = launch_backward_staged<Fam, CK, false, false, true, true>;
   } else {
