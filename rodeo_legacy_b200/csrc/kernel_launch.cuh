@@ -140,10 +140,12 @@ void fill_backward(KernelSet &k) {
     // Draw-only smoothing (solve_sim): one thread per block, two systems per lane, checkpoint interval 1 or 2
     // (kalman_tpx.cuh).  Intervals > 1 exist for that entry point only; the API picks the interval per entry point.
     if constexpr (CK == 1) {
-      k.backward[CKI][BK_MV] = launch_backward_bdw<Fam, true, true, false>;
+      if constexpr (!Fam::kUT) {   // HBM-bound: shared with the structured twin (registry.cu)
+        k.backward[CKI][BK_MV] = launch_backward_bdw<Fam, true, true, false>;
+        k.backward[CKI][BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
+        k.backward_alt[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
+      }
       k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 1, RODEO_TPX_U>;
-      k.backward_alt[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
-      k.backward[CKI][BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
     } else if constexpr (CK == 2) {
       k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 2, RODEO_TPX_U>;
       return;   // the other entry points of this family keep the full history
@@ -158,18 +160,19 @@ void fill_backward(KernelSet &k) {
     // measured 3 % slower (FN solve_mv 2.03 -> 2.10 ms: same register cap, one spill), so the structured sets
     // reuse the general family's instantiation there (bit-identical results; also halves the build).  The
     // FP64-bound kernels (forward filters, log-likelihood smoothers) do use the specialisation.
-    using FamB = typename Fam::General;
-    k.backward[CKI][BK_MV] = launch_backward_tpb<FamB, CK, true, true, false>;
-    k.backward[CKI][BK_SIM] = launch_backward_tpb<FamB, CK, false, false, true>;
-    k.backward[CKI][BK_BOTH] = launch_backward_tpb<FamB, CK, true, true, true>;
-    k.backward_perm[CKI][BK_MV] = k.backward_perm[CKI][BK_SIM] = k.backward_perm[CKI][BK_BOTH] = true;
-    if constexpr (CK == 2) {   // compact variance layouts: diagonal blocks only / marginal variances only
-      k.backward_vl[0][0] = launch_backward_tpb<FamB, 2, true, 2, false>;
-      k.backward_vl[0][1] = launch_backward_tpb<FamB, 2, true, 2, true>;
-      k.backward_vl[1][0] = launch_backward_tpb<FamB, 2, true, 3, false>;
-      k.backward_vl[1][1] = launch_backward_tpb<FamB, 2, true, 3, true>;
-    }
-    if constexpr (!Fam::kUT) {   // the round-1 smoother, kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
+    // (the structured sets leave these slots empty here: registry.cu points them at the general set's launchers)
+    if constexpr (!Fam::kUT) {
+      k.backward[CKI][BK_MV] = launch_backward_tpb<Fam, CK, true, true, false>;
+      k.backward[CKI][BK_SIM] = launch_backward_tpb<Fam, CK, false, false, true>;
+      k.backward[CKI][BK_BOTH] = launch_backward_tpb<Fam, CK, true, true, true>;
+      k.backward_perm[CKI][BK_MV] = k.backward_perm[CKI][BK_SIM] = k.backward_perm[CKI][BK_BOTH] = true;
+      if constexpr (CK == 2) {   // compact variance layouts: diagonal blocks only / marginal variances only
+        k.backward_vl[0][0] = launch_backward_tpb<Fam, 2, true, 2, false>;
+        k.backward_vl[0][1] = launch_backward_tpb<Fam, 2, true, 2, true>;
+        k.backward_vl[1][0] = launch_backward_tpb<Fam, 2, true, 3, false>;
+        k.backward_vl[1][1] = launch_backward_tpb<Fam, 2, true, 3, true>;
+      }
+      // the round-1 smoother, kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
       k.backward_alt[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
       k.backward_alt[CKI][BK_SIM] = launch_backward_staged<Fam, CK, false, false, true>;
       k.backward_alt[CKI][BK_BOTH] = launch_backward_staged<Fam, CK, true, true, true>;
@@ -242,12 +245,11 @@ KernelSet make_kernel_set(const char *name) {
   for (int b = 0; b < BK_COUNT; b++) k.pp_backward[b] = nullptr;
   k.pp_bd_forward = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.pp_bd_backward[b] = nullptr;
-  if constexpr (UNROLL && BD && Ode::n_meas == 2) {   // per-system priors that are block diagonal per system
-    using FamG = typename Fam::General;
-    k.pp_bd_forward = launch_forward_tpb_pp<FamG>;
-    k.pp_bd_backward[BK_MV] = launch_backward_tpb_pp<FamG, 2, true, true, false>;
-    k.pp_bd_backward[BK_SIM] = launch_backward_tpb_pp<FamG, 2, false, false, true>;
-    k.pp_bd_backward[BK_BOTH] = launch_backward_tpb_pp<FamG, 2, true, true, true>;
+  if constexpr (UNROLL && BD && Ode::n_meas == 2 && !ST) {   // per-system priors that are block diagonal per system
+    k.pp_bd_forward = launch_forward_tpb_pp<Fam>;             // (general arithmetic; structured twins borrow them)
+    k.pp_bd_backward[BK_MV] = launch_backward_tpb_pp<Fam, 2, true, true, false>;
+    k.pp_bd_backward[BK_SIM] = launch_backward_tpb_pp<Fam, 2, false, false, true>;
+    k.pp_bd_backward[BK_BOTH] = launch_backward_tpb_pp<Fam, 2, true, true, true>;
   }
   k.wide_forward[0] = k.wide_forward[1] = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.wide_backward[b] = nullptr;

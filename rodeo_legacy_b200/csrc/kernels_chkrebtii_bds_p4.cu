@@ -1,0 +1,7 @@
+// kernels_chkrebtii_bds_p4.cu -- 'chkrebtii' right-hand side, block-diagonal family specialised for structured priors (upper-triangular Q blocks, w = e_order), block size 4.
+#include "kernel_launch.cuh"
+namespace rodeo {
+void register_chkrebtii_bds_p4(KernelSet *out, int *count) {
+  out[(*count)++] = make_kernel_set<OdeChkrebtii, 4, true, true, true>("chkrebtii/bds-p4");
+}
+}  // namespace rodeo

@@ -6,9 +6,27 @@
 namespace rodeo {
 
 #define RODEO_REG(name) void register_##name(KernelSet *, int *);
-RODEO_REG(chkrebtii_dense) RODEO_REG(chkrebtii_bd) RODEO_REG(fitz_dense) RODEO_REG(fitz_bd)
-RODEO_REG(lorenz_dense) RODEO_REG(lorenz_bd) RODEO_REG(mseir_dense) RODEO_REG(mseir_bd)
-RODEO_REG(chkrebtii_bds) RODEO_REG(fitz_bds) RODEO_REG(lorenz_bds) RODEO_REG(mseir_bds)
+RODEO_REG(chkrebtii_dense) RODEO_REG(fitz_dense) RODEO_REG(lorenz_dense) RODEO_REG(mseir_dense)
+RODEO_REG(chkrebtii_bd_p3)
+RODEO_REG(chkrebtii_bd_p4)
+RODEO_REG(chkrebtii_bds_p3)
+RODEO_REG(chkrebtii_bds_p4)
+RODEO_REG(fitz_bd_p2)
+RODEO_REG(fitz_bd_p3)
+RODEO_REG(fitz_bd_p4)
+RODEO_REG(fitz_bds_p2)
+RODEO_REG(fitz_bds_p3)
+RODEO_REG(fitz_bds_p4)
+RODEO_REG(lorenz_bd_p2)
+RODEO_REG(lorenz_bd_p3)
+RODEO_REG(lorenz_bd_p4)
+RODEO_REG(lorenz_bds_p2)
+RODEO_REG(lorenz_bds_p3)
+RODEO_REG(lorenz_bds_p4)
+RODEO_REG(mseir_bd_p2)
+RODEO_REG(mseir_bd_p3)
+RODEO_REG(mseir_bds_p2)
+RODEO_REG(mseir_bds_p3)
 #undef RODEO_REG
 
 void attach_wide(KernelSet *, int);   // kernels_wide.cu
@@ -20,18 +38,56 @@ static std::once_flag g_once;
 static void fill_sets() {
   int c = 0;
   register_chkrebtii_dense(g_sets, &c);
-  register_chkrebtii_bd(g_sets, &c);
   register_fitz_dense(g_sets, &c);
-  register_fitz_bd(g_sets, &c);
   register_lorenz_dense(g_sets, &c);
-  register_lorenz_bd(g_sets, &c);
   register_mseir_dense(g_sets, &c);
-  register_mseir_bd(g_sets, &c);
-  register_chkrebtii_bds(g_sets, &c);
-  register_fitz_bds(g_sets, &c);
-  register_lorenz_bds(g_sets, &c);
-  register_mseir_bds(g_sets, &c);
+  register_chkrebtii_bd_p3(g_sets, &c);
+  register_chkrebtii_bd_p4(g_sets, &c);
+  register_chkrebtii_bds_p3(g_sets, &c);
+  register_chkrebtii_bds_p4(g_sets, &c);
+  register_fitz_bd_p2(g_sets, &c);
+  register_fitz_bd_p3(g_sets, &c);
+  register_fitz_bd_p4(g_sets, &c);
+  register_fitz_bds_p2(g_sets, &c);
+  register_fitz_bds_p3(g_sets, &c);
+  register_fitz_bds_p4(g_sets, &c);
+  register_lorenz_bd_p2(g_sets, &c);
+  register_lorenz_bd_p3(g_sets, &c);
+  register_lorenz_bd_p4(g_sets, &c);
+  register_lorenz_bds_p2(g_sets, &c);
+  register_lorenz_bds_p3(g_sets, &c);
+  register_lorenz_bds_p4(g_sets, &c);
+  register_mseir_bd_p2(g_sets, &c);
+  register_mseir_bd_p3(g_sets, &c);
+  register_mseir_bds_p2(g_sets, &c);
+  register_mseir_bds_p3(g_sets, &c);
   attach_wide(g_sets, c);
+  // A structured set specialises only its FP64-bound kernels (forward filters, log-likelihood and draw-only
+  // smoothers).  Its HBM-bound, output-writing smoothers, the compact-layout and per-system-prior launchers ARE the
+  // general twin's (bit-identical results, nothing compiled twice): fill the empty slots from it.
+  for (int i = 0; i < c; i++) {
+    KernelSet &k = g_sets[i];
+    if (!k.structured) continue;
+    const KernelSet *g = nullptr;
+    for (int j = 0; j < c; j++)
+      if (!g_sets[j].structured && g_sets[j].blockdiag && g_sets[j].ode == k.ode && g_sets[j].n == k.n) g = &g_sets[j];
+    if (!g) continue;
+    for (int ci = 0; ci < kNumCk; ci++)
+      for (int b = 0; b < BK_COUNT; b++) {
+        if (!k.backward[ci][b] && g->backward[ci][b]) {
+          k.backward[ci][b] = g->backward[ci][b];
+          k.backward_perm[ci][b] = g->backward_perm[ci][b];
+        }
+        if (!k.backward_alt[ci][b]) k.backward_alt[ci][b] = g->backward_alt[ci][b];
+      }
+    for (int a = 0; a < 2; a++)
+      for (int b = 0; b < 2; b++)
+        if (!k.backward_vl[a][b]) k.backward_vl[a][b] = g->backward_vl[a][b];
+    if (!k.pp_bd_forward) {
+      k.pp_bd_forward = g->pp_bd_forward;
+      for (int b = 0; b < BK_COUNT; b++) k.pp_bd_backward[b] = g->pp_bd_backward[b];
+    }
+  }
   g_count = c;
 }
 static void init_sets() { std::call_once(g_once, fill_sets); }   // handles may be created from several threads
