@@ -149,6 +149,8 @@ extern "C" int hostsim_solve(int ode, int n, int m, int n_eval, double tmin, dou
                      : run_sc<reg::DenseFam<ODE, NN>>(h, ig, kind, a, var_out);           \
   }                                                                                       \
   if (ode == ID && n == NN) {                                                             \
+    if (blockdiag == 2) /* structured: upper-triangular Q blocks, w = e_order */          \
+      return run<reg::BdFam<ODE, PP, true>, true>(h, ig, kind, a);                        \
     if (blockdiag)                                                                        \
       return unroll ? run<reg::BdFam<ODE, PP>, true>(h, ig, kind, a)                      \
                     : run<loc::BdFam<ODE, PP>, false>(h, ig, kind, a);                    \

@@ -172,3 +172,23 @@ def test_random_dense_problems(seed):
     # a prior that is not positive definite is reported, not hidden
     bad = hostsim.solve("fitz", W, 0.0, 3.0, N, Q, c, -R, x0, theta, z, kind="mv")
     assert bad["status"].all()
+
+
+@pytest.mark.parametrize("name", ["chkrebtii_n200", "fitz_n400", "mseir_n1000"])
+def test_structured_bodies_are_bit_identical(name):
+    """The structured block-diagonal arithmetic (upper-triangular Q blocks, w = e_order: exact zeros skipped,
+    kalman_math.inl) against the general block-diagonal bodies on the IBM-prior golden cases: same bits for every
+    output, every entry point, checkpoint 1 and 2 -- on the CPU, no GPU needed."""
+    g, ode, p, x0, theta = _setup(name)
+    args = (ode, g["W"], p.tmin, p.tmax, p.N, g["Q"], g["c"], g["R"], x0, theta, g["z"])
+    for ck in (1, 2):
+        gen = hostsim.solve(*args, kind="both", blockdiag=1, ck=ck)
+        st = hostsim.solve(*args, kind="both", blockdiag=2, ck=ck)
+        for key in ("x", "mu", "var", "status"):
+            np.testing.assert_array_equal(st[key], gen[key])
+    if name == "fitz_n400":
+        ind, Y, gam = g["thin_ind"], g["Y"], float(g["gamma"])
+        for kind in ("ll_mean", "ll_draw"):
+            a = hostsim.solve(*args, kind=kind, blockdiag=1, thin_index=ind, state_index=[0, 3], Y=Y, gamma=gam)
+            b = hostsim.solve(*args, kind=kind, blockdiag=2, thin_index=ind, state_index=[0, 3], Y=Y, gamma=gam)
+            np.testing.assert_array_equal(a["loglik"], b["loglik"])
