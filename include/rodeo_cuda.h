@@ -258,6 +258,10 @@ int rodeo_cuda_kernel_ms_total(rodeo_problem *p, double *forward_ms, double *bac
  * hist[tile][record][element][32 systems] (csrc/kalman_common.cuh); for two-block block-diagonal priors
  * solved by the thread-per-block kernels, system b sits at position perm16(b) (same file). */
 int rodeo_cuda_debug_copy_history(rodeo_problem *p, void *dst_device, size_t bytes, void *cuda_stream);
+/* test hook: the thread-per-block kernels address a 16-system output row with 32-bit byte offsets; problems whose
+ * rows reach `bytes` (default and maximum 2^31: ~466,000 time steps at n_state 6) run on the previous-generation
+ * kernels instead.  Lowering it exercises that hand-over on ordinary sizes. */
+int rodeo_cuda_debug_set_row_limit(rodeo_problem *p, double bytes);
 /* enable (1) / disable (0) the event recording used by rodeo_cuda_last_kernel_ms / _kernel_ms_total
  * (either value restarts the accumulation) */
 int rodeo_cuda_set_timing(rodeo_problem *p, int enabled);

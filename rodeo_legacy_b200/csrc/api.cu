@@ -42,6 +42,7 @@ struct rodeo_problem {
   bool last_pp_bd = false;         // the last batched-prior solve ran on the block-diagonal kernels
   int ck = 0;                      // requested checkpoint interval of the filter history (0 = auto)
   int var_layout = 0;              // RODEO_VAR_FULL / _BLOCKS / _DIAG
+  double row_limit = 2147483648.0; // bytes of a 16-system output row the thread-per-block kernels address (32-bit)
   // shared-covariance mode (kalman_sc.inl): tables cached per (prior, N), rebuilt after problem_set
   bool shared = false;
   double *tab = nullptr;
@@ -446,11 +447,15 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   // which smoother runs: the current kernel, or the previous generation on request (A/B measurements)
   launch_fn backward = nullptr;
   bool perm = bp_bd;
+  // the thread-per-block kernels keep 32-bit byte offsets inside a 16-system output row: trajectories longer than
+  // that (16 * (N+1) * n^2 * 8 >= 2^31, i.e. ~466,000 steps for n_state 6) run on the previous generation
+  const bool long_rows = 16.0 * (double)T1 * n * n * 8.0 >= p->row_limit;
   if (vl) {
+    if (long_rows) return fail(RODEO_E_UNSUPPORTED, "compact variance layouts: n_eval is too large for the thread-per-block kernels");
     backward = ks->backward_vl[p->var_layout - 1][bk == BK_BOTH ? 1 : 0];
     perm = true;
   } else if (!bp && !shared && !wide) {
-    const bool alt = prefer_staged_backward() && ks->backward_alt[slot][bk];
+    const bool alt = (prefer_staged_backward() || (long_rows && ks->backward_perm[slot][bk])) && ks->backward_alt[slot][bk];
     backward = alt ? ks->backward_alt[slot][bk] : ks->backward[slot][bk];
     perm = !alt && ks->backward_perm[slot][bk];
   }
@@ -604,6 +609,7 @@ int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, co
   bool bd = false;
   rc = batched_prior_is_blockdiag(p, bp, (long)batch, stream, &bd);
   if (rc) return rc;
+  if (16.0 * (double)(p->N + 1) * p->n * p->n * 8.0 >= p->row_limit) bd = false;   // 32-bit row offsets (see run_chunks)
   p->last_pp_bd = bd;
   if (!bd) {
     const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
@@ -765,6 +771,14 @@ int rodeo_cuda_debug_copy_history(rodeo_problem *p, void *dst_device, size_t byt
   if (!p || !dst_device) return fail(RODEO_E_INVALID, "null argument");
   if (bytes > p->ws_bytes) return fail(RODEO_E_INVALID, "more bytes than the workspace holds");
   CK(cudaMemcpyAsync(dst_device, p->ws, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream));
+  return RODEO_OK;
+}
+
+// Test hook: lower the output-row size above which the thread-per-block kernels hand over to the previous
+// generation (default 2^31 bytes), so that the hand-over can be exercised on ordinary problem sizes.
+int rodeo_cuda_debug_set_row_limit(rodeo_problem *p, double bytes) {
+  if (!p || !(bytes > 0.0) || bytes > 2147483648.0) return fail(RODEO_E_INVALID, "bad arguments");
+  p->row_limit = bytes;
   return RODEO_OK;
 }
 

@@ -54,6 +54,7 @@ SYMBOLS = [
     ("rodeo_cuda_loglik", _I, [_V, _I, _L, _V, _V, _V, _L, _V, ctypes.c_int32, _V, ctypes.c_int32,
                                _V, _D, _V, _V, _V]),
     ("rodeo_cuda_debug_copy_history", _I, [_V, _V, _Z, _V]),
+    ("rodeo_cuda_debug_set_row_limit", _I, [_V, _D]),
     ("rodeo_cuda_launch_count", _L, [_V]),
     ("rodeo_cuda_reset_launch_count", _I, [_V]),
     ("rodeo_cuda_last_kernel_ms", _I, [_V, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),

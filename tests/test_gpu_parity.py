@@ -994,3 +994,77 @@ def test_compact_variance_layouts(B, N):
     ks = wl.make_kode(w, shared_cov=True, var_layout="blocks")
     with pytest.raises(NotImplementedError):
         ks.solve_mv(x0d, theta=thd)
+
+
+def test_blocks_with_different_priors_and_offsets():
+    """Blocks that are NOT copies of each other (different sigma per variable, a non-zero mu_state): the
+    thread-per-block kernels take their per-lane prior path (BlockPrior<false>) instead of immediate constant-bank
+    operands.  FitzHugh-Nagumo (two blocks, granule stores) and Lorenz63 (three blocks, draw-only kernel), structured
+    and general arithmetic, against the oracle."""
+    from rodeo_legacy_b200 import ibm_init, indep_init
+    rng = np.random.default_rng(21)
+    for maker, B, sig, xtol in ((wl.fitz_batch, 700, [0.07, 0.31], 1e-9),
+                                (lambda B: wl.lorenz_batch(B, N=400, tmax=1.6), 90, [0.3, 0.5, 0.9], 1e-8)):
+        w, x0, theta = maker(B)
+        n, N = len(w["x0"]), w["N"]
+        nb = len(sig)
+        kin = indep_init(ibm_init((w["tmax"] - w["tmin"]) / N, [3] * nb, sig), [3] * nb)
+        w = dict(w, Q=kin["wgt_state"], R=kin["var_state"], c=1e-4 * rng.standard_normal(n))
+        z = np.asfortranarray(rng.standard_normal((n, N)))
+        ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, z, oracle.MODE_BOTH)
+        x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+        outs = []
+        for st in (True, False):
+            k = wl.make_kode(w, z_state=z, use_structure=st)
+            assert k.structured == st and k.kernel_family == ("blockdiag", "registers")
+            x, mu, var = k.solve(x0d, theta=thd)
+            xs = k.solve_sim(x0d, theta=thd)
+            assert int(k.status.abs().sum()) == 0 and torch.equal(xs, x)
+            assert traj_err(mu.cpu().numpy(), ref["mu"]).max() < 1e-9
+            assert traj_err(x.cpu().numpy(), ref["x"]).max() < xtol
+            assert np.abs(var.cpu().numpy() - ref["var"]).max() < 1e-9 * np.abs(ref["var"]).max()
+            outs.append((x, mu, var))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+
+
+def test_very_long_trajectories_fall_back_to_the_staged_smoother():
+    """The thread-per-block kernels keep 32-bit byte offsets inside a 16-system output row; beyond ~466,000 steps
+    (n_state 6) the previous-generation kernels take over.  (1) the hand-over itself, forced on an ordinary size
+    through the test hook: bit-identical outputs; (2) a 470,000-step solve: runs, clean status, and agrees with the
+    oracle as far as two FP64 codes can over such a horizon (the FitzHugh-Nagumo limit cycle is neutrally stable in
+    phase: 1e-5 after 470,000 steps, 1e-9 over the first 5,000)."""
+    w, x0, theta = wl.fitz_batch(300, seed=2)
+    z = np.asfortranarray(np.random.default_rng(4).standard_normal((6, 400)))
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    k, kf = wl.make_kode(w, z_state=z), wl.make_kode(w, z_state=z)
+    _lib_check(_lib_load().rodeo_cuda_debug_set_row_limit(kf._h, 1024.0))
+    for a, b in zip(k.solve(x0d, theta=thd), kf.solve(x0d, theta=thd)):
+        assert torch.equal(a, b)
+    N = 470000
+    w = wl.fitz(N=400)
+    w = dict(w, N=N, tmax=w["tmax"] * N / 400)
+    from rodeo_legacy_b200 import ibm_init, indep_init
+    kin = indep_init(ibm_init(w["tmax"] / N, [3, 3], [0.1, 0.1]), [3, 3])
+    w.update(Q=kin["wgt_state"], R=kin["var_state"], c=kin["mu_state"])
+    B = 3
+    x0 = np.tile(w["x0"], (B, 1))
+    theta = w["theta0"] * np.exp(0.05 * np.random.default_rng(1).standard_normal((B, 3)))
+    kl = wl.make_kode(w)
+    mu, var = kl.solve_mv(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda())
+    ref = oracle.solve_batch(wl.make_oracle_problem(w), x0, theta, None, oracle.MODE_MV)
+    assert int(kl.status.abs().sum()) == 0 and bool(torch.isfinite(mu).all())
+    mu = mu.cpu().numpy()
+    assert traj_err(mu[:, :5001], ref["mu"][:, :5001]).max() < 1e-8      # measured 1.1e-9
+    assert traj_err(mu, ref["mu"]).max() < 1e-3                        # measured 1.0e-5
+    # the covariance recursion of the probde interrogation (measurement variance = W Sigma_p W^T, a function of the
+    # state covariance itself) drifts apart slowly between two FP64 codes: 1.4e-5 of the largest entry after
+    # 470,000 steps, FP64 rounding over the first 5,000
+    got, want = var.cpu().numpy(), ref["var"]
+    assert np.abs(got[:, 1:5001] - want[:, 1:5001]).max() < 1e-9 * np.abs(want).max()
+    assert np.abs(got[:, 1:] - want[:, 1:]).max() < 1e-4 * np.abs(want).max()
+
+
+def _lib_check(rc):
+    from rodeo_legacy_b200.cuda import _lib
+    _lib.check(rc)
