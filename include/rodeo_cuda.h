@@ -175,7 +175,7 @@ int rodeo_cuda_get_shared_cov(const rodeo_problem *p);
  *   RODEO_VAR_BLOCKS  var_out (B, n_eval+1, n_meas, p, p): the diagonal blocks only, block a = Sigma[a*p:(a+1)*p, a*p:(a+1)*p]
  *   RODEO_VAR_DIAG    var_out (B, n_eval+1, n_state): the marginal variances only
  * Same numbers as the corresponding entries of the full output, bit for bit.  Available for block-diagonal priors
- * with two blocks (the thread-per-block kernels) in general mode; RODEO_E_UNSUPPORTED otherwise.  It applies to
+ * with at least two blocks in general mode; RODEO_E_UNSUPPORTED otherwise (dense priors, single-block priors).  It applies to
  * rodeo_cuda_solve / rodeo_cuda_solve_host (not to the batched-prior entry point, nor to shared-covariance mode). */
 enum { RODEO_VAR_FULL = 0, RODEO_VAR_BLOCKS = 1, RODEO_VAR_DIAG = 2 };
 int rodeo_cuda_set_var_layout(rodeo_problem *p, int layout);

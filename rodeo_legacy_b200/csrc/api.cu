@@ -269,10 +269,10 @@ int rodeo_cuda_set_var_layout(rodeo_problem *p, int layout) {
   if (!p) return fail(RODEO_E_INVALID, "null problem");
   if (layout != RODEO_VAR_FULL && layout != RODEO_VAR_BLOCKS && layout != RODEO_VAR_DIAG)
     return fail(RODEO_E_INVALID, "unknown variance layout");
-  if (layout != RODEO_VAR_FULL && (!p->ks->backward_vl[layout - 1][0] || p->ig != RODEO_INTERROGATE_PROBDE))
+  if (layout != RODEO_VAR_FULL && (!p->ks->backward_vl[layout - 1][0] ||
+                                   (p->ks->vl_ck > 1 && p->ig != RODEO_INTERROGATE_PROBDE)))
     return fail(RODEO_E_UNSUPPORTED,
-                "compact variance layouts need a block-diagonal prior with two blocks (the thread-per-block "
-                "kernels) and the probde interrogation");
+                "compact variance layouts need a block-diagonal prior with at least two blocks");
   p->var_layout = layout;
   return RODEO_OK;
 }
@@ -424,7 +424,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   const bool vl = p->var_layout != RODEO_VAR_FULL && !bp && (bk == BK_MV || bk == BK_BOTH);
   if (vl && (p->shared || !p->ks->backward_vl[p->var_layout - 1][0]))
     return fail(RODEO_E_UNSUPPORTED, "the variance layout is not available in this mode (shared covariance / kernel family)");
-  const int ck = vl ? 2 : bp ? (bp_bd ? 2 : 1) : effective_ck(p, bk), slot = ck_slot(ck);
+  const int ck = vl ? p->ks->vl_ck : bp ? (bp_bd ? 2 : 1) : effective_ck(p, bk), slot = ck_slot(ck);
   const int vw = (bp || p->shared) ? n * n : var_width(p);
   const bool wide_pp = bp && !bp_bd && ks->wide_pp_forward != nullptr;   // dense wide-state kernels, per-system priors
   // history bytes per system of THIS entry point (rodeo_cuda_history_bytes_per_system is the largest over them)
@@ -451,9 +451,10 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   // that (16 * (N+1) * n^2 * 8 >= 2^31, i.e. ~466,000 steps for n_state 6) run on the previous generation
   const bool long_rows = 16.0 * (double)T1 * n * n * 8.0 >= p->row_limit;
   if (vl) {
-    if (long_rows) return fail(RODEO_E_UNSUPPORTED, "compact variance layouts: n_eval is too large for the thread-per-block kernels");
+    if (long_rows && ks->vl_perm)
+      return fail(RODEO_E_UNSUPPORTED, "compact variance layouts: n_eval is too large for the thread-per-block kernels");
     backward = ks->backward_vl[p->var_layout - 1][bk == BK_BOTH ? 1 : 0];
-    perm = true;
+    perm = ks->vl_perm;
   } else if (!bp && !shared && !wide) {
     const bool alt = (prefer_staged_backward() || (long_rows && ks->backward_perm[slot][bk])) && ks->backward_alt[slot][bk];
     backward = alt ? ks->backward_alt[slot][bk] : ks->backward[slot][bk];

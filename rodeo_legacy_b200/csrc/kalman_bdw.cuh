@@ -159,7 +159,22 @@ __device__ __forceinline__ void bdw_emit_var(const double *vt, const BdwRunPlan<
   }
 }
 
-template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+// Compact variance layouts (rodeo_cuda_set_var_layout): VL = 1 the n_meas diagonal (p, p) blocks -- exactly a row of
+// the CTA tile -- VL = 2 the marginal variances.  The warps share out the systems as in bdw_emit_var and write whole
+// runs of WV doubles (MSEIR: 45 or 15 instead of 225).
+template <class L, int VL>
+__device__ __forceinline__ void bdw_emit_var_compact(const double *vt, double *var_out, long b0, long B, long T1, int t,
+                                                     int blk, int lane) {
+  constexpr int p = L::p, nb = L::nb, WV = VL == 1 ? nb * p * p : nb * p;
+  const int rows = (int)(B - b0 < kTile ? B - b0 : kTile);
+  for (int s = blk; s < rows; s += nb) {
+    double *run = var_out + ((b0 + s) * T1 + t) * (long)WV;
+    const double *src = vt + s * BdwRunPlan<L>::ROWW;
+    for (int e = lane; e < WV; e += 32) run[e] = VL == 1 ? src[e] : src[(e / p) * p * p + (e % p) * (p + 1)];
+  }
+}
+
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, int VL = 0>
 __global__ void __launch_bounds__(BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::THREADS,
                                   BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>::MINB)
 kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid_constant__ SolveArgs a) {
@@ -241,7 +256,8 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
       __syncthreads();
       if (DO_MEAN) rm.store(t, tid);      // the 4-step blocks that became complete at this step
       if (DO_SIM) rx.store(t, tid);
-      bdw_emit_var<Fam, L>(vtile, vplan, a.var_out, b0, a.B, T1, t, blk, lane);
+      if constexpr (VL == 0) bdw_emit_var<Fam, L>(vtile, vplan, a.var_out, b0, a.B, T1, t, blk, lane);
+      else bdw_emit_var_compact<L, VL>(vtile, a.var_out, b0, a.B, T1, t, blk, lane);
     } else {
       constexpr int TW = L::TW, NT = L::THREADS;
       double *row = tiles + lane * TW;
@@ -265,10 +281,10 @@ kalman_backward_bdw(const __grid_constant__ typename Fam::PriorT P, const __grid
 
 namespace rodeo {
 
-template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM>
+template <class Fam, bool DO_MEAN, bool DO_VAR, bool DO_SIM, int VL = 0>
 cudaError_t launch_backward_bdw(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
   using L = BdwLayout<Fam, DO_MEAN, DO_VAR, DO_SIM>;
-  auto kern = kalman_backward_bdw<Fam, DO_MEAN, DO_VAR, DO_SIM>;
+  auto kern = kalman_backward_bdw<Fam, DO_MEAN, DO_VAR, DO_SIM, VL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes);
   if (e != cudaSuccess) return e;
   const unsigned grid = (unsigned)((a.B + kTile - 1) / kTile);

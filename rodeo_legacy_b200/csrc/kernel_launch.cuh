@@ -144,6 +144,12 @@ void fill_backward(KernelSet &k) {
         k.backward[CKI][BK_MV] = launch_backward_bdw<Fam, true, true, false>;
         k.backward[CKI][BK_BOTH] = launch_backward_bdw<Fam, true, true, true>;
         k.backward_alt[CKI][BK_SIM] = launch_backward_bdw<Fam, false, false, true>;
+        k.backward_vl[0][0] = launch_backward_bdw<Fam, true, true, false, 1>;   // compact variance layouts
+        k.backward_vl[0][1] = launch_backward_bdw<Fam, true, true, true, 1>;
+        k.backward_vl[1][0] = launch_backward_bdw<Fam, true, true, false, 2>;
+        k.backward_vl[1][1] = launch_backward_bdw<Fam, true, true, true, 2>;
+        k.vl_ck = 1;
+        k.vl_perm = false;
       }
       k.backward[CKI][BK_SIM] = launch_backward_tpx<Fam, 1, RODEO_TPX_U>;
     } else if constexpr (CK == 2) {
@@ -171,6 +177,8 @@ void fill_backward(KernelSet &k) {
         k.backward_vl[0][1] = launch_backward_tpb<Fam, 2, true, 2, true>;
         k.backward_vl[1][0] = launch_backward_tpb<Fam, 2, true, 3, false>;
         k.backward_vl[1][1] = launch_backward_tpb<Fam, 2, true, 3, true>;
+        k.vl_ck = 2;
+        k.vl_perm = true;
       }
       // the round-1 smoother, kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
       k.backward_alt[CKI][BK_MV] = launch_backward_staged<Fam, CK, true, true, false>;
@@ -230,6 +238,8 @@ KernelSet make_kernel_set(const char *name) {
       k.backward_perm[c][b] = false;
     }
   k.backward_vl[0][0] = k.backward_vl[0][1] = k.backward_vl[1][0] = k.backward_vl[1][1] = nullptr;
+  k.vl_ck = 1;
+  k.vl_perm = false;
   fill_backward<Fam, Ode, BD, UNROLL, 1, 0>(k);
   if constexpr (UNROLL) {  // checkpointed history for the register families only
     fill_backward<Fam, Ode, BD, UNROLL, 2, 1>(k);

@@ -82,7 +82,11 @@ static void fill_sets() {
       }
     for (int a = 0; a < 2; a++)
       for (int b = 0; b < 2; b++)
-        if (!k.backward_vl[a][b]) k.backward_vl[a][b] = g->backward_vl[a][b];
+        if (!k.backward_vl[a][b]) {
+          k.backward_vl[a][b] = g->backward_vl[a][b];
+          k.vl_ck = g->vl_ck;
+          k.vl_perm = g->vl_perm;
+        }
     if (!k.pp_bd_forward) {
       k.pp_bd_forward = g->pp_bd_forward;
       for (int b = 0; b < BK_COUNT; b++) k.pp_bd_backward[b] = g->pp_bd_backward[b];

@@ -38,9 +38,11 @@ struct KernelSet {
   // the previous generation of a kernel where one is kept for A/B measurements (RODEO_CUDA_BACKWARD=staged)
   launch_fn backward_alt[kNumCk][BK_COUNT];
   bool backward_perm[kNumCk][BK_COUNT];
-  // compact variance layouts (rodeo_cuda_set_var_layout): [layout - 1][0 = solve_mv, 1 = solve], checkpoint 2,
-  // permuted history; nullptr when not compiled for this set
-  launch_fn backward_vl[2][2];  // backward[][] wants the history in the permuted order (SolveArgs::perm16)
+  // compact variance layouts (rodeo_cuda_set_var_layout): [layout - 1][0 = solve_mv, 1 = solve]; nullptr when not
+  // compiled for this set (two blocks: thread-per-block kernels; >= 3 blocks: warp-per-block kernels)
+  launch_fn backward_vl[2][2];
+  int vl_ck;                      // ... the checkpoint interval those launchers use, and whether they want the
+  bool vl_perm;                   //     permuted history order  // backward[][] wants the history in the permuted order (SolveArgs::perm16)
   int hist_elems;                 // doubles of history per system per step
   // shared-covariance mode (kalman_sc.cuh); all nullptr when not compiled for this set
   cudaError_t (*sc_tables)(const HostPrior &, int zero_H, double *tab, int *fail_out, cudaStream_t);

@@ -245,8 +245,8 @@ class KalmanODE:
     def var_layout(self):
         """Layout of the returned variance: ``"full"`` (default, the reference's (n, n) matrices), ``"blocks"``
         ((n_meas, p, p): the diagonal blocks only) or ``"diag"`` ((n,): marginal variances).  The compact layouts
-        are opt-in for block-diagonal priors with two blocks; they hold the same numbers as the corresponding
-        entries of the full output and cut the bytes written and copied to the host (FitzHugh-Nagumo solve_mv:
+        are opt-in for block-diagonal priors with at least two blocks; they hold the same numbers as the
+        corresponding entries of the full output and cut the bytes written and copied to the host (FitzHugh-Nagumo solve_mv:
         336 -> 192 / 96 bytes per system and step).  Not applied to ``priors=`` calls or shared-covariance mode."""
         return _VAR_LAYOUTS_INV[int(self._lib.rodeo_cuda_get_var_layout(self._h))]
 

@@ -985,12 +985,11 @@ def test_compact_variance_layouts(B, N):
     assert torch.equal(kf.solve_mv(x0d, theta=thd)[1], varf)
     with pytest.raises(ValueError):
         kf.var_layout = "upper"
-    # families without the thread-per-block kernels refuse instead of silently returning the full layout
-    wL, _, _ = wl.lorenz_batch(4, N=50, tmax=0.2)
-    with pytest.raises(NotImplementedError):
-        wl.make_kode(wL, var_layout="blocks")
+    # dense and single-block priors refuse instead of silently returning the full layout
     with pytest.raises(NotImplementedError):
         wl.make_kode(w, force_dense=True, var_layout="diag")
+    with pytest.raises(NotImplementedError):
+        wl.make_kode(wl.chkrebtii(50), var_layout="blocks")
     ks = wl.make_kode(w, shared_cov=True, var_layout="blocks")
     with pytest.raises(NotImplementedError):
         ks.solve_mv(x0d, theta=thd)
@@ -1068,3 +1067,27 @@ def test_very_long_trajectories_fall_back_to_the_staged_smoother():
 def _lib_check(rc):
     from rodeo_legacy_b200.cuda import _lib
     _lib.check(rc)
+
+
+@pytest.mark.parametrize("maker,B", [(lambda B: wl.lorenz_batch(B, N=300, tmax=1.2), 75), (lambda B: wl.mseir_batch(B, N=120), 41)])
+def test_compact_variance_layouts_three_or_more_blocks(maker, B):
+    """var_layout on the warp-per-block kernels (Lorenz63: 3 blocks, MSEIR: 5): the diagonal blocks / marginal
+    variances of the full output bit for bit, solve_mv and solve, device and host entry points."""
+    w, x0, theta = maker(B)
+    n, N = len(w["x0"]), w["N"]
+    nb, p = n // 3, 3
+    z = np.asfortranarray(np.random.default_rng(5).standard_normal((n, N)))
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    kf = wl.make_kode(w, z_state=z)
+    xf, muf, varf = kf.solve(x0d, theta=thd)
+    for lay in ("blocks", "diag"):
+        k = wl.make_kode(w, z_state=z, var_layout=lay)
+        want = (torch.stack([varf[..., a * p:(a + 1) * p, a * p:(a + 1) * p] for a in range(nb)], dim=-3)
+                if lay == "blocks" else torch.diagonal(varf, dim1=-2, dim2=-1)).contiguous()
+        mu, var = k.solve_mv(x0d, theta=thd)
+        assert var.shape == ((B, N + 1, nb, p, p) if lay == "blocks" else (B, N + 1, n))
+        assert torch.equal(mu, muf) and torch.equal(var, want)
+        x, mu2, var2 = k.solve(x0d, theta=thd)
+        assert torch.equal(x, xf) and torch.equal(mu2, muf) and torch.equal(var2, want)
+        muh, varh = k.solve_mv(x0, theta=theta)
+        np.testing.assert_array_equal(varh, want.cpu().numpy())
