@@ -197,7 +197,9 @@ struct TpbLayout {
   // The kernel is HBM-bound and runs best with FEWER resident warps (measured, FN solve_mv, 65,536 systems:
   // 12 warps per SM 2.05 ms, 10: 2.00, 8: 1.99, 6: 1.98, 4: 2.40): with 4,096 equal-length warps the last,
   // partially filled wave is a smaller share of the launch.  Requesting 55 KB per CTA caps it at 4 CTAs = 8 warps.
-  static constexpr size_t smem_bytes = smem_need > 55 * 1024 ? smem_need : 55 * 1024;
+  // Only the variants that write the full variance are HBM-bound; the draw-only and compact-layout variants are
+  // latency / FP64-bound and take every warp the registers allow.
+  static constexpr size_t smem_bytes = (DO_VAR == 1 && smem_need < 55 * 1024) ? 55 * 1024 : smem_need;
 };
 
 // The prior of the lane's block: immediate constant-bank operands when every block has the same Q, R, w, c

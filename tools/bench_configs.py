@@ -46,7 +46,7 @@ def main():
         w, x0, theta = maker(B)
         n = len(w["x0"])
         z = None
-        if mode != "mv":
+        if mode not in ("mv", "mv_pp"):
             np.random.seed(2)
             z = np.asfortranarray(np.random.randn(n, w["N"]))
         k = wl.make_kode(w, z_state=z, checkpoint=a.checkpoint, force_dense=a.dense)
@@ -56,6 +56,8 @@ def main():
             fn = lambda: k.solve_mv(x0d, theta=thd)
         elif mode == "sim":
             fn = lambda: k.solve_sim(x0d, theta=thd)
+        elif mode == "both":
+            fn = lambda: k.solve(x0d, theta=thd)
         elif mode == "mv_pp":       # every system its own var_state (a sweep over the prior scale sigma)
             scale = torch.linspace(0.5, 2.0, B, dtype=torch.float64, device="cuda")
             Rb = torch.from_numpy(np.ascontiguousarray(w["R"])).cuda()[None] * scale[:, None, None] ** 2
@@ -82,6 +84,9 @@ def main():
         ("C4 mseir solve_mv", wl.mseir_batch, 32768, "mv", hist(15) + 8 * (15 + 225)),
         ("C5 fitz loglik (per GPU of 8)", wl.fitz_batch, 131072, "ll", hist(6)),
         ("C2pp fitz solve_mv, per-system var_state", wl.fitz_batch, 65536, "mv_pp", hist(6) + 8 * (6 + 36)),
+        ("C2sim fitz solve_sim", wl.fitz_batch, 65536, "sim", hist(6) + 8 * 6),
+        ("C2both fitz solve", wl.fitz_batch, 65536, "both", hist(6) + 8 * (12 + 36)),
+        ("C4sim mseir solve_sim", wl.mseir_batch, 32768, "sim", hist(15) + 8 * 15),
     ]
     for c in cfgs:
         if sel is None or any(s in c[0] for s in sel):
