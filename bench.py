@@ -242,6 +242,36 @@ def bind_near_gpu(index):
         return f"unbound ({type(e).__name__})"
 
 
+_HOST_KEEP = []
+
+
+def host_buffer(torch, shape, mode="pinned"):
+    """float64 host tensor for the e2e leg: "pinned" = cudaHostAlloc through torch; "thp" = anonymous mmap with
+    MADV_HUGEPAGE, touched, then cudaHostRegister'ed (2 MB pages: 512x fewer IOMMU / TLB entries for the DMA engines
+    than 4 KB pages when several GPUs copy into tens of GB of host memory at once)."""
+    import numpy as np
+    if mode == "pinned":
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    import mmap
+    n = int(np.prod(shape)) * 8
+    huge = 2 << 20
+    m = mmap.mmap(-1, n + huge)
+    try:
+        m.madvise(mmap.MADV_HUGEPAGE)
+    except Exception:
+        pass
+    raw = np.frombuffer(m, dtype=np.uint8)
+    off = (-raw.ctypes.data) % huge
+    arr = raw[off:off + n].view(np.float64).reshape(shape)
+    arr[...] = 0.0                                   # fault the pages in (as huge pages where the kernel allows)
+    t = torch.from_numpy(arr)
+    rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n, 0)
+    if int(rc) != 0:
+        raise RuntimeError(f"cudaHostRegister failed: {rc}")
+    _HOST_KEEP.append((m, t))
+    return t
+
+
 def copy_probe(torch, nbytes=1 << 30, reps=3):
     """H2D / D2H GB/s of this rank between pinned host memory and its GPU (best of `reps`), all ranks at once."""
     host = torch.empty(nbytes // 8, dtype=torch.float64, pin_memory=True)
@@ -269,6 +299,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-host", default="pinned", choices=["pinned", "thp"],
+                    help="host buffers of the e2e leg: cudaHostAlloc, or huge-page mmap + cudaHostRegister")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -372,7 +404,8 @@ def main():
         x0p, thp = pin(Be, N_STATE), pin(Be, 3)
         x0p.copy_(torch.from_numpy(x0[:Be]))
         thp.copy_(torch.from_numpy(theta[:Be]))
-        mup, varp = pin(Be, N_EVAL + 1, N_STATE), pin(Be, N_EVAL + 1, N_STATE, N_STATE)
+        mup = host_buffer(torch, (Be, N_EVAL + 1, N_STATE), args.e2e_host)
+        varp = host_buffer(torch, (Be, N_EVAL + 1, N_STATE, N_STATE), args.e2e_host)
         x0n, thn, mun, varn = x0p.numpy(), thp.numpy(), mup.numpy(), varp.numpy()
         k.solve_mv_into(x0n, thn, mun, varn)           # warm-up (allocates staging buffers)
         barrier()
@@ -385,7 +418,8 @@ def main():
                "h2d_bytes_per_step": Be * (N_STATE + 3) * 8,
                "d2h_bytes_per_step": out_bytes + Be * 4,
                "batch_per_gpu": Be, "steps": args.e2e_steps, "ms_per_step": 1e3 * el / args.e2e_steps,
-               "host_buffers": "pinned", "cpu_binding": binding,
+               "host_buffers": "pinned (cudaHostAlloc)" if args.e2e_host == "pinned" else
+                               "2 MB transparent huge pages, cudaHostRegister", "cpu_binding": binding,
                "copy_probe_GBps": {"h2d_min_over_ranks": min_over_ranks(probe["h2d"]),
                                    "d2h_min_over_ranks": min_over_ranks(probe["d2h"]),
                                    "d2h_sum_over_ranks": None, "note": "1 GiB pinned <-> device, all ranks at once"},
