@@ -207,7 +207,8 @@ int rodeo_cuda_problem_set(rodeo_problem *p, int field, const double *v) {
   p->tab_valid = false;          // the covariance tables depend on Q, R, W
   int rc = select_kernel_set(p); // the structure (hence the kernel family) may have changed
   if (rc == RODEO_OK && p->shared && !p->ks->sc_forward) p->shared = false;
-  if (rc == RODEO_OK && p->var_layout && !p->ks->backward_vl[p->var_layout - 1][0]) p->var_layout = RODEO_VAR_FULL;
+  // (a compact variance layout stays selected: if the new prior has no kernel for it, the next solve fails with
+  // RODEO_E_UNSUPPORTED instead of silently returning another layout)
   return rc;
 }
 

@@ -40,7 +40,6 @@
 namespace rodeo {
 
 constexpr int kGranule = 256;
-constexpr int kSlotBytes = 16 * kGranule;     // one granule of 16 systems
 constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
 
 // Tensor map of one output array for the granule stores: W doubles per (system, time index).
@@ -187,12 +186,8 @@ struct TpbLayout {
 #ifndef RODEO_TPB_WARPS
 #define RODEO_TPB_WARPS 2
 #endif
-#ifndef RODEO_TPB_MINB
-#define RODEO_TPB_MINB 1
-#endif
   static constexpr int WARPS = RODEO_TPB_WARPS;
   static constexpr int THREADS = WARPS * 32;
-  static constexpr int MINB = RODEO_TPB_MINB;
   static constexpr size_t smem_need = (size_t)WARPS * WARP_BYTES + 1024;       // + alignment slack (1024-byte swizzle atoms)
   // The kernel is HBM-bound and runs best with FEWER resident warps (measured, FN solve_mv, 65,536 systems:
   // 12 warps per SM 2.05 ms, 10: 2.00, 8: 1.99, 6: 1.98, 4: 2.40): with 4,096 equal-length warps the last,
