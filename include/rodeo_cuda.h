@@ -125,6 +125,19 @@ int rodeo_cuda_ode_n_theta(int ode);
  * diagonal with n_meas equal blocks and row a of wgt_meas lies inside block a -- what
  * ibm_init / car_init + indep_init + zero_pad always produce).  0: unsupported. */
 int rodeo_cuda_supported(int ode, int n_state, int n_meas, int interrogate);
+/* The same question for a list of block sizes (the reference's n_deriv_prior, one entry per ODE variable:
+ * rodeo/utils/utils.py:97-105, rodeo/ibm/ibm_init.py:54-58 accept any list).  Equal sizes answer like
+ * rodeo_cuda_supported; UNEQUAL sizes (e.g. [3, 4]) return 1 when a dense kernel set was compiled for exactly that
+ * list (csrc/kernels_mixed.cu), else 0.  A handle locates the variables from wgt_meas: when every row is a unit
+ * vector e_c (zero_pad), variable a's block starts at c - (order of the ODE); otherwise the reference functors'
+ * equal split n_state / n_meas is used (tests/eigen/ode_functions.pyx:33-42). */
+int rodeo_cuda_supported_blocks(int ode, int n_blocks, const int32_t *block_sizes, int interrogate);
+/* Enumerate every compiled kernel set, index 0 .. rodeo_cuda_kernel_set_count() - 1: right-hand side id, n_state,
+ * family (blockdiag / structured) and the block sizes it was compiled for (n_meas entries written to block_sizes;
+ * any out pointer may be NULL).  *name points at a static string such as "fitz/n7[3,4]". */
+int rodeo_cuda_kernel_set_count(void);
+int rodeo_cuda_kernel_set_info(int index, int32_t *ode, int32_t *n_state, int32_t *blockdiag, int32_t *structured,
+                               int32_t *block_sizes, const char **name);
 
 /* Creates a problem on the CURRENT CUDA device.  The descriptor's host arrays are copied. */
 int rodeo_cuda_problem_create(const rodeo_problem_desc *desc, rodeo_problem **out);

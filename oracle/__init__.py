@@ -89,7 +89,11 @@ class Problem:
     """The shared part of a batch of solves: prior (Q, c, R), W, grid and RHS name."""
 
     def __init__(self, ode, W, tmin, tmax, n_eval, wgt_state, mu_state, var_state,
-                 interrogate="probde"):
+                 interrogate="probde", block_sizes=None):
+        """block_sizes: the n_deriv_prior list when the blocks are UNEQUAL (the right-hand side then reads
+        variable k where its block starts); None = the reference functors' equal split."""
+        self.offsets = None if block_sizes is None else np.concatenate(
+            [[0], np.cumsum(block_sizes)[:-1]]).astype(np.int32)
         self.ode = ODE_IDS[ode]
         self.interrogate = INTERROGATE[interrogate]
         self.W = _f(W)
@@ -100,8 +104,17 @@ class Problem:
         assert self.Q.shape == (self.n, self.n) and self.R.shape == (self.n, self.n)
 
 
+def _set_offsets(prob):
+    off = getattr(prob, "offsets", None)
+    if off is None:
+        lib().oracle_set_var_offsets(None, ctypes.c_int(0))
+    else:
+        lib().oracle_set_var_offsets(off.ctypes.data_as(_ip), ctypes.c_int(len(off)))
+
+
 def solve(prob, x0, theta=None, z=None, mode=MODE_MV, return_hist=False):
     """One solve.  z is (n, N) as the reference's z_state.  Returns dict."""
+    _set_offsets(prob)
     n, N = prob.n, prob.N
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     theta = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
@@ -131,6 +144,7 @@ def solve(prob, x0, theta=None, z=None, mode=MODE_MV, return_hist=False):
 
 def solve_batch(prob, x0, theta=None, z=None, mode=MODE_MV, nthreads=0):
     """Batch of solves, OpenMP over systems.  x0 (B,n); theta (B,k); z (n,N) or (B,n,N)."""
+    _set_offsets(prob)
     n, N = prob.n, prob.N
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     B = x0.shape[0]
@@ -163,6 +177,7 @@ def solve_batch(prob, x0, theta=None, z=None, mode=MODE_MV, nthreads=0):
 def filter_step(prob, t, mu_filt, var_filt, theta=None):
     """One filter step t -> t+1 (probde) from given filtered moments; var (n, n) symmetric.
     Returns (mu_filt, var_filt) at time index t+1."""
+    _set_offsets(prob)
     n = prob.n
     mu_in = np.ascontiguousarray(mu_filt, dtype=np.float64)
     var_in = _f(var_filt)
@@ -183,6 +198,7 @@ def max_threads():
 def ode_eval(ode, X, t, theta):
     X = np.ascontiguousarray(X, dtype=np.float64)
     th = None if theta is None else np.ascontiguousarray(theta, dtype=np.float64)
+    lib().oracle_set_var_offsets(None, ctypes.c_int(0))
     m = lib().oracle_ode_n_meas(ctypes.c_int(ODE_IDS[ode]))
     out = np.zeros(m)
     lib().oracle_ode_eval(ctypes.c_int(ODE_IDS[ode]), _p(X), ctypes.c_int(len(X)),

@@ -37,6 +37,8 @@ struct rodeo_problem {
   double tmin, tmax;
   std::vector<double> W, Q, c, R;  // column-major host copies
   const KernelSet *ks;
+  bool mixed = false;              // unequal block sizes: wgt_meas places the variables at off[] (a "mixed" dense set)
+  int off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int flags = 0;
   int *bd_flag_dev = nullptr;      // device flag of the batched-prior structure check
   bool last_pp_bd = false;         // the last batched-prior solve ran on the block-diagonal kernels
@@ -96,9 +98,55 @@ static bool is_structured(const rodeo_problem *p) {
   return true;
 }
 
+// Where wgt_meas puts the ODE variables: when every row a is a unit vector e_c (what zero_pad produces,
+// rodeo/utils/utils.py:84-105), variable a's block starts at c - order.  False when W is not of that form (a general
+// measurement matrix: the right-hand side then reads the reference's equal split, tests/eigen/ode_functions.pyx:33-42).
+static bool offsets_from_wgt_meas(const rodeo_problem *p, int *off) {
+  const int n = p->n, m = p->m, ord = ode_order(p->ode);
+  if (m > 8) return false;
+  for (int a = 0; a < m; a++) {
+    int col = -1;
+    for (int j = 0; j < n; j++) {
+      const double w = p->W[a + (size_t)j * m];
+      if (w == 0.0) continue;
+      if (w != 1.0 || col >= 0) return false;
+      col = j;
+    }
+    if (col < ord) return false;
+    off[a] = col - ord;
+    if (a == 0 ? off[0] != 0 : off[a] <= off[a - 1]) return false;
+  }
+  return true;
+}
+
+// the dense kernel set that serves this problem's shape (per-system priors, forced-dense runs)
+static const KernelSet *dense_set(const rodeo_problem *p) {
+  return p->mixed ? find_kernel_set(p->ode, p->n, false, false, p->off) : find_kernel_set(p->ode, p->n, false);
+}
+
 // Pick the kernel family for the current (Q, R, W): block-diagonal when the structure is
 // there (and not disabled by RODEO_FLAG_FORCE_DENSE), dense otherwise.
 static int select_kernel_set(rodeo_problem *p) {
+  int off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool equal = true;
+  if (offsets_from_wgt_meas(p, off)) {
+    for (int a = 0; a < p->m; a++) equal = equal && p->n % p->m == 0 && off[a] == a * (p->n / p->m);
+  } else if (p->n % p->m) {
+    return fail(RODEO_E_UNSUPPORTED, "no compiled kernel: n_state is not a multiple of n_meas and wgt_meas does not "
+                                     "locate the variables (its rows must be unit vectors, as zero_pad builds them)");
+  }
+  p->mixed = !equal;
+  for (int a = 0; a < 8; a++) p->off[a] = equal ? 0 : off[a];
+  if (p->mixed) {   // unequal block sizes: a dense set compiled for exactly these variable offsets
+    p->ks = dense_set(p);
+    if (p->ks) return RODEO_OK;
+    char buf[320], sz[96] = "";
+    for (int a = 0, len = 0; a < p->m; a++)
+      len += snprintf(sz + len, sizeof sz - len, "%s%d", a ? ", " : "", (a + 1 < p->m ? off[a + 1] : p->n) - off[a]);
+    snprintf(buf, sizeof buf, "no compiled kernel for ode=%d with block sizes [%s] (n_state=%d); compiled shapes: "
+             "rodeo_cuda_kernel_set_info, adding one: INTEGRATION.md section 4.1", p->ode, sz, p->n);
+    return fail(RODEO_E_UNSUPPORTED, buf);
+  }
   const KernelSet *dense = find_kernel_set(p->ode, p->n, false), *bd = find_kernel_set(p->ode, p->n, true);
   const bool structured = is_block_diagonal(p);
   const KernelSet *ks = nullptr;
@@ -132,6 +180,39 @@ int rodeo_cuda_supported(int ode, int n_state, int n_meas, int interrogate) {
   if (interrogate < 0 || interrogate > 2) return 0;
   const KernelSet *d = find_kernel_set(ode, n_state, false), *b = find_kernel_set(ode, n_state, true);
   return ((d && d->m == n_meas) ? 1 : 0) | ((b && b->m == n_meas) ? 2 : 0);
+}
+
+// The same question for a list of block sizes (n_deriv_prior): equal sizes answer like rodeo_cuda_supported,
+// unequal sizes 1 when a dense set was compiled for exactly that list, else 0.
+int rodeo_cuda_supported_blocks(int ode, int n_blocks, const int32_t *block_sizes, int interrogate) {
+  if (!block_sizes || n_blocks <= 0 || n_blocks > 8 || n_blocks != ode_n_meas(ode)) return 0;
+  int off[8], n = 0;
+  bool equal = true;
+  for (int a = 0; a < n_blocks; a++) {
+    if (block_sizes[a] <= 0) return 0;
+    off[a] = n;
+    n += block_sizes[a];
+    equal = equal && block_sizes[a] == block_sizes[0];
+  }
+  if (equal) return rodeo_cuda_supported(ode, n, n_blocks, interrogate);
+  if (interrogate < 0 || interrogate > 2) return 0;
+  return find_kernel_set(ode, n, false, false, off) ? 1 : 0;
+}
+
+// Enumerate the compiled kernel sets: index 0 .. rodeo_cuda_kernel_set_count() - 1.  block_sizes gets n_meas entries.
+int rodeo_cuda_kernel_set_count(void) { return kernel_set_count(); }
+int rodeo_cuda_kernel_set_info(int index, int32_t *ode, int32_t *n_state, int32_t *blockdiag, int32_t *structured,
+                               int32_t *block_sizes, const char **name) {
+  const KernelSet *k = kernel_set_at(index);
+  if (!k) return fail(RODEO_E_INVALID, "kernel set index out of range");
+  if (ode) *ode = k->ode;
+  if (n_state) *n_state = k->n;
+  if (blockdiag) *blockdiag = k->blockdiag;
+  if (structured) *structured = k->structured;
+  if (block_sizes)
+    for (int a = 0; a < k->m; a++) block_sizes[a] = (a + 1 < k->m ? k->off[a + 1] : k->n) - k->off[a];
+  if (name) *name = k->name;
+  return RODEO_OK;
 }
 
 int rodeo_cuda_problem_create(const rodeo_problem_desc *d, rodeo_problem **out) {
@@ -220,7 +301,8 @@ static int var_width(const rodeo_problem *p) {
 
 // dense wide-state kernels (kalman_dw.cuh) serve the plain solves of the sets that carry them
 static bool wide_path(const rodeo_problem *p) {
-  return p->ks->wide_hist_elems > 0 && !p->shared && p->ig != RODEO_INTERROGATE_CHKREBTII &&
+  static const bool off = getenv("RODEO_CUDA_NO_WIDE") != nullptr;   // A/B against the rolled kernels
+  return !off && p->ks->wide_hist_elems > 0 && !p->shared && p->ig != RODEO_INTERROGATE_CHKREBTII &&
          p->ks->wide_forward[p->ig] != nullptr;
 }
 
@@ -418,7 +500,7 @@ static int run_chunks(rodeo_problem *p, BackwardKind bk, long batch, const doubl
   const long T1 = (long)p->N + 1;
   // per-system priors: block-diagonal thread-per-block kernels (checkpoint 2, permuted history) when every
   // system's prior has the structure (bp_bd), else the dense family with the full history; never shared-covariance
-  const KernelSet *ks = (bp && !bp_bd) ? find_kernel_set(p->ode, p->n, false) : p->ks;
+  const KernelSet *ks = (bp && !bp_bd) ? dense_set(p) : p->ks;
   const bool shared = p->shared && !bp;
   const bool wide = !bp && wide_path(p) && p->ks->wide_backward[bk] != nullptr;
   // a compact variance layout runs on its own kernels (checkpoint 2) for solve_mv / solve
@@ -614,7 +696,7 @@ int rodeo_cuda_solve_batched_prior(rodeo_problem *p, int mode, int64_t batch, co
   if (16.0 * (double)(p->N + 1) * p->n * p->n * 8.0 >= p->row_limit) bd = false;   // 32-bit row offsets (see run_chunks)
   p->last_pp_bd = bd;
   if (!bd) {
-    const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
+    const KernelSet *dense = dense_set(p);
     if (!dense || !dense->pp_forward)
       return fail(RODEO_E_UNSUPPORTED, "per-system priors that are not block diagonal need a dense kernel set");
   }
@@ -641,7 +723,7 @@ int rodeo_cuda_loglik_batched_prior(rodeo_problem *p, int use_draw, int64_t batc
   if (!(gamma > 0.0)) return fail(RODEO_E_INVALID, "gamma must be positive");
   if (p->ig != RODEO_INTERROGATE_PROBDE)
     return fail(RODEO_E_UNSUPPORTED, "per-system priors need the probde interrogation");
-  const KernelSet *dense = find_kernel_set(p->ode, p->n, false);
+  const KernelSet *dense = dense_set(p);
   const BackwardKind bk = use_draw ? BK_LL_DRAW : BK_LL_MEAN;
   if (!dense || !dense->pp_forward || !(dense->wide_pp_forward ? dense->wide_pp_backward[bk] : dense->pp_backward[bk]))
     return fail(RODEO_E_UNSUPPORTED, "log-likelihood with per-system priors needs a dense kernel set");

@@ -217,6 +217,9 @@ KernelSet make_kernel_set(const char *name) {
   using Fam = typename FamSel<UNROLL, BD, Ode, K, ST>::type;
   KernelSet k;
   k.structured = ST;
+  k.mixed = Ode::mixed;
+  static_assert(!(Ode::mixed && BD), "unequal block sizes run on the dense family");
+  for (int a = 0; a < 8; a++) k.off[a] = a < Ode::n_meas ? Ode::template var_off<Fam::n>(a) : 0;
   k.ode = Ode::id;
   k.n = Fam::n;
   k.m = Ode::n_meas;

@@ -9,7 +9,10 @@ static void attach(KernelSet *sets, int count) {
   using Fam = DwFam<Ode, n>;
   for (int i = 0; i < count; i++) {
     KernelSet &k = sets[i];
-    if (k.ode != Ode::id || k.n != n || k.blockdiag) continue;
+    if (k.ode != Ode::id || k.n != n || k.blockdiag || k.mixed != Ode::mixed) continue;
+    bool same = true;
+    for (int a = 0; a < Ode::n_meas; a++) same = same && k.off[a] == Ode::template var_off<n>(a);
+    if (!same) continue;
     k.wide_forward[IG_PROBDE] = launch_dw_forward<Fam, IG_PROBDE>;
     k.wide_forward[IG_SCHOBERT] = launch_dw_forward<Fam, IG_SCHOBERT>;
     k.wide_backward[BK_MV] = launch_dw_backward<Fam, true, true, false, false>;
@@ -32,6 +35,9 @@ void attach_wide(KernelSet *sets, int count) {
   attach<OdeLorenz63, 9>(sets, count);
   attach<OdeMseir, 10>(sets, count);
   attach<OdeMseir, 15>(sets, count);
+  attach<OdeAt<OdeFitz, 3, 4>, 7>(sets, count);       // unequal block sizes (kernels_mixed.cu)
+  attach<OdeAt<OdeFitz, 4, 3>, 7>(sets, count);
+  attach<OdeAt<OdeLorenz63, 2, 3, 3>, 8>(sets, count);
 }
 
 }  // namespace rodeo

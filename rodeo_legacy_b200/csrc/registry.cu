@@ -7,6 +7,7 @@ namespace rodeo {
 
 #define RODEO_REG(name) void register_##name(KernelSet *, int *);
 RODEO_REG(chkrebtii_dense) RODEO_REG(fitz_dense) RODEO_REG(lorenz_dense) RODEO_REG(mseir_dense)
+RODEO_REG(mixed)
 RODEO_REG(chkrebtii_bd_p3)
 RODEO_REG(chkrebtii_bd_p4)
 RODEO_REG(chkrebtii_bds_p3)
@@ -41,6 +42,7 @@ static void fill_sets() {
   register_fitz_dense(g_sets, &c);
   register_lorenz_dense(g_sets, &c);
   register_mseir_dense(g_sets, &c);
+  register_mixed(g_sets, &c);
   register_chkrebtii_bd_p3(g_sets, &c);
   register_chkrebtii_bd_p4(g_sets, &c);
   register_chkrebtii_bds_p3(g_sets, &c);
@@ -126,12 +128,19 @@ int ode_n_theta(int ode) {
   }
 }
 
-const KernelSet *find_kernel_set(int ode, int n, bool blockdiag, bool structured) {
+const KernelSet *find_kernel_set(int ode, int n, bool blockdiag, bool structured, const int *off) {
   init_sets();
-  for (int i = 0; i < g_count; i++)
-    if (g_sets[i].ode == ode && g_sets[i].n == n && g_sets[i].blockdiag == blockdiag &&
-        g_sets[i].structured == structured)
-      return &g_sets[i];
+  for (int i = 0; i < g_count; i++) {
+    const KernelSet &k = g_sets[i];
+    if (k.ode != ode || k.n != n || k.blockdiag != blockdiag || k.structured != structured) continue;
+    if (!off) {
+      if (!k.mixed) return &k;
+      continue;
+    }
+    bool same = true;
+    for (int a = 0; a < k.m; a++) same = same && k.off[a] == off[a];
+    if (same) return &k;
+  }
   return nullptr;
 }
 int kernel_set_count() {

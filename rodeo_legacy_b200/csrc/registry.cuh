@@ -31,6 +31,8 @@ struct KernelSet {
   bool blockdiag;                 // block-diagonal family (needs structured Q, R, W) or dense
   bool registers;                 // fully unrolled register kernels (else rolled / local memory)
   bool structured;                // block-diagonal family specialised for upper-triangular Q blocks and w = e_order
+  bool mixed;                     // dense set compiled for UNEQUAL block sizes (OdeAt, ode_functors.cuh): the
+  int off[8];                     //   right-hand side reads variable k at state index off[k] (equal split: k * n / m)
   const char *name;
   launch_fn forward[3];           // by interrogation variant
   launch_fn forward_perm[3];      // forward pass that writes the permuted history order (nullptr: forward[] honours perm16)
@@ -71,7 +73,8 @@ int ode_count();                 // registered right-hand sides: ids 0 .. ode_co
 int ode_n_meas(int ode);         // from the functors (ode_functors.cuh); -1 for an unknown id
 int ode_n_theta(int ode);
 int ode_order(int ode);          // order of the ODE: the derivative zero_pad's wgt_meas picks in every block
-const KernelSet *find_kernel_set(int ode, int n, bool blockdiag, bool structured = false);
+// off = nullptr: the equal-split sets; else the dense set compiled for exactly these variable offsets
+const KernelSet *find_kernel_set(int ode, int n, bool blockdiag, bool structured = false, const int *off = nullptr);
 int kernel_set_count();
 const KernelSet *kernel_set_at(int i);
 

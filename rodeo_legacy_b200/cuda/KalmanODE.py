@@ -43,6 +43,34 @@ def register_names():
     return sorted(ODE_FUNS)
 
 
+def compiled_shapes():
+    """Every kernel set compiled into the library: a list of dicts ``ode`` (name), ``n_state``, ``block_sizes``
+    (the ``n_deriv_prior`` it serves: one entry per ODE variable), ``family`` ("dense" takes any prior of that
+    shape, "blockdiag" / "structured" are chosen automatically for block-diagonal priors) and ``name``.  Works
+    without a GPU (rodeo_cuda_kernel_set_info)."""
+    lib = _lib.load()
+    names = {v: k for k, v in ODE_FUNS.items()}
+    out = []
+    for i in range(lib.rodeo_cuda_kernel_set_count()):
+        ode, n, bd, st = (ctypes.c_int32() for _ in range(4))
+        sizes = (ctypes.c_int32 * 8)()
+        name = ctypes.c_char_p()
+        _lib.check(lib.rodeo_cuda_kernel_set_info(i, ctypes.byref(ode), ctypes.byref(n), ctypes.byref(bd),
+                                                  ctypes.byref(st), sizes, ctypes.byref(name)))
+        m = lib.rodeo_cuda_ode_n_meas(ode.value)
+        out.append(dict(ode=names.get(ode.value, ode.value), n_state=n.value, block_sizes=list(sizes[:m]),
+                        family="structured" if st.value else "blockdiag" if bd.value else "dense",
+                        name=name.value.decode()))
+    return out
+
+
+def supports(ode_fun, n_deriv_prior, interrogate="probde"):
+    """True when a kernel set is compiled for this right-hand side and list of block sizes (equal or not)."""
+    sizes = (ctypes.c_int32 * len(n_deriv_prior))(*[int(v) for v in n_deriv_prior])
+    return _lib.load().rodeo_cuda_supported_blocks(_ode_id(ode_fun), len(n_deriv_prior), sizes,
+                                                   _INTERROGATE[interrogate]) != 0
+
+
 def _ode_id(ode_fun):
     name = getattr(ode_fun, "rodeo_cuda_name", ode_fun)
     if isinstance(name, str):

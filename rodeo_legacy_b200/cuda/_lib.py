@@ -30,6 +30,10 @@ SYMBOLS = [
     ("rodeo_cuda_ode_n_meas", _I, [_I]),
     ("rodeo_cuda_ode_n_theta", _I, [_I]),
     ("rodeo_cuda_supported", _I, [_I, _I, _I, _I]),
+    ("rodeo_cuda_supported_blocks", _I, [_I, _I, _V, _I]),
+    ("rodeo_cuda_kernel_set_count", _I, []),
+    ("rodeo_cuda_kernel_set_info", _I, [_I, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p,
+                                        ctypes.POINTER(ctypes.c_char_p)]),
     ("rodeo_cuda_problem_create", _I, [ctypes.POINTER(ProblemDesc), ctypes.POINTER(_V)]),
     ("rodeo_cuda_problem_destroy", _I, [_V]),
     ("rodeo_cuda_problem_set", _I, [_V, _I, _V]),

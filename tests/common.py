@@ -12,6 +12,12 @@ def load_golden(name):
         return {k: f[k] for k in f.files}
 
 
+def load_mixed(name):
+    """One case of tests/golden/mixed_blocks.npz (unequal block sizes; keys are `case__field`)."""
+    with np.load(os.path.join(GOLDEN, "mixed_blocks.npz")) as f:
+        return {k.split("__")[1]: f[k] for k in f.files if k.startswith(name + "__")}
+
+
 def traj_err(a, b, axis=-2):
     """Trajectory-scaled max error per state component:
     max_t |a - b| / max_t |b|, time on `axis` (default: second-to-last, i.e. arrays

@@ -52,6 +52,44 @@ def test_registry_and_error_strings_without_gpu():
     assert b"no compiled kernel" in lib.rodeo_cuda_last_error()
 
 
+def test_unequal_block_sizes_are_enumerated_without_gpu():
+    """n_deriv_prior lists with unequal entries (the reference accepts any list, rodeo/utils/utils.py:97-105):
+    served by dense sets compiled per list (csrc/kernels_mixed.cu), found from where wgt_meas puts the variables."""
+    import numpy as np
+    from rodeo_legacy_b200 import ibm_init, indep_init, zero_pad
+    from rodeo_legacy_b200.cuda import _lib, compiled_shapes, supports
+    lib = _lib.load()
+    shapes = compiled_shapes()
+    assert len(shapes) == lib.rodeo_cuda_kernel_set_count()
+    mixed = {(s["ode"], tuple(s["block_sizes"])) for s in shapes if len(set(s["block_sizes"])) > 1}
+    assert mixed == {("fitz", (2, 3)), ("fitz", (3, 4)), ("fitz", (4, 3)), ("lorenz63", (2, 3, 3))}
+    assert all(s["family"] == "dense" for s in shapes if len(set(s["block_sizes"])) > 1)
+    assert {"ode": "fitz", "n_state": 6, "block_sizes": [3, 3], "family": "structured", "name": "fitz/bds3"} in shapes \
+        or any(s["ode"] == "fitz" and s["block_sizes"] == [3, 3] and s["family"] == "structured" for s in shapes)
+    assert supports("fitz", [3, 4]) and supports("fitz", [4, 3]) and supports("lorenz63", [2, 3, 3])
+    assert supports("fitz", [3, 3]) and supports("mseir", [3] * 5)
+    assert not supports("fitz", [2, 5]) and not supports("lorenz63", [3, 4]) and not supports("fitz", [3, 0])
+
+    def create(n_prior, ode=1):
+        n_deriv = [1] * len(n_prior)
+        n = sum(n_prior)
+        Wm = np.zeros((len(n_prior), sum(n_deriv) + len(n_deriv)))
+        for i in range(len(n_deriv)):
+            Wm[i, 2 * i + 1] = 1
+        W = np.asfortranarray(zero_pad(Wm, n_deriv, n_prior))
+        k = indep_init(ibm_init(0.1, n_prior, [0.1] * len(n_prior)), n_prior)
+        Q, R, c = np.asfortranarray(k["wgt_state"]), np.asfortranarray(k["var_state"]), np.zeros(n)
+        d = _lib.ProblemDesc(n, len(n_prior), 10, ode, 0, 0, 0.0, 1.0, W.ctypes.data, Q.ctypes.data, c.ctypes.data,
+                             R.ctypes.data)
+        h = ctypes.c_void_p()
+        return lib.rodeo_cuda_problem_create(ctypes.byref(d), ctypes.byref(h)), lib.rodeo_cuda_last_error()
+
+    rc, err = create([2, 4])      # 6 = 2 * 3, but the variables are NOT at the equal split: no silent wrong answer
+    assert rc == -2 and b"block sizes [2, 4]" in err
+    rc, err = create([5, 2])
+    assert rc == -2 and b"block sizes [5, 2]" in err
+
+
 def test_front_end_fails_loudly_without_cuda():
     import torch
     from rodeo_legacy_b200.cuda import KalmanODE

@@ -1091,3 +1091,73 @@ def test_compact_variance_layouts_three_or_more_blocks(maker, B):
         assert torch.equal(x, xf) and torch.equal(mu2, muf) and torch.equal(var2, want)
         muh, varh = k.solve_mv(x0, theta=theta)
         np.testing.assert_array_equal(varh, want.cpu().numpy())
+
+
+@pytest.mark.parametrize("name,family", [("fitz_blocks_2_3", "registers"), ("fitz_blocks_3_4", "wide"),
+                                         ("fitz_blocks_4_3", "wide"), ("lorenz_blocks_2_3_3", "wide")])
+def test_unequal_block_sizes(name, family):
+    """n_deriv_prior with unequal entries (VERDICT r1 missing #2): the handle finds the variables from wgt_meas and
+    runs the dense set compiled for that list (csrc/kernels_mixed.cu).  Against the reference's Python path
+    (tests/golden/mixed_blocks.npz) and, on a seeded batch, the oracle with the same offsets."""
+    from tests.common import load_mixed
+    from rodeo_legacy_b200.cuda import supports
+    g = load_mixed(name)
+    sizes = [int(v) for v in g["block_sizes"]]
+    assert supports(ode_name(name), sizes)
+    k = _kode_from_golden(g, name, z_state=np.asfortranarray(g["z"]))
+    assert k.kernel_family == ("dense", family)
+    p4 = 4 in sizes
+    # a p = 4 IBM block: the draws of two FP64 codes agree to ~1e-5 only (cancellation in V~, DESIGN section 3)
+    mtol, vtol, xtol = (1e-9, 1e-8, 5e-5) if p4 else (1e-11, 1e-10, 1e-9)
+    B0 = len(g["theta"])
+    x, mu, var = k.solve(np.tile(g["x0"], (B0, 1)), theta=g["theta"])            # host path
+    assert traj_err(mu, g["mu"]).max() < mtol
+    assert var_err(var[:, 1:], g["var"][:, 1:]).max() < vtol
+    assert traj_err(x, g["x"]).max() < xtol
+    # a seeded batch (ragged: not a multiple of 32) through the device path, every system against the oracle
+    B = 203
+    rng = np.random.default_rng(21)
+    theta = g["theta"][0] * np.exp(0.05 * rng.standard_normal((B, g["theta"].shape[1])))
+    x0 = np.tile(g["x0"], (B, 1)) * (1 + 0.01 * rng.standard_normal((B, len(g["x0"]))))
+    po = oracle.Problem(ode_name(name), g["W"], float(g["tmin"]), float(g["tmax"]), int(g["N"]), g["Q"], g["c"],
+                        g["R"], block_sizes=sizes)
+    ref = oracle.solve_batch(po, x0, theta, g["z"], oracle.MODE_BOTH)
+    x0d, thd = torch.from_numpy(x0).cuda(), torch.from_numpy(theta).cuda()
+    xd, mud, vard = k.solve(x0d, theta=thd)
+    mu2, var2 = k.solve_mv(x0d, theta=thd)
+    x2 = k.solve_sim(x0d, theta=thd)
+    assert torch.equal(mud, mu2) and torch.equal(vard, var2) and torch.equal(xd, x2)
+    # GPU vs oracle: two FP64 codes on the same inputs (tighter than either against SciPy's Cholesky)
+    assert traj_err(mud.cpu().numpy(), ref["mu"]).max() < (1e-9 if p4 else 1e-11)
+    assert var_err(vard.cpu().numpy()[:, 1:], ref["var"][:, 1:]).max() < (1e-8 if p4 else 1e-10)
+    assert not k.status.any().item() and not ref["status"].any()
+    assert traj_err(xd.cpu().numpy(), ref["x"]).max() < (5e-5 if p4 else 1e-9)
+    # fused log-likelihood of the same family equals the density of the returned mean
+    n, N = len(g["x0"]), int(g["N"])
+    ind = np.arange(20, N + 1, 20)
+    comp = [0, sizes[0]]
+    Y = mud[0, ind][:, comp].cpu().numpy() + 0.05
+    got = k.loglik(x0d, thd, Y, ind, comp, 0.2).cpu().numpy()
+    tc = mud[:, ind][:, :, comp].cpu().numpy()
+    want = -Y.size * (np.log(0.2) + 0.5 * np.log(2 * np.pi)) - 0.5 * (((Y[None] - tc) / 0.2) ** 2).sum(axis=(1, 2))
+    assert np.abs(got - want).max() < 1e-9 * np.abs(want).max()
+    # per-system priors keep the offsets of the handle (dense family with a thread-private prior)
+    nb = 12
+    Rb = np.stack([np.asarray(g["R"]) * (1 + 0.1 * i) for i in range(nb)])
+    mup, varp = k.solve_mv(x0d[:nb], theta=thd[:nb], priors=dict(var_state=Rb))
+    for b in (0, 5, nb - 1):
+        pb = oracle.Problem(ode_name(name), g["W"], float(g["tmin"]), float(g["tmax"]), N, g["Q"], g["c"], Rb[b],
+                            block_sizes=sizes)
+        rb = oracle.solve(pb, x0[b], theta[b], None, oracle.MODE_MV)
+        assert traj_err(mup[b].cpu().numpy(), rb["mu"]).max() < (1e-9 if p4 else 1e-11)
+        assert var_err(varp[b].cpu().numpy()[1:], rb["var"][1:]).max() < (1e-8 if p4 else 1e-10)
+
+
+def test_unequal_block_sizes_without_a_compiled_set_fail_loudly():
+    from rodeo_legacy_b200 import ibm_init, indep_init, zero_pad
+    from rodeo_legacy_b200.cuda import KalmanODE, RodeoCudaError
+    n_prior = [2, 4]      # n_state 6 = 2 * 3, but the second variable sits at index 2, not 3
+    W = zero_pad(np.array([[0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]]), [1, 1], n_prior)
+    kinit = indep_init(ibm_init(0.1, n_prior, [0.1, 0.1]), n_prior)
+    with pytest.raises((RodeoCudaError, NotImplementedError), match="block sizes"):
+        KalmanODE(W, 0.0, 40.0, 400, "fitz", **kinit)

@@ -59,6 +59,28 @@ def test_fitz():
     np.testing.assert_array_equal(one["mu"], r["mu"][2])
 
 
+@pytest.mark.parametrize("name", ["fitz_blocks_3_4", "fitz_blocks_4_3", "fitz_blocks_2_3", "lorenz_blocks_2_3_3"])
+def test_unequal_block_sizes(name):
+    """n_deriv_prior with unequal entries (tests/golden/make_golden_mixed.py: the reference's Python path with a
+    right-hand side that reads variable k at the start of block k)."""
+    from tests.common import load_mixed
+    g = load_mixed(name)
+    p = oracle.Problem(ode_name(name), g["W"], float(g["tmin"]), float(g["tmax"]), int(g["N"]), g["Q"], g["c"],
+                       g["R"], block_sizes=g["block_sizes"])
+    B = len(g["theta"])
+    r = oracle.solve_batch(p, np.tile(g["x0"], (B, 1)), g["theta"], g["z"], oracle.MODE_BOTH)
+    assert not r["status"].any()
+    p4 = 4 in g["block_sizes"]          # the p = 4 IBM block: same conditioning as chkrebtii above
+    assert traj_err(r["mu"], g["mu"]).max() < (1e-9 if p4 else 1e-11)
+    assert traj_err(r["x"], g["x"]).max() < (1e-5 if p4 else 1e-9)
+    assert var_err(r["var"][:, 1:], g["var"][:, 1:]).max() < (1e-8 if p4 else 1e-10)
+    if name in ("fitz_blocks_4_3", "lorenz_blocks_2_3_3"):   # the equal split n // n_var reads another component
+        q = oracle.Problem(ode_name(name), g["W"], float(g["tmin"]), float(g["tmax"]), int(g["N"]), g["Q"], g["c"],
+                           g["R"])
+        bad = oracle.solve_batch(q, np.tile(g["x0"], (B, 1)), g["theta"], None, oracle.MODE_MV)
+        assert not (traj_err(bad["mu"], g["mu"]).max() < 1e-3)
+
+
 def test_lorenz_ibm():
     g = load_golden("lorenz_n5000")
     p = _prob(g, "lorenz_n5000")
