@@ -126,7 +126,18 @@ struct TpxLayout {
   // U = 1: 12 resident warps per SM (<= 170 registers) hold a whole 16,384-system Lorenz63 batch (11.1 warps per
   // SM) in ONE wave; at the 190 registers ptxas would take, 10 fit and the launch needs two
   static constexpr int MINB = U == 1 ? 6 : 1;
-  static constexpr size_t smem_bytes = (size_t)WARPS * U * SPW * SYS_BYTES;
+#ifndef RODEO_TPX_PLAIN
+#define RODEO_TPX_PLAIN 1
+#endif
+  // Output path.  kPlain: every step the lanes park their block's p draws in a per-warp shared-memory image
+  // [system][n] (double buffered: one warp barrier per step) and the warp writes it back with plain coalesced
+  // stores, consecutive lanes = consecutive doubles of a system's 8n-byte run.  The kernel is latency-bound, not
+  // HBM-bound (ncu: DRAM 41 %), and the per-system FIFOs + per-lane bulk copies of aligned granules cost more
+  // instructions (serialised UBLKCP issue loops, proxy fences, wait_group) than the partial sectors cost bandwidth.
+  static constexpr bool kPlain = RODEO_TPX_PLAIN != 0;
+  static constexpr int IMG = SPW * n;                       // doubles of one staging image
+  static constexpr int NST = (IMG + 31) / 32;               // store instructions per step
+  static constexpr size_t smem_bytes = kPlain ? (size_t)WARPS * U * 2 * IMG * 8 : (size_t)WARPS * U * SPW * SYS_BYTES;
   static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
 };
 
@@ -175,10 +186,47 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
   };
+  // (kPlain) staging images (shared-state addresses) and this lane's store offsets: double k * 32 + lane of an image =
+  // element el of system sy of the warp, stored at xw[(sy * T1 + t) * n + el]
+  const uint32_t img_base = smem_u32(smem_raw) + (uint32_t)(warp * U) * 2u * L::IMG * 8u;
+  const uint32_t img_wr = img_base + (uint32_t)(s * n + blk * p) * 8u, img_rd = img_base + (uint32_t)lane * 8u;
+  uint32_t img_par = 0;                                     // byte offset of the image in use (0 or IMG * 8)
+  double *const xw = a.x_out + b_first * T1 * n;            // warp-uniform
+  int ooff[U][L::NST];
+  bool ov[U][L::NST];
+#pragma unroll
+  for (int u = 0; u < U; u++)
+#pragma unroll
+    for (int k = 0; k < L::NST; k++) {
+      const int idx = k * 32 + lane, sy = idx / n, el = idx - sy * n;
+      ov[u][k] = L::kPlain && idx < L::IMG && b_first + u * SPW + sy < a.B;
+      ooff[u][k] = (int)((u * SPW + sy) * T1 * n) + el;
+    }
   // park the draws of time index t in the FIFOs; every EK steps (and at t = 0) store the granules they completed
   int since = 0;
   bool reads_pending = false;
   auto emit = [&](int t, double (*x)[p]) {
+    if constexpr (L::kPlain) {   // double buffered: the reads of the other image precede this step's barrier
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int e = 0; e < p; e++)
+          if (lane_on)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(img_wr + img_par + (uint32_t)((u * 2 * L::IMG + e) * 8)), "d"(x[u][e])
+                         : "memory");
+      __syncwarp();
+      const int tn = t * n;
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int k = 0; k < L::NST; k++) {
+          double v;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(img_rd + img_par + (uint32_t)((u * 2 * L::IMG + k * 32) * 8)) : "memory");
+          if (ov[u][k]) xw[ooff[u][k] + tn] = v;
+        }
+      img_par ^= (uint32_t)(L::IMG * 8);
+      return;
+    }
     if (reads_pending) {   // the bulk copies of the last emission round have left the FIFOs
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
@@ -294,7 +342,7 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < p; e++) x[u][e] = x0b[u][e];
   emit(0, x);
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if constexpr (!L::kPlain) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int u = 0; u < U; u++)
     if (valid[u] && a.status && fail[u]) atomicCAS(a.status + b[u], 0, blk * p + fail[u]);

@@ -118,20 +118,25 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32
                "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
                : "memory");
 }
-template <int W, int G>
+template <int W, int G, int SPLIT = 0>
 __device__ __forceinline__ void bulk_step(double *out, const double *src, long b, long B, int T1, int t, long &F) {
   if (b >= B) return;
   const long lo = (b * T1 + t) * (long)(W * 8);
   const long c = (t == 0) ? lo : (lo + G - 1) / G * G;
   if (c < F) {
-    bulk_s2g(reinterpret_cast<char *>(out) + c, src, (uint32_t)(F - c));   // <= G + run bytes, 16-byte multiple
+    if (SPLIT == 0) {
+      bulk_s2g(reinterpret_cast<char *>(out) + c, src, (uint32_t)(F - c));   // <= G + run bytes, 16-byte multiple
+    } else {   // the same bytes at the same moment, as back-to-back pieces of SPLIT bytes
+      for (long a = c; a < F; a += SPLIT)
+        bulk_s2g(reinterpret_cast<char *>(out) + a, src, (uint32_t)(F - a < SPLIT ? F - a : SPLIT));
+    }
     F = c;
   }
 }
-template <int G, bool VAR, bool MEAN, int WAITN = 1, int RD = 0>
+template <int G, bool VAR, bool MEAN, int WAITN = 1, int RD = 0, int SPLIT = 0, int GM = G>
 __global__ void __launch_bounds__(64) k_bulk(double *var, double *mu, long B, int T1, const double *hist = nullptr,
                                              double *sink = nullptr) {
-  constexpr int SRC = ((G + kWv * 8) / 8 + 15) / 16 * 16;      // one source image per warp (contents are irrelevant)
+  constexpr int SRC = (((G > GM ? G : GM) + kWv * 8) / 8 + 15) / 16 * 16;      // one source image per warp (contents are irrelevant)
   __shared__ __align__(128) double src_all[2][SRC];
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
   const long b = ((long)blockIdx.x * 2 + warp) * 32 + lane;
@@ -147,8 +152,8 @@ __global__ void __launch_bounds__(64) k_bulk(double *var, double *mu, long B, in
 #pragma unroll
       for (int e = 0; e < RD; e++) acc += __ldcs(h + ((long)(T1 - 1 - t) * RD + e) * 32);
     }
-    if (VAR) bulk_step<kWv, G>(var, src_w, b, B, T1, t, Fv);
-    if (MEAN) bulk_step<kWm, G>(mu, src_w, b, B, T1, t, Fm);
+    if (VAR) bulk_step<kWv, G, SPLIT>(var, src_w, b, B, T1, t, Fv);
+    if (MEAN) bulk_step<kWm, GM, 0>(mu, src_w, b, B, T1, t, Fm);
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     if (WAITN == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // at most two steps of copies in flight
@@ -283,6 +288,30 @@ int main() {
          [&] { k_bulk<256, true, true, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
   timeit("bulk512 var+mean + 72B/step read", bv + bm + bh,
          [&] { k_bulk<512, true, true, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk1024 var+mean + 72B/step read", bv + bm + bh,
+         [&] { k_bulk<1024, true, true, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk2048 var+mean + 72B/step read", bv + bm + bh,
+         [&] { k_bulk<2048, true, true, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("72B/step read only", bh, [&] { k_bulk<256, false, false, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk1024 var only + 72B/step read", bv + bh,
+         [&] { k_bulk<1024, true, false, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk256 var only + 72B/step read", bv + bh,
+         [&] { k_bulk<256, true, false, 1, 9><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk1024 var (mean 256) as 4 x 256 + read", bv + bm + bh,
+         [&] { k_bulk<1024, true, true, 1, 9, 256, 256><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk1024 var (mean 256) as 8 x 128 + read", bv + bm + bh,
+         [&] { k_bulk<1024, true, true, 1, 9, 128, 256><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk2048 var (mean 256) as 8 x 256 + read", bv + bm + bh,
+         [&] { k_bulk<2048, true, true, 1, 9, 256, 256><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk512 var (mean 256) as 2 x 256 + read", bv + bm + bh,
+         [&] { k_bulk<512, true, true, 1, 9, 256, 256><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 256 mean 512 + read", bv + bm + bh, [&] { k_bulk<256, true, true, 1, 9, 0, 512><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 256 mean 1024 + read", bv + bm + bh, [&] { k_bulk<256, true, true, 1, 9, 0, 1024><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 256 mean 2048 + read", bv + bm + bh, [&] { k_bulk<256, true, true, 1, 9, 0, 2048><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 512 mean 1024 + read", bv + bm + bh, [&] { k_bulk<512, true, true, 1, 9, 0, 1024><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 1024 mean 256 + read", bv + bm + bh, [&] { k_bulk<1024, true, true, 1, 9, 0, 256><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 1024 mean 512 + read", bv + bm + bh, [&] { k_bulk<1024, true, true, 1, 9, 0, 512><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("var 256 as 2 x 128, mean 1024 + read", bv + bm + bh, [&] { k_bulk<256, true, true, 1, 9, 128, 1024><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
   timeit("bulk256 var+mean 16 systems/warp", bv + bm, [&] { k_bulk16<256><<<grid(16), 64>>>(var, mu, B, T1); });
   timeit("bulk512 var+mean 16 systems/warp", bv + bm, [&] { k_bulk16<512><<<grid(16), 64>>>(var, mu, B, T1); });
   timeit("bulk256 mean only", bm, [&] { k_bulk<256, false, true><<<grid(32), 64>>>(var, mu, B, T1); });
