@@ -137,7 +137,19 @@ struct TpxLayout {
   static constexpr bool kPlain = RODEO_TPX_PLAIN != 0;
   static constexpr int IMG = SPW * n;                       // doubles of one staging image
   static constexpr int NST = (IMG + 31) / 32;               // store instructions per step
-  static constexpr size_t smem_bytes = kPlain ? (size_t)WARPS * U * 2 * IMG * 8 : (size_t)WARPS * U * SPW * SYS_BYTES;
+  static constexpr size_t out_bytes = kPlain ? (size_t)WARPS * U * 2 * IMG * 8 : (size_t)WARPS * U * SPW * SYS_BYTES;
+#ifndef RODEO_TPX_ASYNC
+#define RODEO_TPX_ASYNC 1
+#endif
+  // History prefetch.  kAsync: each lane copies its block's next checkpoint record (REC doubles) into its own
+  // shared-memory slots with cp.async (LDGSTS) one group ahead and picks it up with cp.async.wait_group + LDS.
+  // With register prefetches (plain loads a group ahead) the in-flight DRAM loads share a scoreboard with the
+  // z loads of the current step: the DFMA that consumes z waited for the PREFETCH to land (ncu: 27 % of all stall
+  // samples on that one instruction, unchanged when the z loads were hoisted to the top of the step).
+  static constexpr bool kAsync = RODEO_TPX_ASYNC != 0;
+  static constexpr int REC = p + PS;
+  static constexpr size_t stage_off = (out_bytes + 15) / 16 * 16;
+  static constexpr size_t smem_bytes = stage_off + (kAsync ? (size_t)THREADS * U * 2 * REC * 8 : 0);
   static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
 };
 
@@ -185,6 +197,29 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
     for (int e = 0; e < p; e++) mu[e] = ld_stream(h + (blk * p + e) * kTile);
 #pragma unroll
     for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
+  };
+  // (kAsync) cp.async prefetch of record r into stage r & 1 / pick-up from it; slot of element e: [u][stage][e][thread]
+  const uint32_t stage_base = smem_u32(smem_raw) + (uint32_t)L::stage_off + (uint32_t)threadIdx.x * 8u;
+  auto stage_addr = [&](int u, int st, int e) {
+    return stage_base + (uint32_t)((((u * 2 + st) * L::REC + e) * L::THREADS) * 8);
+  };
+  auto prefetch_rec = [&](int u, int r) {
+    const double *h = hb[u] + (size_t)r * NE * kTile;
+    const int st = r & 1;
+#pragma unroll
+    for (int e = 0; e < p; e++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stage_addr(u, st, e)), "l"(h + (blk * p + e) * kTile) : "memory");
+#pragma unroll
+    for (int e = 0; e < PS; e++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stage_addr(u, st, p + e)), "l"(h + (n + blk * PS + e) * kTile)
+                   : "memory");
+  };
+  auto fetch_rec = [&](int u, int r, double *mu, double *S) {
+    const int st = r & 1;
+#pragma unroll
+    for (int e = 0; e < p; e++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(mu[e]) : "r"(stage_addr(u, st, e)) : "memory");
+#pragma unroll
+    for (int e = 0; e < PS; e++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(S[e]) : "r"(stage_addr(u, st, p + e)) : "memory");
   };
   // (kPlain) staging images (shared-state addresses) and this lane's store offsets: double k * 32 + lane of an image =
   // element el of system sy of the warp, stored at xw[(sy * T1 + t) * n + el]
@@ -249,9 +284,12 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
       reads_pending = true;
     }
   };
-  auto z_at = [&](int u, int t, double *zt) {   // z[:, t-1], this block's rows
+  // z[:, t-1], this block's rows.  Volatile loads: issued HERE, at the top of the step; left to the compiler they sink
+  // to their use at the end of the step (x = m~ + L z) and their L2 latency lands on the chain -- ncu: 27 % of
+  // all stall samples on that one DFMA (profiles/r02_backward_tpx_plain_stores_ncu_summary.txt)
+  auto z_at = [&](int u, int t, double *zt) {
 #pragma unroll
-    for (int e = 0; e < p; e++) zt[e] = __ldg(zb[u] + (long)(t - 1) * n + e);
+    for (int e = 0; e < p; e++) zt[e] = ld_once(zb[u] + (long)(t - 1) * n + e);
   };
 
   double x[U][p], cm[U][p], cS[U][PS], nm[U][p], nS[U][PS], mus_unused[p], Ss_unused[PS];
@@ -261,8 +299,12 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
   for (int u = 0; u < U; u++) {
     load_rec(u, 0, cm[u], cS[u]);
-    if (R > 1) load_rec(u, 1, nm[u], nS[u]);
+    if (R > 1) {
+      if constexpr (L::kAsync) prefetch_rec(u, 1);
+      else load_rec(u, 1, nm[u], nS[u]);
+    }
   }
+  if constexpr (L::kAsync) asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
   for (int u = 0; u < U; u++) {   // terminal time index N = record 0
     double zt[p];
@@ -275,13 +317,23 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
   for (int t_hi = N; t_hi > 1;) {   // this group draws time indices t_hi-1 .. max(t_hi-CK, 1)
     const int base = t_hi - CK;
     if (base >= 1) {
+      if constexpr (L::kAsync) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");          // record r (copied a group ago) is in its stage
 #pragma unroll
-      for (int u = 0; u < U; u++) {
+        for (int u = 0; u < U; u++) {
+          fetch_rec(u, r, cm[u], cS[u]);
+          if (r + 1 < R) prefetch_rec(u, r + 1);                      // one group ahead, into the other stage
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      } else {
 #pragma unroll
-        for (int e = 0; e < p; e++) cm[u][e] = nm[u][e];
+        for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int e = 0; e < PS; e++) cS[u][e] = nS[u][e];
-        if (r + 1 < R) load_rec(u, r + 1, nm[u], nS[u]);            // one group ahead
+          for (int e = 0; e < p; e++) cm[u][e] = nm[u][e];
+#pragma unroll
+          for (int e = 0; e < PS; e++) cS[u][e] = nS[u][e];
+          if (r + 1 < R) load_rec(u, r + 1, nm[u], nS[u]);            // one group ahead
+        }
       }
     }
     if (CK == 2) {
