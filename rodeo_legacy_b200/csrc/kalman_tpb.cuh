@@ -188,7 +188,20 @@ struct TpbLayout {
 #endif
   static constexpr int WARPS = RODEO_TPB_WARPS;
   static constexpr int THREADS = WARPS * 32;
-  static constexpr size_t smem_need = (size_t)WARPS * WARP_BYTES + 1024;       // + alignment slack (1024-byte swizzle atoms)
+#ifndef RODEO_TPB_ASYNC
+#define RODEO_TPB_ASYNC 1
+#endif
+  // Variants that draw (DO_SIM) read z[:, t-1] inside every step.  With the history prefetched into REGISTERS a
+  // group ahead, those z loads share a scoreboard with the in-flight DRAM loads and their consumer waits for the
+  // prefetch (found on the Lorenz63 draw smoother, kalman_tpx.cuh).  They prefetch with cp.async into per-lane
+  // shared-memory slots instead and pin the z loads at the top of the step.
+  // Draw-only variants: with the variance slots beside it the extra shared memory costs a resident CTA
+  // (FN solve: 2.80 -> 3.09 ms), and the log-likelihood kernels have no dynamic shared memory at all.
+  static constexpr bool kAsync = DO_SIM && DO_VAR == 0 && RODEO_TPB_ASYNC != 0;
+  static constexpr int REC = p + PS;
+  static constexpr int STAGE_OFF = WARPS * WARP_BYTES;                         // after the output slots
+  static constexpr size_t smem_need = (size_t)WARPS * WARP_BYTES + (kAsync ? (size_t)THREADS * 2 * REC * 8 : 0) +
+                                      1024;                                    // + alignment slack (1024-byte swizzle atoms)
   // The kernel is HBM-bound and runs best with FEWER resident warps (measured, FN solve_mv, 65,536 systems:
   // 12 warps per SM 2.05 ms, 10: 2.00, 8: 1.99, 6: 1.98, 4: 2.40): with 4,096 equal-length warps the last,
   // partially filled wave is a smaller share of the launch.  Requesting 55 KB per CTA caps it at 4 CTAs = 8 warps.
@@ -286,6 +299,7 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
   constexpr int p = L::p, nb = L::nb, n = L::n, PS = L::PS, NE = Fam::NE;
   constexpr int NT = Ode::n_theta > 0 ? Ode::n_theta : 1;
   constexpr unsigned kFull = 0xffffffffu;
+  constexpr bool kAsyncK = L::kAsync && !LL;   // cp.async history prefetch (TpbLayout)
   extern __shared__ unsigned char smem_raw[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long wg = (long)blockIdx.x * L::WARPS + warp;     // warp index in the grid
@@ -377,6 +391,7 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
     if (lane0) tma_commit();
   };
 
+  const double *zb_ = DO_SIM ? a.z + bs * a.z_stride + blk * p : nullptr;
   // ---- history: this block's elements of record r --------------------------------------------------------
   const double *hb = a.hist + hist_offset(upos, 0, R, NE);
   auto load_rec = [&](int r, double *mu, double *S) {
@@ -387,6 +402,33 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
     for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
   };
 
+  // (kAsync) cp.async prefetch of record r into stage r & 1 / pick-up from it; slot of element e: [stage][e][thread]
+  const uint32_t stage_base = ((smem_u32(smem_raw) + 1023u) & ~1023u) + (uint32_t)L::STAGE_OFF + (uint32_t)threadIdx.x * 8u;
+  auto stage_addr = [&](int st, int e) { return stage_base + (uint32_t)(((st * L::REC + e) * L::THREADS) * 8); };
+  auto prefetch_rec = [&](int r) {
+    const double *h = hb + (size_t)r * NE * kTile;
+    const int st = r & 1;
+#pragma unroll
+    for (int e = 0; e < p; e++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stage_addr(st, e)), "l"(h + (blk * p + e) * kTile) : "memory");
+#pragma unroll
+    for (int e = 0; e < PS; e++)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(stage_addr(st, p + e)), "l"(h + (n + blk * PS + e) * kTile)
+                   : "memory");
+  };
+  auto fetch_rec = [&](int r, double *mu, double *S) {
+    const int st = r & 1;
+#pragma unroll
+    for (int e = 0; e < p; e++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(mu[e]) : "r"(stage_addr(st, e)) : "memory");
+#pragma unroll
+    for (int e = 0; e < PS; e++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(S[e]) : "r"(stage_addr(st, p + e)) : "memory");
+  };
+  // z[:, t-1], this block's rows, loaded where this is called (volatile), not where the draw consumes it
+  auto z_at = [&](int t, double *zt) {
+#pragma unroll
+    for (int e = 0; e < p; e++) zt[e] = DO_SIM ? ld_once(zb_ + (long)(t - 1) * n + e) : 0.0;
+  };
+
   // theta and x0 are loaded ONCE with volatile loads: left to the compiler, the x0 load of the last group
   // (base < 1) is speculated into every group and its L2 latency lands on the critical path
   double th[NT], x0b[p];
@@ -394,26 +436,38 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
   for (int e = 0; e < p; e++) x0b[e] = ld_once(a.x0 + bs * n + blk * p + e);
 #pragma unroll
   for (int e = 0; e < NT; e++) th[e] = (Ode::n_theta > 0 && CK > 1) ? ld_once(a.theta + bs * Ode::n_theta + e) : 0.0;
-  const double *zb = DO_SIM ? a.z + bs * a.z_stride + blk * p : nullptr;
 
   double mus[p], Ss[PS], x[p];
   double cm[p], cS[PS], nm[p], nS[PS];     // current / prefetched checkpoint record (this block)
   int fail = 0;
   load_rec(0, cm, cS);
-  if (R > 1) load_rec(1, nm, nS);
+  if (R > 1) {
+    if constexpr (kAsyncK) prefetch_rec(1);
+    else load_rec(1, nm, nS);
+  }
+  if constexpr (kAsyncK) asm volatile("cp.async.commit_group;" ::: "memory");
   {  // terminal time index N = record 0
-    fail = reg::smooth_terminal<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM>(cm, cS, DO_SIM ? zb + (long)(N - 1) * n : nullptr, mus, Ss, x);
+    double zt[p];
+    z_at(N, zt);
+    fail = reg::smooth_terminal<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM>(cm, cS, zt, mus, Ss, x);
     emit(N, mus, Ss, x);
   }
   int r = 1;
   for (int t_hi = N; t_hi > 1;) {   // this group smooths time indices t_hi-1 .. max(t_hi-CK, 1)
     const int base = t_hi - CK;
     if (base >= 1) {
+      if constexpr (kAsyncK) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // record r (copied a group ago) is in its stage
+        fetch_rec(r, cm, cS);
+        if (r + 1 < R) prefetch_rec(r + 1);                    // one group ahead, into the other stage
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      } else {
 #pragma unroll
-      for (int e = 0; e < p; e++) cm[e] = nm[e];
+        for (int e = 0; e < p; e++) cm[e] = nm[e];
 #pragma unroll
-      for (int e = 0; e < PS; e++) cS[e] = nS[e];
-      if (r + 1 < R) load_rec(r + 1, nm, nS);            // one group ahead
+        for (int e = 0; e < PS; e++) cS[e] = nS[e];
+        if (r + 1 < R) load_rec(r + 1, nm, nS);            // one group ahead
+      }
     }
     if constexpr (CK > 1) {
       const int t0 = base >= 1 ? base : 0;
@@ -451,16 +505,20 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
       for (int jf = CK - 2; jf >= 0; jf--) {
         if (jf < nfwd) {
           const int t = t0 + jf + 1;
+          double zt[p];
+          z_at(t, zt);
           const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
-              bp.Q(), bp.c(), bp.R(), sm_[jf], sS_[jf], DO_SIM ? zb + (long)(t - 1) * n : nullptr, mus, Ss, x);
+              bp.Q(), bp.c(), bp.R(), sm_[jf], sS_[jf], zt, mus, Ss, x);
           if (f && !fail) fail = f;
           emit(t, mus, Ss, x);
         }
       }
     }
     if (base >= 1) {
+      double zt[p];
+      z_at(base, zt);
       const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
-          bp.Q(), bp.c(), bp.R(), cm, cS, DO_SIM ? zb + (long)(base - 1) * n : nullptr, mus, Ss, x);
+          bp.Q(), bp.c(), bp.R(), cm, cS, zt, mus, Ss, x);
       if (f && !fail) fail = f;
       emit(base, mus, Ss, x);
     }
