@@ -633,7 +633,7 @@ def main():
                          "algorithmic_note": "SURVEY 8(d) bytes (the reference's four dense history arrays + the output); "
                                              "the kernel moves fewer because predicted moments are recomputed, covariances "
                                              "are stored packed per block and every second record is re-run (checkpoint 2)",
-                         "forward": {"kernel": "kalman_forward_tpb" if tpb else "kalman_forward",
+                         "forward": {"kernel": "kalman_forward_wpb" if tpb else "kalman_forward",
                                      "kernel_ms": fwd_ms, "traffic": traffic["forward"],
                                      "achieved": traffic["forward"] / fwd_s / 1e9,
                                      "frac": traffic["forward"] / fwd_s / 1e9 / peak,

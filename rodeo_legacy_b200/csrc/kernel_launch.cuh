@@ -53,6 +53,7 @@ inline typename Fam::PriorT make_prior(const HostPrior &h) {
 #include "kalman_sc.cuh"
 #include "kalman_tpb.cuh"
 #include "kalman_tpx.cuh"
+#include "kalman_wpb.cuh"
 namespace rodeo {
 
 template <class Fam, bool UNROLL, int IG>
@@ -103,6 +104,20 @@ cudaError_t launch_forward(const HostPrior &h, const SolveArgs &a, cudaStream_t 
   kalman_forward<Fam, UNROLL, IG><<<grid_for(a.perm16 ? (a.B + 255) / 256 * 256 : a.B), kThreadsPerBlock, 0, s>>>(
       make_prior<Fam>(h), a);
   return cudaGetLastError();
+}
+
+// Forward pass of the block-diagonal register families: one warp per diagonal block (kalman_wpb.cuh);
+// RODEO_CUDA_FORWARD=legacy restores the thread-per-block (two blocks) / thread-per-system (three or more) kernels.
+template <class Fam, int IG, bool TWO>
+cudaError_t launch_forward_bd(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {
+  // Measured (B200): two blocks, FN 65,536 x 400: 0.368 -> 0.337 ms.  Three or more blocks: a gain only where the
+  // pass is bound by its history stores (full history: MSEIR 32,768 x 1000 1.99 -> 1.85 ms); with a checkpointed
+  // history the per-step CTA barrier costs more than the extra warps bring (MSEIR interval 2: 0.95 -> 1.28 ms,
+  // Lorenz63 1.87 -> 1.90 ms), so those keep one thread per system.
+  const bool wpb = !prefer_legacy_forward() && (TWO || a.ck == 1);
+  if (wpb) return launch_forward_wpb<Fam, IG>(h, a, s);
+  if constexpr (TWO) return launch_forward_tpb<Fam, IG>(h, a, s);
+  else return launch_forward<Fam, true, IG>(h, a, s);
 }
 
 template <class Fam, bool UNROLL, int CK, bool DO_MEAN, bool DO_VAR, bool DO_SIM, bool LOGLIK>
@@ -230,10 +245,15 @@ KernelSet make_kernel_set(const char *name) {
   k.forward[IG_SCHOBERT] = launch_forward<Fam, UNROLL, IG_SCHOBERT>;
   k.forward[IG_CHKREBTII] = launch_forward<Fam, UNROLL, IG_CHKREBTII>;
   k.forward_perm[0] = k.forward_perm[1] = k.forward_perm[2] = nullptr;
-  if constexpr (UNROLL && BD && Ode::n_meas == 2) {   // thread-per-block forward (kalman_tpb.cuh)
-    k.forward_perm[IG_PROBDE] = launch_forward_tpb<Fam, IG_PROBDE>;
-    k.forward_perm[IG_SCHOBERT] = launch_forward_tpb<Fam, IG_SCHOBERT>;
-    k.forward_perm[IG_CHKREBTII] = launch_forward_tpb<Fam, IG_CHKREBTII>;
+  if constexpr (UNROLL && BD && Ode::n_meas == 2) {   // warp-per-block forward (kalman_wpb.cuh), permuted order
+    k.forward_perm[IG_PROBDE] = launch_forward_bd<Fam, IG_PROBDE, true>;
+    k.forward_perm[IG_SCHOBERT] = launch_forward_bd<Fam, IG_SCHOBERT, true>;
+    k.forward_perm[IG_CHKREBTII] = launch_forward_bd<Fam, IG_CHKREBTII, true>;
+  }
+  if constexpr (UNROLL && BD && Ode::n_meas >= 3) {   // warp-per-block forward, plain order
+    k.forward[IG_PROBDE] = launch_forward_bd<Fam, IG_PROBDE, false>;
+    k.forward[IG_SCHOBERT] = launch_forward_bd<Fam, IG_SCHOBERT, false>;
+    k.forward[IG_CHKREBTII] = launch_forward_bd<Fam, IG_CHKREBTII, false>;
   }
   for (int c = 0; c < kNumCk; c++)
     for (int b = 0; b < BK_COUNT; b++) {
