@@ -170,17 +170,17 @@ RD_UNROLL_IN
 // The same update for ONE diagonal block with a scalar measurement  y_a = w^T x_a:
 //   A = w^T Sp; s = A w (+ A w under probde); K = A / s; mu_f = mu_p + K (y_a - w^T mu_p);
 //   Sf = Sp - A^T K.   The m x m Cholesky of the dense update degenerates to one division.
+// The two halves are separate routines so that a kernel can start the division (which needs only Sp) before the
+// right-hand side is known (kalman_wpb.cuh); update_block is their composition, so every kernel runs the same
+// operations in the same order.
 template <int p, int WK = -1>
-RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool zero_H,
-                       double *dumpK = nullptr) {
-  double A[p];
-  double s = 0.0, e = ya;
-  if (WK >= 0) {                 // w = e_WK: A = row WK of Sp, s = Sp(WK, WK), e = y - mu_p[WK]
+RD_HD int update_block_gain(const double *w, const double *S, bool zero_H, double *A, double *inv) {
+  double s = 0.0;
+  if (WK >= 0) {                 // w = e_WK: A = row WK of Sp, s = Sp(WK, WK)
     constexpr int K = WK >= 0 ? WK : 0;
 RD_UNROLL
     for (int j = 0; j < p; j++) A[j] = S[sidx<p>(K, j)];
     s = A[K];
-    e = sub_rn(ya, mu[K]);
   } else {
 RD_UNROLL
     for (int j = 0; j < p; j++) {
@@ -190,14 +190,23 @@ RD_UNROLL_IN
       A[j] = v;
     }
 RD_UNROLL
-    for (int j = 0; j < p; j++) {
-      s += A[j] * w[j];
-      e -= w[j] * mu[j];
-    }
+    for (int j = 0; j < p; j++) s += A[j] * w[j];
   }
   if (!zero_H) s = s + s;
-  const int fail = (s > 0.0) ? 0 : 1;
-  const double inv = 1.0 / s;
+  *inv = 1.0 / s;
+  return (s > 0.0) ? 0 : 1;
+}
+template <int p, int WK = -1>
+RD_HD void update_block_apply(const double *w, double *mu, double *S, double ya, const double *A, double inv,
+                              double *dumpK = nullptr) {
+  double e = ya;
+  if (WK >= 0) {                 // e = y - mu_p[WK]
+    constexpr int K = WK >= 0 ? WK : 0;
+    e = sub_rn(ya, mu[K]);
+  } else {
+RD_UNROLL
+    for (int j = 0; j < p; j++) e -= w[j] * mu[j];
+  }
 RD_UNROLL
   for (int j = 0; j < p; j++) {
     const double kj = A[j] * inv;
@@ -206,6 +215,13 @@ RD_UNROLL
 RD_UNROLL_IN
     for (int i = 0; i <= j; i++) S[sidx<p>(i, j)] -= A[i] * kj;
   }
+}
+template <int p, int WK = -1>
+RD_HD int update_block(const double *w, double *mu, double *S, double ya, bool zero_H,
+                       double *dumpK = nullptr) {
+  double A[p], inv;
+  const int fail = update_block_gain<p, WK>(w, S, zero_H, A, &inv);
+  update_block_apply<p, WK>(w, mu, S, ya, A, inv, dumpK);
   return fail;
 }
 

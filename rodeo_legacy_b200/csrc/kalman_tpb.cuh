@@ -597,7 +597,7 @@ kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
 #pragma unroll
   for (int e = 0; e < NT; e++) th[e] = (Ode::n_theta > 0) ? a.theta[bs * Ode::n_theta + e] : 0.0;
   const double *zb = (IG == IG_CHKREBTII) ? a.z + bs * a.z_stride + blk * p : nullptr;
-  double *hb = a.hist + hist_offset(upos, 0, R, NE);
+  double *h = a.hist + hist_offset(upos, R - 1, R, NE);   // records are stored from r = R - 1 down to r = 0
   int t_fail = 0x7fffffff;     // first time index at which this block's innovation variance was not positive
   int back = N - 1;            // distance of time index t + 1 from the end
   int until = back % ck;       // steps until the next stored record
@@ -632,11 +632,11 @@ kalman_forward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
 #pragma unroll
     for (int e = 0; e < PS; e++) S[e] = Sp[e];
     if (until == 0) {
-      double *h = hb + (size_t)(back / ck) * NE * kTile;
 #pragma unroll
       for (int e = 0; e < p; e++) __stcs(h + (blk * p + e) * kTile, mu[e]);
 #pragma unroll
       for (int e = 0; e < PS; e++) __stcs(h + (n + blk * PS + e) * kTile, S[e]);
+      h -= NE * kTile;
       until = ck;
     }
     until--;

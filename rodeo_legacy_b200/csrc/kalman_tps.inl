@@ -165,17 +165,22 @@ RD_UNROLL
   const long hpos = a.perm16 ? perm16(b) : b;     // position of this system in the history
   const double *zb = (IG == IG_CHKREBTII) ? a.z + b * a.z_stride : nullptr;
   int fail = 0;
+  // time index t+1 is kept when its distance N-(t+1) from the end is a multiple of ck: records r = R-1 down to 0.
+  // A countdown and a running pointer: no division by the run-time interval inside the loop.
+  int until = (N - 1) % ck;
+  double *h = a.hist + hist_offset(hpos, R - 1, R, NE);
   for (int t = 0; t < N; t++) {
     int f = Fam::template step<IG>(P, t, th, zb, mu, S);
     if (f && !fail) fail = f;
-    const int back = N - (t + 1);                 // distance of time index t+1 from the end
-    if (back % ck == 0) {
-      double *h = a.hist + hist_offset(hpos, back / ck, R, NE);
+    if (until == 0) {
 RD_UNROLL
       for (int i = 0; i < n; i++) h[i * kTile] = mu[i];
 RD_UNROLL
       for (int i = 0; i < NS; i++) h[(n + i) * kTile] = S[i];
+      h -= NE * kTile;
+      until = ck;
     }
+    until--;
   }
   if (a.status) a.status[b] = fail;
 }

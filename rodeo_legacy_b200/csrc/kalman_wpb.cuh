@@ -60,16 +60,22 @@ kalman_forward_wpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
 #pragma unroll
   for (int e = 0; e < NT; e++) th[e] = (Ode::n_theta > 0) ? a.theta[bs * Ode::n_theta + e] : 0.0;
   const double *zb = (IG == IG_CHKREBTII) ? a.z + bs * a.z_stride + blk * p : nullptr;
-  double *hb = a.hist + hist_offset(u, 0, R, NE);
+  // records are stored from the last one (r = R - 1, the earliest time index kept) down to r = 0 (time index N):
+  // a running pointer, no division by the run-time interval inside the loop
+  double *h = a.hist + hist_offset(u, R - 1, R, NE);
   int t_fail = 0x7fffffff;     // first time index at which this block's innovation variance was not positive
   int back = N - 1;            // distance of time index t + 1 from the end
   int until = back % ck;       // steps until the next stored record
+  // shared-state addresses of the exchange slots, computed once (left to the compiler, the thread index is
+  // re-read with S2R in every step: ncu, 6 % of the stall samples)
+  const uint32_t lead_wr = smem_u32(&lead_s[0][blk][lane]), lead_rd = smem_u32(&lead_s[0][0][lane]);
+  uint32_t par = 0;            // byte offset of the slots of this step's parity
+  auto publish = [&](double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(lead_wr + par), "d"(v) : "memory"); };
   for (int t = 0; t < N; t++, back--) {
     double mup[p], Sp[PS];
     reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), mu, mup);
-    double lead = mup[0];
     int f = 0;
-    if (IG != IG_CHKREBTII) lead_s[t & 1][blk][lane] = lead;   // published before the covariance work
+    if (IG != IG_CHKREBTII) publish(mup[0]);   // before the covariance work
     reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), S, Sp, nullptr);
     if (IG == IG_CHKREBTII) {   // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
       double xs[p], V[PS], zt[p];
@@ -78,17 +84,22 @@ kalman_forward_wpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
 #pragma unroll
       for (int e = 0; e < p; e++) zt[e] = zb[(long)t * n + e];
       f = reg::state_sim<p>(xs, mup, V, zt);
-      lead_s[t & 1][blk][lane] = xs[0];
+      publish(xs[0]);
     }
+    // the gain needs only Sigma_pred: its division runs while the blocks meet (update_block = gain + apply)
+    double A[p], inv;
+    const int f2 = reg::update_block_gain<p, Fam::kWK>(bp.w(), Sp, IG == IG_SCHOBERT, A, &inv);
     __syncthreads();
     double X[n];
 #pragma unroll
     for (int e = 0; e < n; e++) X[e] = 0.0;
 #pragma unroll
-    for (int k = 0; k < nb; k++) X[k * p] = lead_s[t & 1][k][lane];
+    for (int k = 0; k < nb; k++)
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(X[k * p]) : "r"(lead_rd + par + (uint32_t)(k * 32 * 8)) : "memory");
+    par ^= (uint32_t)(nb * 32 * 8);
     const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / P.n_eval;
     const double ya = ode_component<Ode, n>(blk, X, tt, th);
-    const int f2 = reg::update_block<p, Fam::kWK>(bp.w(), mup, Sp, ya, IG == IG_SCHOBERT);
+    reg::update_block_apply<p, Fam::kWK>(bp.w(), mup, Sp, ya, A, inv);
     if ((f | f2) && t_fail == 0x7fffffff) t_fail = t;
 #pragma unroll
     for (int e = 0; e < p; e++) mu[e] = mup[e];
@@ -96,11 +107,11 @@ kalman_forward_wpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
     for (int e = 0; e < PS; e++) S[e] = Sp[e];
     if (until == 0) {
       // (idle lanes of the last tile store the safe system's record: the padded positions hold finite numbers)
-      double *h = hb + (size_t)(back / ck) * NE * kTile;
 #pragma unroll
       for (int e = 0; e < p; e++) __stcs(h + (blk * p + e) * kTile, mu[e]);
 #pragma unroll
       for (int e = 0; e < PS; e++) __stcs(h + (n + blk * PS + e) * kTile, S[e]);
+      h -= NE * kTile;
       until = ck;
     }
     until--;
@@ -122,14 +133,15 @@ kalman_forward_wpb(const __grid_constant__ typename Fam::PriorT P, const __grid_
   }
 }
 
-// RODEO_CUDA_FORWARD=legacy keeps the previous forward kernels (A/B measurements)
-inline bool prefer_legacy_forward() {
-  static const bool v = [] {
+// RODEO_CUDA_FORWARD=legacy keeps the previous forward kernels, =wpb forces this one (A/B measurements)
+inline int forward_preference() {
+  static const int v = [] {
     const char *e = getenv("RODEO_CUDA_FORWARD");
-    return e && e[0] == 'l';
+    return !e ? 0 : e[0] == 'l' ? 1 : e[0] == 'w' ? 2 : 0;
   }();
   return v;
 }
+inline bool prefer_legacy_forward() { return forward_preference() == 1; }
 
 template <class Fam, int IG>
 cudaError_t launch_forward_wpb(const HostPrior &h, const SolveArgs &a, cudaStream_t s) {

@@ -114,7 +114,7 @@ cudaError_t launch_forward_bd(const HostPrior &h, const SolveArgs &a, cudaStream
   // pass is bound by its history stores (full history: MSEIR 32,768 x 1000 1.99 -> 1.85 ms); with a checkpointed
   // history the per-step CTA barrier costs more than the extra warps bring (MSEIR interval 2: 0.95 -> 1.28 ms,
   // Lorenz63 1.87 -> 1.90 ms), so those keep one thread per system.
-  const bool wpb = !prefer_legacy_forward() && (TWO || a.ck == 1);
+  const bool wpb = !prefer_legacy_forward() && (TWO || a.ck == 1 || forward_preference() == 2);
   if (wpb) return launch_forward_wpb<Fam, IG>(h, a, s);
   if constexpr (TWO) return launch_forward_tpb<Fam, IG>(h, a, s);
   else return launch_forward<Fam, true, IG>(h, a, s);
