@@ -1161,3 +1161,51 @@ def test_unequal_block_sizes_without_a_compiled_set_fail_loudly():
     kinit = indep_init(ibm_init(0.1, n_prior, [0.1, 0.1]), n_prior)
     with pytest.raises((RodeoCudaError, NotImplementedError), match="block sizes"):
         KalmanODE(W, 0.0, 40.0, 400, "fitz", **kinit)
+
+
+_FORWARD_AB = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from tests import workloads as wl
+out = {{}}
+for name, maker, B, kw in [("fitz", wl.fitz_batch, 700, {{}}), ("fitz_sch", wl.fitz_batch, 300, dict(interrogate="schobert")),
+                           ("fitz_chk", wl.fitz_batch, 300, dict(interrogate="chkrebtii")),
+                           ("mseir", lambda B: wl.mseir_batch(B, N=120), 70, {{}}),
+                           ("lorenz", lambda B: wl.lorenz_batch(B, N=200, tmax=0.8), 45, {{}})]:
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(11).standard_normal((n, w["N"])))
+    k = wl.make_kode(w, z_state=z, **kw)
+    x, mu, var = k.solve(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda())
+    out[name + "_x"], out[name + "_mu"], out[name + "_var"] = x.cpu().numpy(), mu.cpu().numpy(), var.cpu().numpy()
+np.savez({path!r}, **out)
+"""
+
+
+def test_forward_kernels_are_bit_identical(tmp_path):
+    """The warp-per-block forward filter (kalman_wpb.cuh, the default for two-block priors and for full-history
+    passes with three or more blocks) against the kernels it replaced (RODEO_CUDA_FORWARD=legacy: thread per
+    block / thread per system) and forced everywhere (=wpb: also the checkpointed passes with three or more
+    blocks): every output of `solve` bit for bit, for the three interrogation variants.  The preference is read
+    once per process, so each setting runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("default", "legacy", "wpb"):
+        path = str(tmp_path / f"{mode}.npz")
+        env = dict(os.environ)
+        env.pop("RODEO_CUDA_FORWARD", None)
+        if mode != "default":
+            env["RODEO_CUDA_FORWARD"] = mode
+        r = subprocess.run([sys.executable, "-c", _FORWARD_AB.format(root=root, path=path)], env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[mode] = dict(np.load(path))
+    for key, ref in res["legacy"].items():
+        if key.endswith("_mu") and "_sch" not in key:
+            assert np.isfinite(ref).all(), key
+        # (schobert: H = 0 leaves Sigma_f singular and diverges for most theta draws -- the NaNs must match too)
+        for mode in ("default", "wpb"):
+            assert np.array_equal(ref, res[mode][key], equal_nan=True), (mode, key)
