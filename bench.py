@@ -547,6 +547,14 @@ def main():
             for _ in range(args.e2e_steps):
                 xs = kz.solve_sim(x0, theta=theta)
             el_sim = (time.perf_counter() - t0) / args.e2e_steps
+            xp = torch.empty((B, N_EVAL + 1, N_STATE), dtype=torch.float64, pin_memory=True)   # allocated once by the caller
+            kz.solve_sim_into(x0, theta, xp.numpy())
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                kz.solve_sim_into(x0, theta, xp.numpy())
+            el_simp = (time.perf_counter() - t0) / args.e2e_steps
+            sim_same = bool(np.array_equal(xp.numpy(), xs))
+            del xp
             Y, ind, sind = wl.fitz_observations(kz, w)
             lln = kz.loglik(x0, theta, Y, ind, sind, 0.2)      # NumPy in -> NumPy out
             t0 = time.perf_counter()
@@ -558,6 +566,11 @@ def main():
                               "h2d_bytes_per_step": B * (N_STATE + 3) * 8 + z.nbytes,
                               "d2h_bytes_per_step": B * (N_EVAL + 1) * N_STATE * 8 + B * 4,
                               "host_buffers": "pageable NumPy arrays (the call a reference user makes)"},
+                "solve_sim_into": {"value": B / el_simp, "unit": UNIT, "ms_per_step": 1e3 * el_simp,
+                                   "h2d_bytes_per_step": B * (N_STATE + 3) * 8 + z.nbytes,
+                                   "d2h_bytes_per_step": B * (N_EVAL + 1) * N_STATE * 8 + B * 4,
+                                   "host_buffers": "result into a pinned buffer the caller allocated once",
+                                   "same_draws_as_solve_sim": sim_same},
                 "loglik": {"value": B / el_ll, "unit": UNIT, "ms_per_step": 1e3 * el_ll,
                            "h2d_bytes_per_step": B * (N_STATE + 3) * 8, "d2h_bytes_per_step": B * 12,
                            "host_buffers": "pageable NumPy arrays", "checksum": float(np.sum(lln))}}

@@ -519,9 +519,18 @@ class KalmanODE:
         """(posterior mean, posterior variance) -- KalmanODE.pyx:429-463."""
         return self._run(MODE_MV, x0, W, theta, priors=priors)[1:]
 
+    # Host path writing into caller-provided NumPy buffers (float64, C-contiguous, exact shape; checked).  A fresh
+    # pageable np.empty result costs its first-touch page faults and a staged copy on every call (FN solve_sim,
+    # 65,536 systems: 280 ms for 1.26 GB); buffers the caller allocates once -- ideally pinned, e.g.
+    # torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy() -- take the copy at PCIe speed (25 ms).
     def solve_mv_into(self, x0, theta, mu_out, var_out):
-        """Host path writing into caller-provided (e.g. pinned) NumPy buffers."""
         self._run(MODE_MV, x0, None, theta, out=(None, mu_out, var_out))
+
+    def solve_sim_into(self, x0, theta, x_out):
+        self._run(MODE_SIM, x0, None, theta, out=(x_out, None, None))
+
+    def solve_into(self, x0, theta, x_out, mu_out, var_out):
+        self._run(MODE_BOTH, x0, None, theta, out=(x_out, mu_out, var_out))
 
     # ---- fused thinning + Gaussian log-likelihood (examples/inference.py:54-56, 66-94) ------
     def loglik(self, x0, theta, Y, thin_index, state_ind, gamma, use_draw=False, priors=None):

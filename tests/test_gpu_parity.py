@@ -1209,3 +1209,26 @@ def test_forward_kernels_are_bit_identical(tmp_path):
         # (schobert: H = 0 leaves Sigma_f singular and diverges for most theta draws -- the NaNs must match too)
         for mode in ("default", "wpb"):
             assert np.array_equal(ref, res[mode][key], equal_nan=True), (mode, key)
+
+
+def test_into_variants_write_caller_buffers():
+    """solve_sim_into / solve_into / solve_mv_into (host path into buffers the caller allocated once, e.g. pinned):
+    the same numbers as the returning methods, bad buffers refused before anything is copied."""
+    w, x0, theta = wl.fitz_batch(1500, seed=8)
+    z = np.asfortranarray(np.random.default_rng(8).standard_normal((6, w["N"])))
+    k = wl.make_kode(w, z_state=z)
+    x, mu, var = k.solve(x0, theta=theta)
+    T = w["N"] + 1
+    pin = lambda *s: torch.empty(s, dtype=torch.float64, pin_memory=True).numpy()
+    xo, mo, vo = pin(1500, T, 6), pin(1500, T, 6), pin(1500, T, 6, 6)
+    k.solve_into(x0, theta, xo, mo, vo)
+    assert np.array_equal(xo, x) and np.array_equal(mo, mu) and np.array_equal(vo, var)
+    xo[:] = 0.0
+    k.solve_sim_into(x0, theta, xo)
+    assert np.array_equal(xo, k.solve_sim(x0, theta=theta)) and np.array_equal(xo, x)
+    mo[:] = 0.0
+    k.solve_mv_into(x0, theta, mo, vo)
+    assert np.array_equal(mo, mu)
+    for bad in (np.empty((1500, T, 6), dtype=np.float32), np.empty((1499, T, 6)), np.empty((1500, T, 12))[:, :, ::2]):
+        with pytest.raises(TypeError):
+            k.solve_sim_into(x0, theta, bad)
