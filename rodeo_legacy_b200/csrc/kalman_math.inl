@@ -60,6 +60,28 @@ RD_UNROLL_IN
   }
 }
 
+// The two halves of chol_solve_vec: x <- L^{-1} x and x <- L^{-T} x.
+template <int n>
+RD_HD void chol_fwd_vec(const double *L, const double *invd, double *x, int stride) {
+RD_UNROLL
+  for (int i = 0; i < n; i++) {
+    double s = x[i * stride];
+RD_UNROLL_IN
+    for (int k = 0; k < i; k++) s -= L[sidx<n>(i, k)] * x[k * stride];
+    x[i * stride] = s * invd[i];
+  }
+}
+template <int n>
+RD_HD void chol_bwd_vec(const double *L, const double *invd, double *x, int stride) {
+RD_UNROLL
+  for (int i = n - 1; i >= 0; i--) {
+    double s = x[i * stride];
+RD_UNROLL_IN
+    for (int k = i + 1; k < n; k++) s -= L[sidx<n>(k, i)] * x[k * stride];
+    x[i * stride] = s * invd[i];
+  }
+}
+
 // Structured priors (detected on the host, api.cu: is_structured).  UT: Q is upper triangular (what ibm_init
 // produces: a Toeplitz upper-triangular transition block); the terms with an exactly-zero coefficient are
 // skipped, the others are accumulated in the same order, so for finite data the results are bit-identical
@@ -332,8 +354,45 @@ RD_UNROLL_IN
     }
     return fail;
   }
+  // With Sigma_p = L L^T the gain is T~ = L^{-T} U, U = L^{-1} T (T = Q Sigma_f).  The draw needs only U:
+  //   m~ = mu_f + T~^T (x+ - mu_p+) = mu_f + U^T (L^{-1} (x+ - mu_p+)),   V~ = Sigma_f - T~^T T = Sigma_f - U^T U
+  // (KalmanTV.h:511-523 with the products associated the other way): no backward substitution and no second
+  // Q Sigma_f for the draw-only smoothers, and V~ is formed as a symmetric difference.  Mean and variance then
+  // take T~ = L^{-T} U as before (U is overwritten in place, after the draw).
 RD_UNROLL
-  for (int j = 0; j < n; j++) chol_solve_vec<n>(Sp, invd, T + j, n);  // T~ (:458)
+  for (int j = 0; j < n; j++) chol_fwd_vec<n>(Sp, invd, T + j, n);   // U
+  if (DO_SIM) {
+    double w[n], mt[n], V[NS], zt[n];
+RD_UNROLL
+    for (int k = 0; k < n; k++) w[k] = x[k] - mup[k];
+    chol_fwd_vec<n>(Sp, invd, w, 1);
+RD_UNROLL
+    for (int i = 0; i < n; i++) {
+      double s = muf[i];
+RD_UNROLL_IN
+      for (int k = 0; k < n; k++) s += T[k * n + i] * w[k];
+      mt[i] = s;
+    }
+RD_UNROLL
+    for (int i = 0; i < NS; i++) V[i] = rec_S2[i * STRIDE];
+RD_UNROLL
+    for (int k = 0; k < n; k++)
+RD_UNROLL
+      for (int i = 0; i < n; i++)
+RD_UNROLL_IN
+        for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * T[k * n + j];
+RD_UNROLL
+    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
+    int f2 = state_sim<n>(x, mt, V, zt);
+    if (f2 && !fail) fail = f2;
+    if (dumpL) {                             // V now holds chol_lower(V~)
+RD_UNROLL
+      for (int i = 0; i < NS; i++) dumpL[i] = V[i];
+    }
+  }
+  if (!(DO_MEAN || DO_VAR || dumpT)) return fail;
+RD_UNROLL
+  for (int j = 0; j < n; j++) chol_bwd_vec<n>(Sp, invd, T + j, n);   // T~ (:458)
   if (dumpT) {                               // shared-covariance tables: the smoother gain
 RD_UNROLL
     for (int i = 0; i < n * n; i++) dumpT[i] = T[i];
@@ -348,47 +407,6 @@ RD_UNROLL
 RD_UNROLL_IN
       for (int k = 0; k < n; k++) s += T[k * n + i] * dmu[k];
       mus[i] = s;
-    }
-  }
-  if (DO_SIM) {                              // KalmanTV.h:511-527
-    double dx[n], mt[n], V[NS], Sf[NS], zt[n];
-RD_UNROLL
-    for (int k = 0; k < n; k++) dx[k] = x[k] - mup[k];
-RD_UNROLL
-    for (int i = 0; i < n; i++) {
-      double s = muf[i];
-RD_UNROLL_IN
-      for (int k = 0; k < n; k++) s += T[k * n + i] * dx[k];
-      mt[i] = s;
-    }
-RD_UNROLL
-    for (int i = 0; i < NS; i++) {
-      Sf[i] = rec_S2[i * STRIDE];
-      V[i] = Sf[i];
-    }
-    // V~ = Sigma_f - T~^T (Q Sigma_f): row k of Q Sigma_f is recomputed (T was overwritten)
-RD_UNROLL
-    for (int k = 0; k < n; k++) {
-      double Tk[n];
-RD_UNROLL
-      for (int j = 0; j < n; j++) {
-        double s = 0.0;
-RD_UNROLL_IN
-        for (int l = UT ? k : 0; l < n; l++) s += Q[k * n + l] * Sf[sidx<n>(l, j)];
-        Tk[j] = s;
-      }
-RD_UNROLL
-      for (int i = 0; i < n; i++)
-RD_UNROLL_IN
-        for (int j = i; j < n; j++) V[sidx<n>(i, j)] -= T[k * n + i] * Tk[j];
-    }
-RD_UNROLL
-    for (int i = 0; i < n; i++) zt[i] = zt_ptr[i];
-    int f2 = state_sim<n>(x, mt, V, zt);
-    if (f2 && !fail) fail = f2;
-    if (dumpL) {                             // V now holds chol_lower(V~)
-RD_UNROLL
-      for (int i = 0; i < NS; i++) dumpL[i] = V[i];
     }
   }
   if (DO_VAR) {                              // Sigma_s = Sigma_f + T~^T D T~  (:461-465)
