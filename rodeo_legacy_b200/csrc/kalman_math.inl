@@ -13,8 +13,10 @@
 //
 // Arithmetic follows the reference's KalmanTV (rodeo/eigen/KalmanTV.h): predict :280-294,
 // update :324-357, smooth_mv :447-467, smooth_sim :503-533, state_sim :619-628, with the
-// probde interrogation of rodeo/eigen/KalmanTVODE.h:333-341.  Only the summation order
-// and the use of symmetry / block structure differ (results agree to FP64 rounding).
+// probde interrogation of rodeo/eigen/KalmanTVODE.h:333-341.  Only the summation order,
+// the use of symmetry / block structure and the association of two products differ (results
+// agree to FP64 rounding): the mean-only step solves Sigma_p v = mu_s+ - mu_p+ once instead of
+// forming the gain, and the draw goes through U = L^{-1} Q Sigma_f (see smooth_step).
 
 // In-place lower Cholesky of a packed symmetric matrix (right-looking):
 // on exit A(i, j), i >= j holds L(i, j) and invd[j] = 1 / L(j, j).
