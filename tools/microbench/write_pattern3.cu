@@ -118,6 +118,51 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32
                "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
                : "memory");
 }
+// the same copy with an L2 eviction policy (HINT: 1 evict_first, 2 evict_last, 3 no_allocate)
+template <int HINT>
+__device__ __forceinline__ void bulk_s2g_hint(void *dst, const void *src_smem, uint32_t bytes) {
+  uint64_t pol;
+  if (HINT == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (HINT == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst),
+               "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+template <int W, int G, int HINT>
+__device__ __forceinline__ void bulk_step_hint(double *out, const double *src, long b, long B, int T1, int t, long &F) {
+  if (b >= B) return;
+  const long lo = (b * T1 + t) * (long)(W * 8);
+  const long c = (t == 0) ? lo : (lo + G - 1) / G * G;
+  if (c < F) {
+    bulk_s2g_hint<HINT>(reinterpret_cast<char *>(out) + c, src, (uint32_t)(F - c));
+    F = c;
+  }
+}
+template <int G, int HINT>
+__global__ void __launch_bounds__(64) k_bulk_hint(double *var, double *mu, long B, int T1, const double *hist, double *sink) {
+  constexpr int SRC = ((G + kWv * 8) / 8 + 15) / 16 * 16;
+  __shared__ __align__(128) double src_all[2][SRC];
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  const long b = ((long)blockIdx.x * 2 + warp) * 32 + lane;
+  double *src_w = src_all[warp];
+  for (int i = lane; i < SRC; i += 32) src_w[i] = i;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  long Fv = (b + 1) * T1 * (long)(kWv * 8), Fm = (b + 1) * T1 * (long)(kWm * 8);
+  const double *h = hist + ((long)blockIdx.x * 2 + warp) * (long)T1 * 9 * 32 + lane;
+  double acc = 0.0;
+  for (int t = T1 - 1; t >= 0; t--) {
+#pragma unroll
+    for (int e = 0; e < 9; e++) acc += __ldcs(h + ((long)(T1 - 1 - t) * 9 + e) * 32);
+    bulk_step_hint<kWv, G, HINT>(var, src_w, b, B, T1, t, Fv);
+    bulk_step_hint<kWm, G, HINT>(mu, src_w, b, B, T1, t, Fm);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (acc == 12345.678) sink[0] = acc;
+}
 template <int W, int G, int SPLIT = 0>
 __device__ __forceinline__ void bulk_step(double *out, const double *src, long b, long B, int T1, int t, long &F) {
   if (b >= B) return;
@@ -312,6 +357,9 @@ int main() {
   timeit("var 1024 mean 256 + read", bv + bm + bh, [&] { k_bulk<1024, true, true, 1, 9, 0, 256><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
   timeit("var 1024 mean 512 + read", bv + bm + bh, [&] { k_bulk<1024, true, true, 1, 9, 0, 512><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
   timeit("var 256 as 2 x 128, mean 1024 + read", bv + bm + bh, [&] { k_bulk<256, true, true, 1, 9, 128, 1024><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk256 var+mean + read, stores evict_first", bv + bm + bh, [&] { k_bulk_hint<256, 1><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk256 var+mean + read, stores evict_last", bv + bm + bh, [&] { k_bulk_hint<256, 2><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
+  timeit("bulk256 var+mean + read, stores evict_unchanged", bv + bm + bh, [&] { k_bulk_hint<256, 3><<<grid(32), 64>>>(var, mu, B, T1, hist, sink); });
   timeit("bulk256 var+mean 16 systems/warp", bv + bm, [&] { k_bulk16<256><<<grid(16), 64>>>(var, mu, B, T1); });
   timeit("bulk512 var+mean 16 systems/warp", bv + bm, [&] { k_bulk16<512><<<grid(16), 64>>>(var, mu, B, T1); });
   timeit("bulk256 mean only", bm, [&] { k_bulk<256, false, true><<<grid(32), 64>>>(var, mu, B, T1); });
