@@ -149,7 +149,13 @@ struct TpxLayout {
   static constexpr bool kAsync = RODEO_TPX_ASYNC != 0;
   static constexpr int REC = p + PS;
   static constexpr size_t stage_off = (out_bytes + 15) / 16 * 16;
-  static constexpr size_t smem_bytes = stage_off + (kAsync ? (size_t)THREADS * U * 2 * REC * 8 : 0);
+  // Right-hand sides with more than three parameters (MSEIR: six) park theta in per-lane shared-memory slots and
+  // re-read it in the re-run step: held in registers it pushes the five-block instance over the 168-register cap
+  // (44 bytes of spills, solve_sim smoother 3.32 -> 3.61 ms with the U-form draw).
+  static constexpr int NTH = Fam::Ode::n_theta;
+  static constexpr bool kThetaSmem = CK > 1 && NTH > 3;
+  static constexpr size_t theta_off = stage_off + (kAsync ? (size_t)THREADS * U * 2 * REC * 8 : 0);
+  static constexpr size_t smem_bytes = theta_off + (kThetaSmem ? (size_t)THREADS * U * NTH * 8 : 0);
   static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
 };
 
@@ -189,7 +195,14 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < p; e++) x0b[u][e] = ld_once(a.x0 + bs[u] * n + blk * p + e);
 #pragma unroll
-    for (int e = 0; e < NT; e++) th[u][e] = (Ode::n_theta > 0 && CK > 1) ? ld_once(a.theta + bs[u] * Ode::n_theta + e) : 0.0;
+    for (int e = 0; e < NT; e++) {
+      th[u][e] = (Ode::n_theta > 0 && CK > 1) ? ld_once(a.theta + bs[u] * Ode::n_theta + e) : 0.0;
+      if constexpr (L::kThetaSmem)
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(smem_u32(smem_raw) + (uint32_t)L::theta_off +
+                                                     (uint32_t)(((u * NT + e) * L::THREADS + (int)threadIdx.x) * 8)),
+                     "d"(th[u][e])
+                     : "memory");
+    }
   }
   auto load_rec = [&](int u, int r, double *mu, double *S) {
     const double *h = hb[u] + (size_t)r * NE * kTile;
@@ -363,7 +376,19 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
           for (int e = 0; e < n; e++) X[e] = 0.0;
 #pragma unroll
           for (int k = 0; k < nb; k++) X[k * p] = __shfl_sync(kFull, fm[0], k * SPW + s);
-          Ode::template eval<n>(X, tt, th[u], y);
+          if constexpr (L::kThetaSmem) {   // this lane's own slots: no barrier needed
+            double thl[NT];
+#pragma unroll
+            for (int e = 0; e < NT; e++)
+              asm volatile("ld.shared.f64 %0, [%1];"
+                           : "=d"(thl[e])
+                           : "r"(smem_u32(smem_raw) + (uint32_t)L::theta_off +
+                                 (uint32_t)(((u * NT + e) * L::THREADS + (int)threadIdx.x) * 8))
+                           : "memory");
+            Ode::template eval<n>(X, tt, thl, y);
+          } else {
+            Ode::template eval<n>(X, tt, th[u], y);
+          }
           double ya = y[0];
 #pragma unroll
           for (int k = 1; k < nb; k++) ya = (blk == k) ? y[k] : ya;
