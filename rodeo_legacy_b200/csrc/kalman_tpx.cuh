@@ -1,20 +1,30 @@
 // kalman_tpx.cuh -- draw-only backward kernel (solve_sim) of the block-diagonal family with >= 3 blocks:
-// one THREAD PER DIAGONAL BLOCK, U systems per lane, checkpointed history.  Written for BASELINE config 3
-// (Lorenz63, 16,384 x0, n_eval 5000, solve_sim), the config furthest from its bytes in round 1:
+// one THREAD PER DIAGONAL BLOCK, checkpointed history.  Written for BASELINE config 3 (Lorenz63, 16,384 x0,
+// n_eval 5000, solve_sim), the config furthest from its bytes in round 1:
 //   * 16,384 systems x 3 blocks are 49,152 independent 5,000-step chains = 10.4 warps per SM: the step is bound by
-//     the LATENCY of one block step (two 3 x 3 Cholesky factorisations in sequence), not by throughput.  Each
-//     lane therefore runs the blocks of U = 2 different systems interleaved (independent instruction streams:
-//     the compiler overlaps their dependency chains), which halves the latency per system.
+//     the dependent FP64 chain of one block step (two 3 x 3 Cholesky factorisations in sequence: 6 x 67 cycles of
+//     rsqrt alone, tools/microbench/fp64_latency.cu), not by throughput or bandwidth (ncu: DRAM 40 %).  Everything
+//     else is therefore kept OFF that chain:
 //   * the warp-per-block kernel (kalman_bdw.cuh) needs the full history because re-running the filter means a
 //     CTA barrier per step; here the blocks of a system sit in one warp and exchange the m predicted values the
 //     right-hand side needs with shuffles, so checkpoint interval 2 works: half the history traffic
-//     (Lorenz63: 17.7 -> 8.9 GB written and read).
-//   * draws leave through a per-system FIFO in shared memory as whole 256-byte-aligned granules, one
-//     cp.async.bulk per granule issued by the lane of block 0 (72-byte runs: a granule every 3.6 steps per
-//     system, so the per-lane issue loop that was too slow for 288-byte variance runs is cheap here).
+//     (Lorenz63: 17.7 -> 8.9 GB written and read);
+//   * history: each lane copies its block's next checkpoint record into its own shared-memory slots with cp.async
+//     (LDGSTS) one group ahead and picks it up with cp.async.wait_group + LDS.  With register prefetches (plain
+//     loads a group ahead) the in-flight DRAM loads shared a scoreboard with the z loads of the current step: the
+//     DFMA that consumes z waited for the PREFETCH to land (ncu: 27 % of all stall samples on that one instruction,
+//     unchanged when the z loads were hoisted).  5.25 -> 4.79 ms, DRAM reads 17.9 -> 9.2 GB;
+//   * draws: every step the lanes park their block's p values in a per-warp shared-memory image [system][n]
+//     (double buffered: one warp barrier per step) and the warp writes it back with plain coalesced stores,
+//     consecutive lanes = consecutive doubles of a system's 8n-byte run.  The first version kept per-system FIFOs
+//     and issued one cp.async.bulk per completed 256-byte granule (what the HBM-bound headline smoother needs):
+//     1.2 G more instructions (serialised UBLKCP issue loops, proxy fences, wait_group), 5.74 vs 5.24 ms;
+//   * z[:, t-1] is loaded with volatile loads at the top of the step; right-hand sides with more than three
+//     parameters re-read theta from per-lane shared-memory slots (registers: the cap below).
 // Lane = blk * SPW + s, SPW = 32 / n_blocks systems per warp and slot; warp w owns systems
-// [w * SPW * U, (w + 1) * SPW * U), system of (slot u, lane s) = w * SPW * U + u * SPW + s.  History in the plain
-// (unpermuted) tile order.  Warps never synchronise with each other.
+// [w * SPW * U, (w + 1) * SPW * U), system of (slot u, lane s) = w * SPW * U + u * SPW + s (U = 1 is what is built:
+// two systems per lane for instruction-level parallelism measured 11.3 vs 5.3 ms, ptxas serialises the streams at
+// 234 registers).  History in the plain (unpermuted) tile order.  Warps never synchronise with each other.
 #pragma once
 #include <cstdint>
 
@@ -22,139 +32,24 @@
 
 namespace rodeo {
 
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem),
-               "r"(bytes)
-               : "memory");
-}
-
-// FIFO of one output stream (W doubles per system and step) of ONE system: the image of the not-yet-stored
-// bytes of its trajectory, addressed by global byte offset modulo the FIFO size.
-// EK = steps between emissions: the FIFO holds what an emission can leave pending plus EK runs.
-template <int W, int EK = 1>
-struct OutFifo {
-  static constexpr int RUN = W * 8;                                     // bytes per step
-  static constexpr int SLACK = kGranule - cgcd(RUN, kGranule);          // most bytes left pending after an emission
-  static constexpr int CB = (SLACK + EK * RUN + 15) / 16 * 16;          // FIFO bytes
-  static constexpr bool kEven = (W % 2 == 0);                           // every run boundary is 16-byte aligned
-  uint32_t base;   // shared-memory address of this system's FIFO (16-byte aligned)
-  int off;         // (global byte offset of the current run) mod CB
-  int pend;        // bytes at and above the current run that are in the FIFO but not yet stored
-  __device__ __forceinline__ void init(uint32_t smem_base, long g_top) {
-    base = smem_base;
-    off = (int)((g_top * RUN) % CB);   // g_top = global run index one past the trajectory's last run
-    pend = 0;
-  }
-  __device__ __forceinline__ void advance() {   // to the next (lower) run: once per time index, before put
-    off -= RUN;
-    if (off < 0) off += CB;
-    pend += RUN;
-  }
-  template <int CNT>
-  __device__ __forceinline__ void put_at(int e0, const double *v) const {   // doubles e0 .. e0+CNT-1 of the run
-    int o = off + 8 * e0;
-    if (o >= CB) o -= CB;
-    const int room = CB - o;
-#pragma unroll
-    for (int i = 0; i < CNT; i++) {
-      const int d = 8 * i >= room ? 8 * i - CB : 8 * i;
-      asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + (uint32_t)(o + d)), "d"(v[i]) : "memory");
-    }
-  }
-  // bytes [gs, gs + len) of the array (inside one granule) from FIFO offset so
-  __device__ __forceinline__ void copy_out(char *out, long gs, int so, int len) const {
-    if constexpr (!kEven) {   // run boundaries are only 8-byte aligned: ragged edges by plain stores
-      if (gs & 8) {
-        double v;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)so));
-        *reinterpret_cast<double *>(out + gs) = v;
-        gs += 8;
-        so += 8;
-        if (so >= CB) so -= CB;
-        len -= 8;
-      }
-      if (len & 8) {
-        int st = so + len - 8;
-        if (st >= CB) st -= CB;
-        double v;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)st));
-        *reinterpret_cast<double *>(out + gs + len - 8) = v;
-        len -= 8;
-      }
-      if (len <= 0) return;
-    }
-    const int l1 = len < CB - so ? len : CB - so;
-    bulk_s2g(out + gs, base + (uint32_t)so, (uint32_t)l1);
-    if (l1 < len) bulk_s2g(out + gs + l1, base, (uint32_t)(len - l1));
-  }
-  // After the current run (global run index g, time index t) is in the FIFO: store every granule it
-  // completed (everything at t = 0).  Called by ONE lane of the system; the caller commits the group.
-  __device__ __forceinline__ void emit(char *out, long g, int t) {
-    const long a = g * RUN;
-    const int d = (t == 0) ? 0 : (int)((kGranule - (a & (kGranule - 1))) & (kGranule - 1));   // up to the next boundary
-    if (pend > d) {
-      long gs = a + d;
-      int so = off + d;
-      if (so >= CB) so -= CB;
-      int len = pend - d;
-      while (len > 0) {
-        const int room = kGranule - (int)(gs & (kGranule - 1));
-        const int l = len < room ? len : room;
-        copy_out(out, gs, so, l);
-        gs += l;
-        so += l;
-        if (so >= CB) so -= CB;
-        len -= l;
-      }
-      pend = d;
-    }
-  }
-};
-
 template <class Fam, int CK, int U>
 struct TpxLayout {
   static constexpr int p = Fam::p, nb = Fam::nb, n = Fam::n, PS = Fam::PS;
   static constexpr int SPW = 32 / nb, LANES = SPW * nb;
-  // Draws are 8 n bytes per step (Lorenz63: 72): a granule completes every 256 / (8 n) steps per system.  The
-  // emission round (proxy fence, warp barriers, per-lane bulk-copy issue loop) runs every EK steps instead of
-  // every step: ncu showed it was ~40 % of the kernel's instructions at EK = 1.
-  static constexpr int EK = 4;
-  using Fifo = OutFifo<n, EK>;
-  // per-system stride: an odd number of 16-byte chunks (FIFO rows of different systems start in different banks)
-  static constexpr int SYS_BYTES = (Fifo::CB / 16) % 2 == 1 ? Fifo::CB : Fifo::CB + 16;
   static constexpr int WARPS = 2, THREADS = WARPS * 32;
   // U = 1: 12 resident warps per SM (<= 170 registers) hold a whole 16,384-system Lorenz63 batch (11.1 warps per
   // SM) in ONE wave; at the 190 registers ptxas would take, 10 fit and the launch needs two
   static constexpr int MINB = U == 1 ? 6 : 1;
-#ifndef RODEO_TPX_PLAIN
-#define RODEO_TPX_PLAIN 1
-#endif
-  // Output path.  kPlain: every step the lanes park their block's p draws in a per-warp shared-memory image
-  // [system][n] (double buffered: one warp barrier per step) and the warp writes it back with plain coalesced
-  // stores, consecutive lanes = consecutive doubles of a system's 8n-byte run.  The kernel is latency-bound, not
-  // HBM-bound (ncu: DRAM 41 %), and the per-system FIFOs + per-lane bulk copies of aligned granules cost more
-  // instructions (serialised UBLKCP issue loops, proxy fences, wait_group) than the partial sectors cost bandwidth.
-  static constexpr bool kPlain = RODEO_TPX_PLAIN != 0;
-  static constexpr int IMG = SPW * n;                       // doubles of one staging image
+  static constexpr int IMG = SPW * n;                       // doubles of one staging image of the draws
   static constexpr int NST = (IMG + 31) / 32;               // store instructions per step
-  static constexpr size_t out_bytes = kPlain ? (size_t)WARPS * U * 2 * IMG * 8 : (size_t)WARPS * U * SPW * SYS_BYTES;
-#ifndef RODEO_TPX_ASYNC
-#define RODEO_TPX_ASYNC 1
-#endif
-  // History prefetch.  kAsync: each lane copies its block's next checkpoint record (REC doubles) into its own
-  // shared-memory slots with cp.async (LDGSTS) one group ahead and picks it up with cp.async.wait_group + LDS.
-  // With register prefetches (plain loads a group ahead) the in-flight DRAM loads share a scoreboard with the
-  // z loads of the current step: the DFMA that consumes z waited for the PREFETCH to land (ncu: 27 % of all stall
-  // samples on that one instruction, unchanged when the z loads were hoisted to the top of the step).
-  static constexpr bool kAsync = RODEO_TPX_ASYNC != 0;
-  static constexpr int REC = p + PS;
-  static constexpr size_t stage_off = (out_bytes + 15) / 16 * 16;
-  // Right-hand sides with more than three parameters (MSEIR: six) park theta in per-lane shared-memory slots and
-  // re-read it in the re-run step: held in registers it pushes the five-block instance over the 168-register cap
-  // (44 bytes of spills, solve_sim smoother 3.32 -> 3.61 ms with the U-form draw).
+  static constexpr int REC = p + PS;                        // doubles of one block's history record
   static constexpr int NTH = Fam::Ode::n_theta;
+  // six parameters (MSEIR) in registers push the five-block instance over the 168-register cap (44 bytes of
+  // spills, solve_sim smoother 3.61 ms; from shared memory 3.14 ms)
   static constexpr bool kThetaSmem = CK > 1 && NTH > 3;
-  static constexpr size_t theta_off = stage_off + (kAsync ? (size_t)THREADS * U * 2 * REC * 8 : 0);
+  // dynamic shared memory: [draw images: WARPS x U x 2 x IMG][record slots: U x 2 stages x REC x THREADS][theta]
+  static constexpr size_t stage_off = ((size_t)WARPS * U * 2 * IMG * 8 + 15) / 16 * 16;
+  static constexpr size_t theta_off = stage_off + (size_t)THREADS * U * 2 * REC * 8;
   static constexpr size_t smem_bytes = theta_off + (kThetaSmem ? (size_t)THREADS * U * NTH * 8 : 0);
   static_assert(CK == 1 || CK == 2, "thread-per-block smoother: checkpoint interval 1 or 2");
 };
@@ -178,9 +73,8 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
   const long T1 = (long)N + 1;
   const BlockPrior<Fam, UNIFORM> bp(P, blk);
 
-  long b[U], bs[U], g[U];
+  long b[U], bs[U];
   bool valid[U];
-  typename L::Fifo fx[U];
   const double *hb[U], *zb[U];
   double th[U][NT], x0b[U][p];
 #pragma unroll
@@ -188,8 +82,6 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
     b[u] = b_first + u * SPW + s;
     valid[u] = lane_on && b[u] < a.B;
     bs[u] = b[u] < a.B ? b[u] : b_first;                   // a safe system for the loads of idle lanes
-    g[u] = (bs[u] + 1) * T1;
-    fx[u].init(smem_u32(smem_raw) + (uint32_t)(((warp * U + u) * SPW + s) * L::SYS_BYTES), g[u]);
     hb[u] = a.hist + hist_offset(bs[u], 0, R, NE);
     zb[u] = a.z + bs[u] * a.z_stride + blk * p;
 #pragma unroll
@@ -211,7 +103,7 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < PS; e++) S[e] = ld_stream(h + (n + blk * PS + e) * kTile);
   };
-  // (kAsync) cp.async prefetch of record r into stage r & 1 / pick-up from it; slot of element e: [u][stage][e][thread]
+  // cp.async prefetch of record r into stage r & 1 / pick-up from it; slot of element e: [u][stage][e][thread]
   const uint32_t stage_base = smem_u32(smem_raw) + (uint32_t)L::stage_off + (uint32_t)threadIdx.x * 8u;
   auto stage_addr = [&](int u, int st, int e) {
     return stage_base + (uint32_t)((((u * 2 + st) * L::REC + e) * L::THREADS) * 8);
@@ -234,7 +126,7 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < PS; e++) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(S[e]) : "r"(stage_addr(u, st, p + e)) : "memory");
   };
-  // (kPlain) staging images (shared-state addresses) and this lane's store offsets: double k * 32 + lane of an image =
+  // staging images of the draws (shared-state addresses) and this lane's store offsets: double k * 32 + lane of an image =
   // element el of system sy of the warp, stored at xw[(sy * T1 + t) * n + el]
   const uint32_t img_base = smem_u32(smem_raw) + (uint32_t)(warp * U) * 2u * L::IMG * 8u;
   const uint32_t img_wr = img_base + (uint32_t)(s * n + blk * p) * 8u, img_rd = img_base + (uint32_t)lane * 8u;
@@ -247,77 +139,49 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int k = 0; k < L::NST; k++) {
       const int idx = k * 32 + lane, sy = idx / n, el = idx - sy * n;
-      ov[u][k] = L::kPlain && idx < L::IMG && b_first + u * SPW + sy < a.B;
+      ov[u][k] = idx < L::IMG && b_first + u * SPW + sy < a.B;
       ooff[u][k] = (int)((u * SPW + sy) * T1 * n) + el;
     }
-  // park the draws of time index t in the FIFOs; every EK steps (and at t = 0) store the granules they completed
-  int since = 0;
-  bool reads_pending = false;
+  // park the draws of time index t in the image of this step's parity, one warp barrier, coalesced stores
+  // (double buffered: the reads of the other image precede this step's barrier)
   auto emit = [&](int t, double (*x)[p]) {
-    if constexpr (L::kPlain) {   // double buffered: the reads of the other image precede this step's barrier
 #pragma unroll
-      for (int u = 0; u < U; u++)
+    for (int u = 0; u < U; u++)
 #pragma unroll
-        for (int e = 0; e < p; e++)
-          if (lane_on)
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(img_wr + img_par + (uint32_t)((u * 2 * L::IMG + e) * 8)), "d"(x[u][e])
-                         : "memory");
-      __syncwarp();
-      const int tn = t * n;
+      for (int e = 0; e < p; e++)
+        if (lane_on)
+          asm volatile("st.shared.f64 [%0], %1;" ::"r"(img_wr + img_par + (uint32_t)((u * 2 * L::IMG + e) * 8)), "d"(x[u][e])
+                       : "memory");
+    __syncwarp();
+    const int tn = t * n;
 #pragma unroll
-      for (int u = 0; u < U; u++)
+    for (int u = 0; u < U; u++)
 #pragma unroll
-        for (int k = 0; k < L::NST; k++) {
-          double v;
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(img_rd + img_par + (uint32_t)((u * 2 * L::IMG + k * 32) * 8)) : "memory");
-          if (ov[u][k]) xw[ooff[u][k] + tn] = v;
-        }
-      img_par ^= (uint32_t)(L::IMG * 8);
-      return;
-    }
-    if (reads_pending) {   // the bulk copies of the last emission round have left the FIFOs
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      reads_pending = false;
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      g[u] -= 1;
-      fx[u].advance();
-      fx[u].template put_at<p>(blk * p, x[u]);
-    }
-    if (++since == L::EK || t == 0) {
-      since = 0;
-      fence_proxy_async();   // the rows (generic proxy) become visible to the bulk copies (async proxy) ...
-      __syncwarp();          // ... of every lane of a system, before the lane of block 0 issues the stores
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        if (valid[u] && blk == 0) fx[u].emit(reinterpret_cast<char *>(a.x_out), g[u], t);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      reads_pending = true;
-    }
+      for (int k = 0; k < L::NST; k++) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(img_rd + img_par + (uint32_t)((u * 2 * L::IMG + k * 32) * 8)) : "memory");
+        if (ov[u][k]) xw[ooff[u][k] + tn] = v;
+      }
+    img_par ^= (uint32_t)(L::IMG * 8);
   };
   // z[:, t-1], this block's rows.  Volatile loads: issued HERE, at the top of the step; left to the compiler they sink
   // to their use at the end of the step (x = m~ + L z) and their L2 latency lands on the chain -- ncu: 27 % of
-  // all stall samples on that one DFMA (profiles/r02_backward_tpx_plain_stores_ncu_summary.txt)
+  // all stall samples on that one DFMA
   auto z_at = [&](int u, int t, double *zt) {
 #pragma unroll
     for (int e = 0; e < p; e++) zt[e] = ld_once(zb[u] + (long)(t - 1) * n + e);
   };
 
-  double x[U][p], cm[U][p], cS[U][PS], nm[U][p], nS[U][PS], mus_unused[p], Ss_unused[PS];
+  double x[U][p], cm[U][p], cS[U][PS], mus_unused[p], Ss_unused[PS];
   int fail[U];
 #pragma unroll
   for (int u = 0; u < U; u++) fail[u] = 0;
 #pragma unroll
   for (int u = 0; u < U; u++) {
     load_rec(u, 0, cm[u], cS[u]);
-    if (R > 1) {
-      if constexpr (L::kAsync) prefetch_rec(u, 1);
-      else load_rec(u, 1, nm[u], nS[u]);
-    }
+    if (R > 1) prefetch_rec(u, 1);
   }
-  if constexpr (L::kAsync) asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
   for (int u = 0; u < U; u++) {   // terminal time index N = record 0
     double zt[p];
@@ -330,24 +194,13 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
   for (int t_hi = N; t_hi > 1;) {   // this group draws time indices t_hi-1 .. max(t_hi-CK, 1)
     const int base = t_hi - CK;
     if (base >= 1) {
-      if constexpr (L::kAsync) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");          // record r (copied a group ago) is in its stage
+      asm volatile("cp.async.wait_group 0;" ::: "memory");            // record r (copied a group ago) is in its stage
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          fetch_rec(u, r, cm[u], cS[u]);
-          if (r + 1 < R) prefetch_rec(u, r + 1);                      // one group ahead, into the other stage
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-#pragma unroll
-          for (int e = 0; e < p; e++) cm[u][e] = nm[u][e];
-#pragma unroll
-          for (int e = 0; e < PS; e++) cS[u][e] = nS[u][e];
-          if (r + 1 < R) load_rec(u, r + 1, nm[u], nS[u]);            // one group ahead
-        }
+      for (int u = 0; u < U; u++) {
+        fetch_rec(u, r, cm[u], cS[u]);
+        if (r + 1 < R) prefetch_rec(u, r + 1);                        // one group ahead, into the other stage
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     if (CK == 2) {
       const int t0 = base >= 1 ? base : 0;
@@ -419,7 +272,6 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
 #pragma unroll
     for (int e = 0; e < p; e++) x[u][e] = x0b[u][e];
   emit(0, x);
-  if constexpr (!L::kPlain) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int u = 0; u < U; u++)
     if (valid[u] && a.status && fail[u]) atomicCAS(a.status + b[u], 0, blk * p + fail[u]);
