@@ -193,6 +193,14 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
   int r = 1;
   for (int t_hi = N; t_hi > 1;) {   // this group draws time indices t_hi-1 .. max(t_hi-CK, 1)
     const int base = t_hi - CK;
+    // z of the group's FIRST time index is issued before the asynchronous copies of this group: loaded after them,
+    // its consumer waited for them (12 % of the stall samples; 4.31 -> 4.11 ms).  Hoisting the second index as
+    // well costs registers (spills at the 168 cap: 4.20 ms; with theta moved to shared memory instead: 4.25 ms).
+    double ztA[U][p];
+    if (CK == 2) {
+#pragma unroll
+      for (int u = 0; u < U; u++) z_at(u, (base >= 1 ? base : 0) + 1, ztA[u]);
+    }
     if (base >= 1) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");            // record r (copied a group ago) is in its stage
 #pragma unroll
@@ -220,8 +228,8 @@ kalman_backward_tpx(const __grid_constant__ typename Fam::PriorT P, const __grid
         const double tt = P.tmin + (P.tmax - P.tmin) * (t0 + 1) / P.n_eval;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          double fm[p], fS[PS], zt[p];
-          z_at(u, t, zt);
+          double fm[p], fS[PS];
+          const double *zt = ztA[u];
           reg::predict_mean<p, Fam::kUT>(bp.Q(), bp.c(), cm[u], fm);
           reg::predict_var<p, false, Fam::kUT>(bp.Q(), bp.R(), cS[u], fS, nullptr);
           double X[n], y[Fam::m];
