@@ -455,6 +455,10 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
   int r = 1;
   for (int t_hi = N; t_hi > 1;) {   // this group smooths time indices t_hi-1 .. max(t_hi-CK, 1)
     const int base = t_hi - CK;
+    // (draw-only variants) z of the group's first time index, t_hi - 1, is loaded BEFORE the group's asynchronous
+    // copies: loaded after them its consumer waits for them (kalman_tpx.cuh)
+    double ztA[p];
+    if constexpr (kAsyncK && CK > 1) z_at(t_hi - 1, ztA);
     if (base >= 1) {
       if constexpr (kAsyncK) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");   // record r (copied a group ago) is in its stage
@@ -506,7 +510,12 @@ kalman_backward_tpb(const __grid_constant__ typename Fam::PriorT P, const __grid
         if (jf < nfwd) {
           const int t = t0 + jf + 1;
           double zt[p];
-          z_at(t, zt);
+          if (kAsyncK && t == t_hi - 1) {
+#pragma unroll
+            for (int e = 0; e < p; e++) zt[e] = ztA[e];
+          } else {
+            z_at(t, zt);
+          }
           const int f = reg::smooth_step<p, 1, DO_MEAN, (DO_VAR != 0), DO_SIM, false, Fam::kUT>(
               bp.Q(), bp.c(), bp.R(), sm_[jf], sS_[jf], zt, mus, Ss, x);
           if (f && !fail) fail = f;
