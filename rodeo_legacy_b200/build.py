@@ -81,11 +81,12 @@ def build(force=False, verbose=False, ptxas_info=False):
 def build_microbench():
     """tools/microbench: write_pattern (no-compute kernel writing the smoother's output pattern: what the
     memory system sustains for 288-byte runs of 65,536 interleaved streams), fp64_peak (sustained DFMA
-    rate; MEASURED_PEAKS.json has no FP64 figure) and the write_pattern2 sensitivity experiment.  bench.py
-    runs the first two next to the kernels.  Returns the binaries' paths."""
+    rate; MEASURED_PEAKS.json has no FP64 figure), the write_pattern2 / write_pattern3 store-scheme experiments and
+    fp64_latency (dependent-issue latency of DFMA, 1/x, rsqrt).  bench.py runs the first two next to the kernels.
+    Returns the binaries' paths."""
     root = os.path.dirname(HERE)
     outs = []
-    for name in ("write_pattern", "fp64_peak", "write_pattern2"):
+    for name in ("write_pattern", "fp64_peak", "write_pattern2", "write_pattern3", "fp64_latency"):
         src = os.path.join(root, "tools", "microbench", name + ".cu")
         out = src[:-3]
         if _stale(out, [src]):
