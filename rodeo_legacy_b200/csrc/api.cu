@@ -302,8 +302,7 @@ static int var_width(const rodeo_problem *p) {
 // dense wide-state kernels (kalman_dw.cuh) serve the plain solves of the sets that carry them
 static bool wide_path(const rodeo_problem *p) {
   static const bool off = getenv("RODEO_CUDA_NO_WIDE") != nullptr;   // A/B against the rolled kernels
-  return !off && p->ks->wide_hist_elems > 0 && !p->shared && p->ig != RODEO_INTERROGATE_CHKREBTII &&
-         p->ks->wide_forward[p->ig] != nullptr;
+  return !off && p->ks->wide_hist_elems > 0 && !p->shared && p->ks->wide_forward[p->ig] != nullptr;
 }
 
 int rodeo_cuda_problem_info(const rodeo_problem *p, int32_t *blockdiag, int32_t *registers,

@@ -223,7 +223,20 @@ kalman_dw_forward(const __grid_constant__ typename Fam::PriorT P, const __grid_c
     dw_qcol<n>(Qu, Sf, T);
     dw_predict_cov<n, LD>(Qu, Rs, T, XA, j, act, Pc);
     const double tt = P.tmin + (P.tmax - P.tmin) * (t + 1) / N;
-    Ode::template eval<n>(mup, tt, th, y);
+    if (IG == IG_CHKREBTII) {   // x_state ~ N(mu_pred, Sigma_pred) with z[:, t]  (KalmanODE.pyx:13-49)
+      double V[n], vinv[n], xs[n];
+#pragma unroll
+      for (int i = 0; i < n; i++) V[i] = act ? Pc[i] : ((i == j) ? 1.0 : 0.0);   // identity columns in idle lanes
+      const int fc = dw_chol<n>(V, vinv, j);
+      if (fc && !fail) fail = fc;
+      // x = mu_p + L z: lane k contributes L[:, k] z[k]; the row sums are all-reduced, so every lane gets the vector
+      const double zk = act ? a.z[bs * a.z_stride + (long)t * n + j] : 0.0;
+#pragma unroll
+      for (int i = 0; i < n; i++) xs[i] = mup[i] + dw_sum((act && i >= j) ? V[i] * zk : 0.0);
+      Ode::template eval<n>(xs, tt, th, y);
+    } else {
+      Ode::template eval<n>(mup, tt, th, y);
+    }
     // A[:, j] = W P[:, j]
     double Ac[m];
 #pragma unroll

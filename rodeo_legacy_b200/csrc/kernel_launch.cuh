@@ -284,7 +284,7 @@ KernelSet make_kernel_set(const char *name) {
     k.pp_bd_backward[BK_SIM] = launch_backward_tpb_pp<Fam, 2, false, false, true>;
     k.pp_bd_backward[BK_BOTH] = launch_backward_tpb_pp<Fam, 2, true, true, true>;
   }
-  k.wide_forward[0] = k.wide_forward[1] = nullptr;
+  k.wide_forward[0] = k.wide_forward[1] = k.wide_forward[2] = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.wide_backward[b] = nullptr;
   k.wide_pp_forward = nullptr;
   for (int b = 0; b < BK_COUNT; b++) k.wide_pp_backward[b] = nullptr;

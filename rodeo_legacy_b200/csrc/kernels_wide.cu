@@ -15,6 +15,7 @@ static void attach(KernelSet *sets, int count) {
     if (!same) continue;
     k.wide_forward[IG_PROBDE] = launch_dw_forward<Fam, IG_PROBDE>;
     k.wide_forward[IG_SCHOBERT] = launch_dw_forward<Fam, IG_SCHOBERT>;
+    k.wide_forward[IG_CHKREBTII] = launch_dw_forward<Fam, IG_CHKREBTII>;
     k.wide_backward[BK_MV] = launch_dw_backward<Fam, true, true, false, false>;
     k.wide_backward[BK_SIM] = launch_dw_backward<Fam, false, false, true, false>;
     k.wide_backward[BK_BOTH] = launch_dw_backward<Fam, true, true, true, false>;

@@ -62,7 +62,7 @@ struct KernelSet {
   // dense wide-state kernels (kalman_dw.cuh: half a warp per system); nullptr / 0 when not compiled.
   // Used for every entry point under the probde and schobert interrogations; they keep
   // their own history layout (wide_hist_elems doubles per system per step, full history).
-  launch_fn wide_forward[2];
+  launch_fn wide_forward[3];           // by interrogation variant
   launch_fn wide_backward[BK_COUNT];
   launch_pp_fn wide_pp_forward;
   launch_pp_fn wide_pp_backward[BK_COUNT];

@@ -1232,3 +1232,22 @@ def test_into_variants_write_caller_buffers():
     for bad in (np.empty((1500, T, 6), dtype=np.float32), np.empty((1499, T, 6)), np.empty((1500, T, 12))[:, :, ::2]):
         with pytest.raises(TypeError):
             k.solve_sim_into(x0, theta, bad)
+
+
+@pytest.mark.parametrize("maker,B,mtol,vtol", [
+    (lambda B: wl.lorenz_batch(B, N=301, tmax=1.2), 37, 1e-9, 1e-7),
+    (lambda B: wl.mseir_batch(B, N=150), 21, 1e-9, 1e-7)])
+def test_chkrebtii_interrogation_on_the_wide_dense_kernels(maker, B, mtol, vtol):
+    """forecast (the chkrebtii interrogation, rodeo/cython/KalmanODE.pyx:13-49: the right-hand side is evaluated at a
+    draw from N(mu_pred, Sigma_pred) with z[:, t]) on the half-warp-per-system kernels for dense wide states
+    (kalman_dw.cuh; they used to hand this variant to the rolled kernels), against the oracle."""
+    w, x0, theta = maker(B)
+    n = len(w["x0"])
+    z = np.asfortranarray(np.random.default_rng(6).standard_normal((n, w["N"])))
+    k = wl.make_kode(w, z_state=z, interrogate="chkrebtii", force_dense=True)
+    assert k.kernel_family == ("dense", "wide")           # the wide kernels, not the rolled ones
+    ref = oracle.solve_batch(wl.make_oracle_problem(w, interrogate="chkrebtii"), x0, theta, z, oracle.MODE_MV)
+    mu, var = (a.cpu().numpy() for a in k.solve_mv(torch.from_numpy(x0).cuda(), theta=torch.from_numpy(theta).cuda()))
+    assert np.isfinite(mu).all() and int(np.count_nonzero(k.status.cpu().numpy())) == 0
+    assert traj_err(mu, ref["mu"]).max() < mtol
+    assert var_err(var[:, 1:], ref["var"][:, 1:]).max() < vtol
